@@ -1,0 +1,107 @@
+/*
+ * mmhermite.h — C ABI of libmmhermite.so, the B200 (sm_100a) Gaussian-to-Fock engine.
+ *
+ * The reference (XanaduAI/MrMustard) has no FFI: its plug-in interface for this path is the backend
+ * method table looked up by name in BackendManager._apply (mrmustard/math/backend_manager.py:89-116)
+ * plus the `strategies.*` functions the backends call.  Every entry point below replaces one of those
+ * Python-level functions; the citation after "replaces:" is the reference file:line whose semantics
+ * (argument meaning, layout, in-place `out` contract, error classes) the entry point reproduces.
+ * The Python binding a maintainer adds on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - all tensors are C-contiguous complex128, passed as `const void*` / `void*` to interleaved
+ *     (re, im) doubles; index arithmetic is int64; `shape` has `ndim` entries, every entry >= 1.
+ *   - `*_host` entry points take HOST pointers and perform the H2D/D2H copies themselves (numpy
+ *     drop-in).  The others take DEVICE pointers valid on the current CUDA device and enqueue work on
+ *     `stream` (a cudaStream_t passed as void*; NULL = the legacy default stream) without synchronising.
+ *   - return value: 0 = OK; negative = invalid-argument class (the Python shim re-raises the
+ *     reference's exception type, see mmh_error_string); positive = cudaError_t of the failing call.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns an error.
+ */
+#ifndef MMHERMITE_H
+#define MMHERMITE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMH_OK 0
+#define MMH_ERR_BAD_NDIM (-1)      /* ndim < 1 or > MMH_MAX_DIM                                  -> ValueError */
+#define MMH_ERR_BAD_SHAPE (-2)     /* an entry of shape < 1, or a cutoff beyond the sqrt table   -> ValueError */
+#define MMH_ERR_NULL_POINTER (-3)  /* a required pointer is NULL                                 -> ValueError */
+#define MMH_ERR_BAD_BATCH (-4)     /* batch < 0                                                  -> ValueError */
+#define MMH_ERR_UNSUPPORTED (-5)   /* combination not implemented by the CUDA path               -> NotImplementedError */
+#define MMH_ERR_NO_DEVICE (-6)     /* no CUDA device / wrong architecture                        -> RuntimeError */
+#define MMH_ERR_TOO_LARGE (-7)     /* lattice does not fit the index type / device memory        -> MemoryError */
+
+#define MMH_MAX_DIM 32
+
+/* library / device management ------------------------------------------------------------------ */
+int mmh_version(void);
+const char *mmh_error_string(int status);
+int mmh_device_count(int *count_out);
+int mmh_set_device(int device);            /* cudaSetDevice for the calling thread */
+int mmh_device_synchronize(void);
+/* number of kernel launches enqueued by this library since load (for bench.py's gpu_launches) */
+int64_t mmh_launch_count(void);
+
+/* pinned host memory for the numpy drop-in (results are handed to numpy without a pageable bounce) */
+int mmh_host_alloc(void **ptr_out, int64_t bytes);
+int mmh_host_free(void *ptr);
+
+/* forward: Bargmann triple -> Fock lattice -------------------------------------------------------
+ * replaces: strategies.vanilla_numba (stable=0) / strategies.stable_numba (stable=1)
+ *           mrmustard/math/lattice/strategies/vanilla/core.py:25-124 and :127-213,
+ *           reached through BackendNumpy.hermite_renormalized (math/backend_numpy.py:381-392).
+ * A[ndim,ndim], b[ndim], c[1] -> G[prod(shape)].  Every element of G is overwritten (the reference's
+ * `out` contract, core.py:73).  Pivot rule, term order and per-element IEEE arithmetic are those of the
+ * reference, so the result is bit-identical to it (tests/test_gpu_forward.py).                      */
+int mmh_forward(int ndim, const int64_t *shape, const void *dA, const void *db, const void *dc,
+                void *dG, int stable, void *stream);
+int mmh_forward_host(int ndim, const int64_t *shape, const void *A, const void *b, const void *c,
+                     void *G, int stable);
+
+/* replaces: strategies.vanilla_batch_numba  (vanilla/batch.py:27-61), reached through
+ *           BackendNumpy.hermite_renormalized_batched (math/backend_numpy.py:394-403).
+ * A[batch,ndim,ndim], b[batch,ndim], c[batch] -> G[batch,prod(shape)] (batch on the first axis).    */
+int mmh_forward_batched(int64_t batch, int ndim, const int64_t *shape, const void *dA, const void *db,
+                        const void *dc, void *dG, int stable, void *stream);
+int mmh_forward_batched_host(int64_t batch, int ndim, const int64_t *shape, const void *A,
+                             const void *b, const void *c, void *G, int stable);
+
+/* vector-Jacobian product ------------------------------------------------------------------------
+ * replaces: strategies.vanilla_vjp_numba (vanilla/gradients.py:25-82), called from the jax backend's
+ *           custom_vjp bwd (math/jax_vjps/hermite.py:86-102).
+ * G[prod(shape)], c[1], dLdG[prod(shape)] -> dLdA[ndim,ndim] (symmetrised), dLdb[ndim], dLdc[1].
+ * Holomorphic cotangent convention (no conjugation), as in the reference.                           */
+int mmh_vjp(int ndim, const int64_t *shape, const void *dG, const void *dc, const void *ddLdG,
+            void *dLdA_out, void *dLdb_out, void *dLdc_out, void *stream);
+int mmh_vjp_host(int ndim, const int64_t *shape, const void *G, const void *c, const void *dLdG,
+                 void *dLdA_out, void *dLdb_out, void *dLdc_out);
+
+/* replaces: strategies.vanilla_batch_vjp_numba (vanilla/gradients.py:85-116;
+ *           math/jax_vjps/hermite.py:146-175).  Per-triple gradients, no reduction across the batch:
+ * G[batch,N], c[batch], dLdG[batch,N] -> dLdA[batch,ndim,ndim], dLdb[batch,ndim], dLdc[batch].      */
+int mmh_vjp_batched(int64_t batch, int ndim, const int64_t *shape, const void *dG, const void *dc,
+                    const void *ddLdG, void *dLdA_out, void *dLdb_out, void *dLdc_out, void *stream);
+int mmh_vjp_batched_host(int64_t batch, int ndim, const int64_t *shape, const void *G, const void *c,
+                         const void *dLdG, void *dLdA_out, void *dLdb_out, void *dLdc_out);
+
+/* binomial (fill by total photon number with early stop) -------------------------------------------
+ * replaces: strategies.binomial (strategies/binomial.py:30-72) with steps.binomial_step
+ *           (lattice/steps.py:208-235) and paths.binomial_subspace_basis (lattice/paths.py:24-72),
+ *           reached through BackendNumpy.hermite_renormalized_binomial (math/backend_numpy.py:405-421).
+ * Levels |k| = 1 .. global_cutoff-1 are filled in order; after each level norm += sum |G_k|^2 and the
+ * fill stops once norm > max_l2.  Untouched entries of G are zero.  norm_out (HOST pointer) receives
+ * the accumulated norm; the call synchronises `stream` before returning.                            */
+int mmh_binomial(int ndim, const int64_t *shape, const void *dA, const void *db, const void *dc,
+                 double max_l2, int64_t global_cutoff, void *dG, double *norm_out, void *stream);
+int mmh_binomial_host(int ndim, const int64_t *shape, const void *A, const void *b, const void *c,
+                      double max_l2, int64_t global_cutoff, void *G, double *norm_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMHERMITE_H */

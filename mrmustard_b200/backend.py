@@ -1,0 +1,88 @@
+"""Operator-level mirror of the reference's `math.hermite_renormalized*` entry points.
+
+`hermite_renormalized` reproduces BackendManager.hermite_renormalized's batching semantics
+(mrmustard/math/backend_manager.py:643-727: fully batched / b-batched / unbatched, batch flatten and
+reshape, `stable or settings.STABLE_FOCK_CONVERSION`, the out-shape check and its ValueError);
+`hermite_renormalized_batched` and `hermite_renormalized_binomial` reproduce the BackendNumpy methods
+(mrmustard/math/backend_numpy.py:394-421).  Everything computes on the GPU through `strategies`.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import strategies
+
+
+class _Settings:
+    """The two reference settings that reach this path (mrmustard/utils/settings.py:67-74,101)."""
+    STABLE_FOCK_CONVERSION = False
+    AUTOSHAPE_PROBABILITY = 0.99999
+
+
+settings = _Settings()
+
+
+def _reference_settings():
+    """Use the live mrmustard settings object when the drop-in is installed, else ours."""
+    import sys
+    mm = sys.modules.get("mrmustard")
+    return getattr(mm, "settings", settings) if mm is not None else settings
+
+
+def hermite_renormalized_unbatched(A, b, c, shape, stable=False, out=None):
+    """BackendNumpy.hermite_renormalized (backend_numpy.py:381-392)."""
+    if stable:
+        return strategies.stable_numba(tuple(shape), A, b, c, out)
+    return strategies.vanilla_numba(tuple(shape), A, b, c, out)
+
+
+def hermite_renormalized_batched(A, b, c, shape, stable=False, out=None):
+    """BackendNumpy.hermite_renormalized_batched (backend_numpy.py:394-403)."""
+    return strategies.vanilla_batch_numba(tuple(shape), A, b, c, stable, out)
+
+
+def hermite_renormalized_binomial(A, B, C, shape, max_l2=None, global_cutoff=None):
+    """BackendNumpy.hermite_renormalized_binomial (backend_numpy.py:405-421)."""
+    shape = tuple(shape)
+    s = _reference_settings()
+    return strategies.binomial(
+        shape, A, B, C,
+        max_l2=max_l2 or s.AUTOSHAPE_PROBABILITY,
+        global_cutoff=global_cutoff or sum(shape) - len(shape) + 1,
+    )[0]
+
+
+def hermite_renormalized(A, b, c, shape, stable=False, out=None):
+    """BackendManager.hermite_renormalized (backend_manager.py:643-727)."""
+    A = np.asarray(A)
+    b = np.asarray(b)
+    c = np.asarray(c)
+    shape = tuple(shape)
+
+    def check_out_shape(batch_shape):
+        if out is not None and any(d_out < d for d_out, d in zip(out.shape, batch_shape + shape)):
+            raise ValueError(f"batch+shape {batch_shape + shape} is too large for out.shape={out.shape}")
+
+    stable = stable or _reference_settings().STABLE_FOCK_CONVERSION
+    if A.ndim > 2 and b.ndim > 1 and c.ndim > 0:
+        batch_shape = A.shape[:-2]
+        check_out_shape(batch_shape)
+        if b.shape[:-1] != batch_shape:
+            raise ValueError(f"b.shape={b.shape} must match batch_shape={batch_shape}")
+        if c.shape[: len(batch_shape)] != batch_shape:
+            raise ValueError(f"c.shape={c.shape} must match batch_shape={batch_shape}")
+        B = int(np.prod(batch_shape))
+        result = hermite_renormalized_batched(
+            A.reshape(B, *A.shape[-2:]), b.reshape(B, b.shape[-1]), c.reshape(B), shape, stable,
+            out.reshape(B, *shape) if out is not None else None)
+        return result.reshape(batch_shape + shape)
+    if A.ndim == 2 and b.ndim > 1:  # b-batched
+        batch_shape = b.shape[:-1]
+        check_out_shape(batch_shape)
+        B = int(np.prod(batch_shape))
+        result = hermite_renormalized_batched(
+            np.broadcast_to(A, (B, *A.shape)), b.reshape(B, b.shape[-1]), np.broadcast_to(c, (B,)), shape, stable,
+            out.reshape(B, *shape) if out is not None else None)
+        return result.reshape(batch_shape + shape)
+    check_out_shape(())
+    return hermite_renormalized_unbatched(A, b, c, shape, stable, out)

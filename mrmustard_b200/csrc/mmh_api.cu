@@ -1,0 +1,404 @@
+// mmh_api.cu — C ABI (include/mmhermite.h) over the sm_100a kernels: argument validation, per-device
+// context (sqrt tables, workspace, grid-barrier counters), kernel selection, and the host-pointer
+// variants that stage through device scratch.  No CPU compute path exists in this library.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "mmh_params.cuh"
+
+
+#define CK(call)                                   \
+    do {                                           \
+        cudaError_t e_ = (call);                   \
+        if (e_ != cudaSuccess) return (int)e_;     \
+    } while (0)
+
+static std::atomic<long long> g_launches{0};
+static std::mutex g_mutex;
+
+// ---- per-device context ---------------------------------------------------------------------------
+struct Scratch {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+struct DeviceCtx {
+    bool init = false;
+    int sm_count = 0;
+    int cc_major = 0;
+    double *sq = nullptr, *rsq = nullptr;
+    int table_len = 0;
+    unsigned *barrier = nullptr;  // 64 counters; one is consumed per cooperative launch (round robin)
+    int barrier_next = 0;
+    Scratch partial;              // VJP partial sums
+    Scratch norm;                 // binomial norm scalar
+    Scratch host_slots[8];        // staging for the *_host entry points
+};
+static DeviceCtx g_ctx[64];
+
+static int ensure_scratch(Scratch &s, size_t bytes) {
+    if (s.bytes >= bytes && s.ptr) return 0;
+    if (s.ptr) { CK(cudaDeviceSynchronize()); CK(cudaFree(s.ptr)); s.ptr = nullptr; s.bytes = 0; }
+    size_t want = bytes < 256 ? 256 : bytes;
+    CK(cudaMalloc(&s.ptr, want));
+    s.bytes = want;
+    return 0;
+}
+
+static int ensure_tables(DeviceCtx &c, int need) {
+    if (need <= c.table_len) return 0;
+    int len = 4096;
+    while (len < need) len *= 2;
+    std::vector<double> hs(len), hr(len);
+    for (int n = 0; n < len; n++) {
+        hs[n] = std::sqrt((double)n);               // SQRT = np.sqrt(np.arange(...)) (core.py:22)
+        hr[n] = n ? 1.0 / hs[n] : 0.0;              // correctly rounded reciprocal for div_by_table
+    }
+    if (c.sq) { CK(cudaDeviceSynchronize()); CK(cudaFree(c.sq)); CK(cudaFree(c.rsq)); c.sq = c.rsq = nullptr; c.table_len = 0; }
+    CK(cudaMalloc(&c.sq, sizeof(double) * len));
+    CK(cudaMalloc(&c.rsq, sizeof(double) * len));
+    CK(cudaMemcpy(c.sq, hs.data(), sizeof(double) * len, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c.rsq, hr.data(), sizeof(double) * len, cudaMemcpyHostToDevice));
+    c.table_len = len;
+    return 0;
+}
+
+static int get_ctx(DeviceCtx **out) {
+    int dev = 0, ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1) { cudaGetLastError(); return MMH_ERR_NO_DEVICE; }
+    e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { cudaGetLastError(); return MMH_ERR_NO_DEVICE; }
+    if (dev < 0 || dev >= 64) return MMH_ERR_NO_DEVICE;
+    DeviceCtx &c = g_ctx[dev];
+    if (!c.init) {
+        cudaDeviceProp prop;
+        e = cudaGetDeviceProperties(&prop, dev);
+        if (e != cudaSuccess) { cudaGetLastError(); return MMH_ERR_NO_DEVICE; }
+        if (prop.major != 10) return MMH_ERR_NO_DEVICE;  // sm_100a cubin only
+        c.sm_count = prop.multiProcessorCount;
+        c.cc_major = prop.major;
+        CK(cudaMalloc(&c.barrier, 64 * sizeof(unsigned)));
+        CK(cudaMemset(c.barrier, 0, 64 * sizeof(unsigned)));
+        c.init = true;
+    }
+    *out = &c;
+    return 0;
+}
+
+static int make_desc(int ndim, const int64_t *shape, LatticeDesc *d, int *maxdim) {
+    if (ndim < 1 || ndim > MMH_MAX_DIM) return MMH_ERR_BAD_NDIM;
+    if (!shape) return MMH_ERR_NULL_POINTER;
+    memset(d, 0, sizeof(*d));
+    d->D = ndim;
+    long long N = 1;
+    int mx = 1;
+    for (int i = 0; i < ndim; i++) {
+        if (shape[i] < 1 || shape[i] > (1 << 24)) return MMH_ERR_BAD_SHAPE;
+        d->shape[i] = (int)shape[i];
+        if (shape[i] > mx) mx = (int)shape[i];
+        if (N > (1LL << 40) / shape[i]) return MMH_ERR_TOO_LARGE;
+        N *= shape[i];
+    }
+    d->N = N;
+    d->strides[ndim - 1] = 1;
+    for (int i = ndim - 1; i > 0; i--) d->strides[i - 1] = d->strides[i] * d->shape[i];
+    *maxdim = mx;
+    return 0;
+}
+
+static inline int round_up32(long long v) { return (int)((v + 31) / 32 * 32); }
+
+// ---- forward --------------------------------------------------------------------------------------
+static const long long kSmallPanel = 1024;     // panels up to this size are filled by one CTA
+static const long long kSingleCtaN = 16384;    // lattices up to this size use the one-CTA kernel
+
+static int forward_impl(long long batch, int ndim, const int64_t *shape, const void *dA, const void *db,
+                        const void *dc, void *dG, int stable, cudaStream_t st) {
+    if (batch < 0) return MMH_ERR_BAD_BATCH;
+    LatticeDesc d;
+    int mx;
+    int rc = make_desc(ndim, shape, &d, &mx);
+    if (rc) return rc;
+    if (batch == 0) return MMH_OK;
+    if (!dA || !db || !dc || !dG) return MMH_ERR_NULL_POINTER;
+    DeviceCtx *ctx;
+    if ((rc = get_ctx(&ctx))) return rc;
+    if ((rc = ensure_tables(*ctx, mx + 1))) return rc;
+
+    FwdParams p;
+    p.d = d;
+    p.A = (const c128 *)dA; p.b = (const c128 *)db; p.c = (const c128 *)dc; p.G = (c128 *)dG;
+    p.sq = ctx->sq; p.rsq = ctx->rsq;
+    p.batch = batch; p.barrier = nullptr; p.small_stage_lo = 0;
+    const size_t smem = sizeof(c128) * (size_t)(ndim * ndim + ndim);
+
+    const bool per_cta = d.N <= kSingleCtaN || batch >= 2LL * ctx->sm_count;
+    if (per_cta) {
+        long long maxpanel = stable ? d.N / d.shape[ndim - 1] : d.strides[0];
+        int block = round_up32(maxpanel);
+        if (block < 32) block = 32;
+        if (block > 256) block = 256;
+        long long grid = batch;
+        if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
+        g_launches++;
+        CK(mmh_launch_fwd_cta(p, stable != 0, (int)grid, block, smem, st));
+        return MMH_OK;
+    }
+    // large lattices: one cooperative launch per lattice, every SM on the same lattice
+    const int block = 256;
+    int per_sm = 0;
+    CK(mmh_coop_max_blocks(stable != 0, block, smem, &per_sm));
+    if (per_sm < 1) return MMH_ERR_UNSUPPORTED;
+    if (per_sm > 2) per_sm = 2;
+    const int grid = ctx->sm_count * per_sm;
+    int lo = ndim;  // stages >= lo are filled by CTA 0 alone
+    while (lo > 0 && d.strides[lo - 1] <= kSmallPanel) lo--;
+    if (lo == 0) lo = 1;  // keep at least one grid-wide stage so that every CTA has work
+    for (long long l = 0; l < batch; l++) {
+        FwdParams q = p;
+        q.A = p.A + l * ndim * ndim; q.b = p.b + l * ndim; q.c = p.c + l; q.G = p.G + l * d.N;
+        q.batch = 1;
+        q.small_stage_lo = lo;
+        q.barrier = ctx->barrier + ctx->barrier_next;
+        ctx->barrier_next = (ctx->barrier_next + 1) % 64;
+        CK(cudaMemsetAsync(q.barrier, 0, sizeof(unsigned), st));
+        g_launches++;
+        CK(mmh_launch_fwd_coop(q, stable != 0, grid, block, smem, st));
+    }
+    return MMH_OK;
+}
+
+// ---- vjp ------------------------------------------------------------------------------------------
+static int vjp_impl(long long batch, int ndim, const int64_t *shape, const void *dG, const void *dc,
+                    const void *dg, void *oA, void *ob, void *oc, cudaStream_t st) {
+    if (batch < 0) return MMH_ERR_BAD_BATCH;
+    LatticeDesc d;
+    int mx;
+    int rc = make_desc(ndim, shape, &d, &mx);
+    if (rc) return rc;
+    if (batch == 0) return MMH_OK;
+    if (!dG || !dc || !dg || !oA || !ob || !oc) return MMH_ERR_NULL_POINTER;
+    DeviceCtx *ctx;
+    if ((rc = get_ctx(&ctx))) return rc;
+    if ((rc = ensure_tables(*ctx, mx + 1))) return rc;
+    VjpParams p;
+    p.d = d;
+    p.G = (const c128 *)dG; p.g = (const c128 *)dg; p.c = (const c128 *)dc;
+    p.dA = (c128 *)oA; p.db = (c128 *)ob; p.dc = (c128 *)oc;
+    p.sq = ctx->sq;
+    p.batch = batch;
+    p.nacc = ndim + ndim * (ndim + 1) / 2 + 1;
+    const int block = 256;
+    long long want = (d.N + block * 4 - 1) / (block * 4);   // ~4 points per thread
+    long long cap = (8LL * ctx->sm_count + batch - 1) / batch; // ~8 CTAs per SM over the whole batch
+    if (cap < 1) cap = 1;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    if (want > 65535) want = 65535;
+    p.nblk = (int)want;
+    if ((rc = ensure_scratch(ctx->partial, sizeof(c128) * (size_t)batch * p.nblk * p.nacc))) return rc;
+    p.partial = (c128 *)ctx->partial.ptr;
+    g_launches += 2;
+    CK(mmh_launch_vjp(p, p.nblk, block, st));
+    return MMH_OK;
+}
+
+// ---- binomial -------------------------------------------------------------------------------------
+static int binomial_impl(int ndim, const int64_t *shape, const void *dA, const void *db, const void *dc,
+                         double max_l2, long long global_cutoff, void *dG, double *norm_out, cudaStream_t st) {
+    LatticeDesc d;
+    int mx;
+    int rc = make_desc(ndim, shape, &d, &mx);
+    if (rc) return rc;
+    if (!dA || !db || !dc || !dG) return MMH_ERR_NULL_POINTER;
+    DeviceCtx *ctx;
+    if ((rc = get_ctx(&ctx))) return rc;
+    if ((rc = ensure_tables(*ctx, mx + 1))) return rc;
+    if ((rc = ensure_scratch(ctx->norm, sizeof(double)))) return rc;
+    long long maxlevel = 0;
+    for (int i = 0; i < ndim; i++) maxlevel += d.shape[i] - 1;
+    BinomParams p;
+    p.d = d;
+    p.A = (const c128 *)dA; p.b = (const c128 *)db; p.c = (const c128 *)dc; p.G = (c128 *)dG;
+    p.sq = ctx->sq; p.rsq = ctx->rsq;
+    p.max_l2 = max_l2;
+    p.global_cutoff = global_cutoff < maxlevel + 1 ? global_cutoff : maxlevel + 1;  // empty levels add 0
+    p.norm_out = (double *)ctx->norm.ptr;
+    CK(cudaMemsetAsync(dG, 0, sizeof(c128) * (size_t)d.N, st));  // np.zeros (binomial.py:51)
+    long long Q = d.N / d.shape[ndim - 1];
+    int block = round_up32(Q);
+    if (block < 32) block = 32;
+    if (block > 1024) block = 1024;
+    const size_t smem = sizeof(c128) * (size_t)(ndim * ndim + ndim) + sizeof(double) * 40;
+    g_launches++;
+    CK(mmh_launch_binomial(p, block, smem, st));
+    double norm = 0.0;
+    CK(cudaMemcpyAsync(&norm, p.norm_out, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (norm_out) *norm_out = norm;
+    return MMH_OK;
+}
+
+// ---- host staging ---------------------------------------------------------------------------------
+static int stage_in(DeviceCtx &c, int slot, const void *host, size_t bytes, void **dev) {
+    int rc = ensure_scratch(c.host_slots[slot], bytes);
+    if (rc) return rc;
+    *dev = c.host_slots[slot].ptr;
+    if (host && bytes) CK(cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, 0));
+    return 0;
+}
+
+extern "C" {
+
+int mmh_version(void) { return 100; }
+
+const char *mmh_error_string(int status) {
+    switch (status) {
+        case MMH_OK: return "ok";
+        case MMH_ERR_BAD_NDIM: return "ndim must be in [1, 32]";
+        case MMH_ERR_BAD_SHAPE: return "every entry of shape must be >= 1 (and < 2^24)";
+        case MMH_ERR_NULL_POINTER: return "required pointer is NULL";
+        case MMH_ERR_BAD_BATCH: return "batch must be >= 0";
+        case MMH_ERR_UNSUPPORTED: return "not supported by the CUDA path";
+        case MMH_ERR_NO_DEVICE: return "no usable CUDA device (an sm_100 GPU is required; there is no CPU fallback)";
+        case MMH_ERR_TOO_LARGE: return "lattice too large";
+        default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "unknown error";
+    }
+}
+
+int mmh_device_count(int *count_out) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    if (count_out) *count_out = n;
+    return MMH_OK;
+}
+
+int mmh_set_device(int device) { CK(cudaSetDevice(device)); return MMH_OK; }
+int mmh_device_synchronize(void) { CK(cudaDeviceSynchronize()); return MMH_OK; }
+int64_t mmh_launch_count(void) { return g_launches.load(); }
+
+int mmh_host_alloc(void **ptr_out, int64_t bytes) {
+    if (!ptr_out) return MMH_ERR_NULL_POINTER;
+    CK(cudaHostAlloc(ptr_out, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault));
+    return MMH_OK;
+}
+int mmh_host_free(void *ptr) { if (ptr) CK(cudaFreeHost(ptr)); return MMH_OK; }
+
+int mmh_forward(int ndim, const int64_t *shape, const void *dA, const void *db, const void *dc, void *dG,
+                int stable, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return forward_impl(1, ndim, shape, dA, db, dc, dG, stable, (cudaStream_t)stream);
+}
+
+int mmh_forward_batched(int64_t batch, int ndim, const int64_t *shape, const void *dA, const void *db,
+                        const void *dc, void *dG, int stable, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return forward_impl(batch, ndim, shape, dA, db, dc, dG, stable, (cudaStream_t)stream);
+}
+
+int mmh_forward_batched_host(int64_t batch, int ndim, const int64_t *shape, const void *A, const void *b,
+                             const void *c, void *G, int stable) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (batch < 0) return MMH_ERR_BAD_BATCH;
+    LatticeDesc d; int mx;
+    int rc = make_desc(ndim, shape, &d, &mx);
+    if (rc) return rc;
+    if (batch == 0) return MMH_OK;
+    if (!A || !b || !c || !G) return MMH_ERR_NULL_POINTER;
+    DeviceCtx *ctx;
+    if ((rc = get_ctx(&ctx))) return rc;
+    void *dA, *db, *dc, *dG;
+    const size_t D = ndim;
+    if ((rc = stage_in(*ctx, 0, A, sizeof(c128) * batch * D * D, &dA))) return rc;
+    if ((rc = stage_in(*ctx, 1, b, sizeof(c128) * batch * D, &db))) return rc;
+    if ((rc = stage_in(*ctx, 2, c, sizeof(c128) * batch, &dc))) return rc;
+    if ((rc = stage_in(*ctx, 3, nullptr, sizeof(c128) * batch * (size_t)d.N, &dG))) return rc;
+    if ((rc = forward_impl(batch, ndim, shape, dA, db, dc, dG, stable, 0))) return rc;
+    CK(cudaMemcpyAsync(G, dG, sizeof(c128) * batch * (size_t)d.N, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    return MMH_OK;
+}
+
+int mmh_forward_host(int ndim, const int64_t *shape, const void *A, const void *b, const void *c, void *G,
+                     int stable) {
+    return mmh_forward_batched_host(1, ndim, shape, A, b, c, G, stable);
+}
+
+int mmh_vjp(int ndim, const int64_t *shape, const void *dG, const void *dc, const void *ddLdG, void *oA,
+            void *ob, void *oc, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return vjp_impl(1, ndim, shape, dG, dc, ddLdG, oA, ob, oc, (cudaStream_t)stream);
+}
+
+int mmh_vjp_batched(int64_t batch, int ndim, const int64_t *shape, const void *dG, const void *dc,
+                    const void *ddLdG, void *oA, void *ob, void *oc, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return vjp_impl(batch, ndim, shape, dG, dc, ddLdG, oA, ob, oc, (cudaStream_t)stream);
+}
+
+int mmh_vjp_batched_host(int64_t batch, int ndim, const int64_t *shape, const void *G, const void *c,
+                         const void *dLdG, void *oA, void *ob, void *oc) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (batch < 0) return MMH_ERR_BAD_BATCH;
+    LatticeDesc d; int mx;
+    int rc = make_desc(ndim, shape, &d, &mx);
+    if (rc) return rc;
+    if (batch == 0) return MMH_OK;
+    if (!G || !c || !dLdG || !oA || !ob || !oc) return MMH_ERR_NULL_POINTER;
+    DeviceCtx *ctx;
+    if ((rc = get_ctx(&ctx))) return rc;
+    const size_t D = ndim;
+    void *dG, *dg, *dc, *dAo, *dbo, *dco;
+    if ((rc = stage_in(*ctx, 0, G, sizeof(c128) * batch * (size_t)d.N, &dG))) return rc;
+    if ((rc = stage_in(*ctx, 1, dLdG, sizeof(c128) * batch * (size_t)d.N, &dg))) return rc;
+    if ((rc = stage_in(*ctx, 2, c, sizeof(c128) * batch, &dc))) return rc;
+    if ((rc = stage_in(*ctx, 4, nullptr, sizeof(c128) * batch * D * D, &dAo))) return rc;
+    if ((rc = stage_in(*ctx, 5, nullptr, sizeof(c128) * batch * D, &dbo))) return rc;
+    if ((rc = stage_in(*ctx, 6, nullptr, sizeof(c128) * batch, &dco))) return rc;
+    if ((rc = vjp_impl(batch, ndim, shape, dG, dc, dg, dAo, dbo, dco, 0))) return rc;
+    CK(cudaMemcpyAsync(oA, dAo, sizeof(c128) * batch * D * D, cudaMemcpyDeviceToHost, 0));
+    CK(cudaMemcpyAsync(ob, dbo, sizeof(c128) * batch * D, cudaMemcpyDeviceToHost, 0));
+    CK(cudaMemcpyAsync(oc, dco, sizeof(c128) * batch, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    return MMH_OK;
+}
+
+int mmh_vjp_host(int ndim, const int64_t *shape, const void *G, const void *c, const void *dLdG, void *oA,
+                 void *ob, void *oc) {
+    return mmh_vjp_batched_host(1, ndim, shape, G, c, dLdG, oA, ob, oc);
+}
+
+int mmh_binomial(int ndim, const int64_t *shape, const void *dA, const void *db, const void *dc,
+                 double max_l2, int64_t global_cutoff, void *dG, double *norm_out, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return binomial_impl(ndim, shape, dA, db, dc, max_l2, global_cutoff, dG, norm_out, (cudaStream_t)stream);
+}
+
+int mmh_binomial_host(int ndim, const int64_t *shape, const void *A, const void *b, const void *c,
+                      double max_l2, int64_t global_cutoff, void *G, double *norm_out) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    LatticeDesc d; int mx;
+    int rc = make_desc(ndim, shape, &d, &mx);
+    if (rc) return rc;
+    if (!A || !b || !c || !G) return MMH_ERR_NULL_POINTER;
+    DeviceCtx *ctx;
+    if ((rc = get_ctx(&ctx))) return rc;
+    const size_t D = ndim;
+    void *dA, *db, *dc, *dG;
+    if ((rc = stage_in(*ctx, 0, A, sizeof(c128) * D * D, &dA))) return rc;
+    if ((rc = stage_in(*ctx, 1, b, sizeof(c128) * D, &db))) return rc;
+    if ((rc = stage_in(*ctx, 2, c, sizeof(c128), &dc))) return rc;
+    if ((rc = stage_in(*ctx, 3, nullptr, sizeof(c128) * (size_t)d.N, &dG))) return rc;
+    if ((rc = binomial_impl(ndim, shape, dA, db, dc, max_l2, global_cutoff, dG, norm_out, 0))) return rc;
+    CK(cudaMemcpyAsync(G, dG, sizeof(c128) * (size_t)d.N, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    return MMH_OK;
+}
+
+}  // extern "C"

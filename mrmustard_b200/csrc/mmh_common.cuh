@@ -1,0 +1,82 @@
+// mmh_common.cuh — shared device helpers for the Gaussian-to-Fock kernels (sm_100a).
+//
+// Arithmetic contract (DESIGN.md "Numerics"): the forward kernels reproduce the reference's
+// per-element IEEE-754 double arithmetic exactly (vanilla/core.py:97-104): every product and sum is
+// rounded separately (explicit __dmul_rn/__dadd_rn so that ptxas can never contract them into DFMA),
+// terms are accumulated in the reference's order, and the final division by sqrt(k_i) is a correctly
+// rounded IEEE division.  The *schedule* (which amplitude is computed when, and by which thread) is
+// free, because every amplitude only depends on amplitudes that are already final.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mmhermite.h"
+
+typedef double2 c128;  // (x = re, y = im), 16-byte aligned
+
+struct LatticeDesc {
+    int D;
+    int pad_;
+    long long N;                        // prod(shape)
+    int shape[MMH_MAX_DIM];
+    long long strides[MMH_MAX_DIM];     // row-major element strides, strides[D-1] = 1
+};
+
+__device__ __forceinline__ c128 c_make(double re, double im) { return make_double2(re, im); }
+
+// complex * complex, exactly as numba lowers it: (ac - bd, ad + bc), four products and two sums, no FMA.
+__device__ __forceinline__ c128 c_mul(c128 x, c128 y) {
+    return make_double2(__dsub_rn(__dmul_rn(x.x, y.x), __dmul_rn(x.y, y.y)),
+                        __dadd_rn(__dmul_rn(x.x, y.y), __dmul_rn(x.y, y.x)));
+}
+// complex * real (the reference promotes the real to (s, +0) first; identical up to the sign of zero)
+__device__ __forceinline__ c128 c_scale(c128 x, double s) {
+    return make_double2(__dmul_rn(x.x, s), __dmul_rn(x.y, s));
+}
+__device__ __forceinline__ c128 c_add(c128 x, c128 y) {
+    return make_double2(__dadd_rn(x.x, y.x), __dadd_rn(x.y, y.y));
+}
+
+// Correctly rounded x / s given r = RN(1/s), s > 0 normal.
+//   q0 = RN(x r);  e0 = x - s q0 (exact, FMA);  q1 = RN(q0 + e0 r)   -> |q1 - x/s| < 1 ulp
+//   e1 = x - s q1 (exact);                      q2 = RN(q1 + e1 r)   -> RN(x/s)  (Markstein's theorem)
+// The exactness of e needs x away from the subnormal range, and inf/nan/0 need IEEE special-casing,
+// so anything outside 2^-900 < |x| < 2^900 takes the plain IEEE division.
+__device__ __forceinline__ double div_by_table(double x, double s, double r) {
+    // biased exponent of x in [124, 1923)  <=>  2^-899 <= |x| < 2^900, tested on the integer pipe
+    unsigned hi = (unsigned)__double2hiint(x) & 0x7fffffffu;
+    if (hi - (124u << 20) < ((1923u - 124u) << 20)) {
+        double q = __dmul_rn(x, r);
+        double e = __fma_rn(-s, q, x);
+        q = __fma_rn(e, r, q);
+        e = __fma_rn(-s, q, x);
+        return __fma_rn(e, r, q);
+    }
+    return __ddiv_rn(x, s);
+}
+__device__ __forceinline__ c128 c_div_table(c128 v, double s, double r) {
+    return make_double2(div_by_table(v.x, s, r), div_by_table(v.y, s, r));
+}
+__device__ __forceinline__ c128 c_div_real(c128 v, double s) {
+    return make_double2(__ddiv_rn(v.x, s), __ddiv_rn(v.y, s));
+}
+
+// fused complex multiply-accumulate for the VJP reductions (tolerance-gated, not bit-exact): acc += x*y
+__device__ __forceinline__ void c_fma(c128 &acc, c128 x, c128 y) {
+    acc.x = fma(x.x, y.x, acc.x);
+    acc.x = fma(-x.y, y.y, acc.x);
+    acc.y = fma(x.x, y.y, acc.y);
+    acc.y = fma(x.y, y.x, acc.y);
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}

@@ -1,0 +1,327 @@
+// mmh_forward.cu — forward Gaussian-to-Fock kernels (generic dimension), sm_100a.
+//
+// Schedule ("panel march").  With the reference's pivot rule (first non-zero index,
+// pivots.py:21-34 / core.py:90-94) a point k whose first non-zero index is i reads only
+//     G[k - e_i], G[k - 2 e_i], G[k - e_i - e_j]  (j > i),
+// all of which have the same zero prefix k_0..k_{i-1} = 0 and k_i smaller by one or two.  Hence, for a
+// fixed "stage" i and "step" s = k_i >= 1, the panel  { k : k_<i = 0, k_i = s, k_>i free }  of
+// strides[i] points is embarrassingly parallel given the panels s-1 and s-2 of the same stage (panel 0
+// of stage i is the whole sub-lattice of the stages > i).  The lattice is filled by stages D-1 .. 0 and
+// steps 1 .. shape[i]-1: sum_i (shape[i]-1) dependent steps instead of prod(shape) dependent points.
+//
+// The per-point arithmetic is the reference's (core.py:97-104), see mmh_common.cuh.
+#include "mmh_params.cuh"
+
+
+// one amplitude of stage i, step s, panel offset f  (vanilla pivot rule)
+__device__ __forceinline__ c128 vanilla_point(const LatticeDesc &d, const c128 *sA, const c128 *sb,
+                                              const c128 *G, const double *__restrict__ sq,
+                                              const double *__restrict__ rsq, int i, int s, long long f) {
+    const int D = d.D;
+    const long long si = d.strides[i];
+    const long long pivot = (long long)(s - 1) * si + f;
+    c128 val = c_mul(sb[i], G[pivot]);                                                  // core.py:97
+    if (s >= 2) val = c_add(val, c_mul(c_scale(sA[i * D + i], sq[s - 1]), G[pivot - si]));  // :101
+    long long rem = f;
+    for (int j = i + 1; j < D; j++) {                                                   // :102-103
+        const long long sj = d.strides[j];
+        const int kj = (int)(rem / sj);
+        rem -= (long long)kj * sj;
+        if (kj > 0) val = c_add(val, c_mul(c_scale(sA[i * D + j], sq[kj]), G[pivot - sj]));
+    }
+    return c_div_table(val, sq[s], rsq[s]);                                             // :104
+}
+
+// 32-bit flavour of the same (N < 2^31): cheaper index arithmetic
+__device__ __forceinline__ c128 vanilla_point32(const LatticeDesc &d, const c128 *sA, const c128 *sb,
+                                                const c128 *G, const double *__restrict__ sq,
+                                                const double *__restrict__ rsq, int i, int s, unsigned f) {
+    const int D = d.D;
+    const unsigned si = (unsigned)d.strides[i];
+    const unsigned pivot = (unsigned)(s - 1) * si + f;
+    c128 val = c_mul(sb[i], G[pivot]);
+    if (s >= 2) val = c_add(val, c_mul(c_scale(sA[i * D + i], sq[s - 1]), G[pivot - si]));
+    unsigned rem = f;
+    for (int j = i + 1; j < D; j++) {
+        const unsigned sj = (unsigned)d.strides[j];
+        const unsigned kj = rem / sj;
+        rem -= kj * sj;
+        if (kj > 0) val = c_add(val, c_mul(c_scale(sA[i * D + j], sq[kj]), G[pivot - sj]));
+    }
+    return c_div_table(val, sq[s], rsq[s]);
+}
+
+// stable point (core.py:183-211): average of the update over every pivot i with k_i > 0
+__device__ c128 stable_point(const LatticeDesc &d, const c128 *sA, const c128 *sb,
+                             const c128 *G, const double *__restrict__ sq, const int *k,
+                             long long flat) {
+    const int D = d.D;
+    c128 vals = c_make(0.0, 0.0);
+    int np = 0;
+    for (int i = 0; i < D; i++) {
+        if (k[i] == 0) continue;
+        np++;
+        const long long pivot = flat - d.strides[i];
+        c128 val = c_mul(sb[i], G[pivot]);
+        for (int j = 0; j < i; j++)
+            if (k[j] > 0) val = c_add(val, c_mul(c_scale(sA[i * D + j], sq[k[j]]), G[pivot - d.strides[j]]));
+        if (k[i] > 1) val = c_add(val, c_mul(c_scale(sA[i * D + i], sq[k[i] - 1]), G[pivot - d.strides[i]]));
+        for (int j = i + 1; j < D; j++)
+            if (k[j] > 0) val = c_add(val, c_mul(c_scale(sA[i * D + j], sq[k[j]]), G[pivot - d.strides[j]]));
+        vals = c_add(vals, c_div_real(val, sq[k[i]]));
+    }
+    return c_div_real(vals, (double)np);
+}
+
+// Fill stages [stage_lo, stage_hi] (descending) of one lattice with the threads of one CTA.
+__device__ void cta_fill_vanilla(const LatticeDesc &d, const c128 *sA, const c128 *sb, c128 *G,
+                                 const double *sq, const double *rsq, int stage_hi, int stage_lo) {
+    const bool small = d.N < 0x7fffffffLL;
+    for (int i = stage_hi; i >= stage_lo; i--) {
+        const long long P = d.strides[i];
+        const int S = d.shape[i];
+        for (int s = 1; s < S; s++) {
+            if (small) {
+                const unsigned base = (unsigned)s * (unsigned)P;
+                for (unsigned f = threadIdx.x; f < (unsigned)P; f += blockDim.x)
+                    G[base + f] = vanilla_point32(d, sA, sb, G, sq, rsq, i, s, f);
+            } else {
+                const long long base = (long long)s * P;
+                for (long long f = threadIdx.x; f < P; f += blockDim.x)
+                    G[base + f] = vanilla_point(d, sA, sb, G, sq, rsq, i, s, f);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Level-wavefront fill for the stable rule: level n = |k|; threads enumerate the prefix (k_0..k_{D-2})
+// and derive k_{D-1} = n - sum(prefix).
+__device__ void cta_fill_stable(const LatticeDesc &d, const c128 *sA, const c128 *sb, c128 *G,
+                                const double *sq) {
+    const int D = d.D;
+    const int last = d.shape[D - 1];
+    const long long Q = d.N / last;  // number of prefixes
+    int maxlevel = 0;
+    for (int i = 0; i < D; i++) maxlevel += d.shape[i] - 1;
+    int k[MMH_MAX_DIM];
+    for (int n = 1; n <= maxlevel; n++) {
+        for (long long q = threadIdx.x; q < Q; q += blockDim.x) {
+            long long rem = q * last;
+            int sum = 0;
+            for (int j = 0; j < D - 1; j++) {
+                k[j] = (int)(rem / d.strides[j]);
+                rem -= (long long)k[j] * d.strides[j];
+                sum += k[j];
+            }
+            const int kl = n - sum;
+            if (kl < 0 || kl >= last) continue;
+            k[D - 1] = kl;
+            const long long flat = q * last + kl;
+            G[flat] = stable_point(d, sA, sb, G, sq, k, flat);
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void load_Ab(const FwdParams &p, long long lattice, c128 *sA, c128 *sb) {
+    const int D = p.d.D;
+    const c128 *A = p.A + lattice * D * D;
+    const c128 *b = p.b + lattice * D;
+    for (int t = threadIdx.x; t < D * D; t += blockDim.x) sA[t] = A[t];
+    for (int t = threadIdx.x; t < D; t += blockDim.x) sb[t] = b[t];
+}
+
+// K2-generic: one CTA per triple (grid-stride over the batch); the lattice lives in global memory and
+// is re-read through L1/L2 (the CTA is the only reader and writer of its lattice).
+template <bool STABLE>
+__global__ void __launch_bounds__(256) k_fwd_cta(FwdParams p) {
+    extern __shared__ c128 smem[];
+    c128 *sA = smem;
+    c128 *sb = smem + p.d.D * p.d.D;
+    for (long long l = blockIdx.x; l < p.batch; l += gridDim.x) {
+        __syncthreads();
+        load_Ab(p, l, sA, sb);
+        c128 *G = p.G + l * p.d.N;
+        if (threadIdx.x == 0) G[0] = p.c[l];
+        __syncthreads();
+        if (STABLE) cta_fill_stable(p.d, sA, sb, G, p.sq);
+        else cta_fill_vanilla(p.d, sA, sb, G, p.sq, p.rsq, p.d.D - 1, 0);
+    }
+}
+
+// monotone-counter grid barrier; every CTA of a cooperative launch calls it the same number of times
+__device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned &epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        epoch++;
+        red_release_add_u32(counter, 1u);
+        const unsigned target = epoch * gridDim.x;
+        while (ld_acquire_u32(counter) < target) { }
+    }
+    __syncthreads();
+}
+
+// K1-coop: one lattice, all SMs.  CTA 0 fills the small trailing stages alone (CTA barriers only), then
+// every remaining (stage, step) panel is spread over the grid with one grid barrier per step.
+__global__ void __launch_bounds__(256) k_fwd_coop(FwdParams p) {
+    extern __shared__ c128 smem[];
+    c128 *sA = smem;
+    c128 *sb = smem + p.d.D * p.d.D;
+    const LatticeDesc &d = p.d;
+    load_Ab(p, 0, sA, sb);
+    c128 *G = p.G;
+    unsigned epoch = 0;
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) G[0] = p.c[0];
+        __syncthreads();
+        cta_fill_vanilla(d, sA, sb, G, p.sq, p.rsq, d.D - 1, p.small_stage_lo);
+        __threadfence();
+    } else {
+        __syncthreads();
+    }
+    const bool small = d.N < 0x7fffffffLL;
+    for (int i = p.small_stage_lo - 1; i >= 0; i--) {
+        const long long P = d.strides[i];
+        const int S = d.shape[i];
+        for (int s = 1; s < S; s++) {
+            grid_barrier(p.barrier, epoch);
+            const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            const long long step = (long long)gridDim.x * blockDim.x;
+            if (small) {
+                const unsigned base = (unsigned)s * (unsigned)P;
+                for (unsigned f = (unsigned)t0; f < (unsigned)P; f += (unsigned)step)
+                    G[base + f] = vanilla_point32(d, sA, sb, G, p.sq, p.rsq, i, s, f);
+            } else {
+                const long long base = (long long)s * P;
+                for (long long f = t0; f < P; f += step)
+                    G[base + f] = vanilla_point(d, sA, sb, G, p.sq, p.rsq, i, s, f);
+            }
+        }
+    }
+}
+
+// K1-stable-coop: level wavefront over the whole grid with one grid barrier per level.
+__global__ void __launch_bounds__(256) k_stable_coop(FwdParams p) {
+    extern __shared__ c128 smem[];
+    c128 *sA = smem;
+    c128 *sb = smem + p.d.D * p.d.D;
+    const LatticeDesc &d = p.d;
+    load_Ab(p, 0, sA, sb);
+    c128 *G = p.G;
+    if (blockIdx.x == 0 && threadIdx.x == 0) G[0] = p.c[0];
+    const int D = d.D;
+    const int last = d.shape[D - 1];
+    const long long Q = d.N / last;
+    int maxlevel = 0;
+    for (int i = 0; i < D; i++) maxlevel += d.shape[i] - 1;
+    int k[MMH_MAX_DIM];
+    unsigned epoch = 0;
+    for (int n = 1; n <= maxlevel; n++) {
+        grid_barrier(p.barrier, epoch);
+        for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < Q;
+             q += (long long)gridDim.x * blockDim.x) {
+            long long rem = q * last;
+            int sum = 0;
+            for (int j = 0; j < D - 1; j++) {
+                k[j] = (int)(rem / d.strides[j]);
+                rem -= (long long)k[j] * d.strides[j];
+                sum += k[j];
+            }
+            const int kl = n - sum;
+            if (kl < 0 || kl >= last) continue;
+            k[D - 1] = kl;
+            const long long flat = q * last + kl;
+            G[flat] = stable_point(d, sA, sb, G, p.sq, k, flat);
+        }
+    }
+}
+
+// ---- binomial: level wavefront in one CTA with deterministic per-level norm and early stop ---------
+// (binomial.py:58-71, steps.py:208-235).  The vanilla update is used for every point of a level; the
+// reference additionally adds exact zeros for j < i (steps.py:63-64), which does not change the value.
+
+__global__ void __launch_bounds__(1024) k_binomial_cta(BinomParams p) {
+    extern __shared__ c128 smem[];
+    const LatticeDesc &d = p.d;
+    const int D = d.D;
+    c128 *sA = smem;
+    c128 *sb = smem + D * D;
+    double *red = (double *)(sb + D);  // blockDim.x / 32 partial sums + 1 broadcast slot
+    for (int t = threadIdx.x; t < D * D; t += blockDim.x) sA[t] = p.A[t];
+    for (int t = threadIdx.x; t < D; t += blockDim.x) sb[t] = p.b[t];
+    c128 *G = p.G;
+    const c128 c0 = p.c[0];
+    if (threadIdx.x == 0) G[0] = c0;
+    const double a0 = hypot(c0.x, c0.y);
+    double norm = __dmul_rn(a0, a0);  // np.abs(c) ** 2 (binomial.py:55)
+    __syncthreads();
+    const int last = d.shape[D - 1];
+    const long long Q = d.N / last;
+    int maxlevel = 0;
+    for (int i = 0; i < D; i++) maxlevel += d.shape[i] - 1;
+    for (long long n = 1; n < p.global_cutoff; n++) {
+        double part = 0.0;
+        if (n <= maxlevel) {
+            for (long long q = threadIdx.x; q < Q; q += blockDim.x) {
+                long long rem = q * last;
+                int sum = 0, piv = -1, spiv = 0;
+                long long fpanel = 0;  // offset of the point inside its (stage, step) panel
+                for (int j = 0; j < D - 1; j++) {
+                    const int kj = (int)(rem / d.strides[j]);
+                    rem -= (long long)kj * d.strides[j];
+                    sum += kj;
+                    if (piv < 0) { if (kj > 0) { piv = j; spiv = kj; } }
+                    else fpanel += (long long)kj * d.strides[j];
+                }
+                const long long kl = n - sum;
+                if (kl < 0 || kl >= last) continue;
+                if (piv < 0) { piv = D - 1; spiv = (int)kl; }
+                else fpanel += kl;
+                const c128 v = vanilla_point(d, sA, sb, G, p.sq, p.rsq, piv, spiv, fpanel);
+                G[q * last + kl] = v;
+                const double a = hypot(v.x, v.y);
+                part += a * a;
+            }
+        }
+        // deterministic block reduction (fixed tree)
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int w = 0; w < (int)(blockDim.x + 31) / 32; w++) s += red[w];
+            red[32] = s;
+        }
+        __syncthreads();
+        norm += red[32];
+        __syncthreads();
+        if (norm > p.max_l2) break;
+    }
+    if (threadIdx.x == 0) *p.norm_out = norm;
+}
+
+// ---- host-side launchers (called from mmh_api.cu) -------------------------------------------------
+cudaError_t mmh_launch_fwd_cta(const FwdParams &p, bool stable, int grid, int block, size_t smem,
+                               cudaStream_t st) {
+    if (stable) k_fwd_cta<true><<<grid, block, smem, st>>>(p);
+    else k_fwd_cta<false><<<grid, block, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t mmh_coop_max_blocks(bool stable, int block, size_t smem, int *per_sm) {
+    if (stable) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_stable_coop, block, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_fwd_coop, block, smem);
+}
+
+cudaError_t mmh_launch_fwd_coop(const FwdParams &p, bool stable, int grid, int block, size_t smem,
+                                cudaStream_t st) {
+    void *args[] = { (void *)&p };
+    if (stable) return cudaLaunchCooperativeKernel((void *)k_stable_coop, dim3(grid), dim3(block), args, smem, st);
+    return cudaLaunchCooperativeKernel((void *)k_fwd_coop, dim3(grid), dim3(block), args, smem, st);
+}
+
+cudaError_t mmh_launch_binomial(const BinomParams &p, int block, size_t smem, cudaStream_t st) {
+    k_binomial_cta<<<1, block, smem, st>>>(p);
+    return cudaGetLastError();
+}

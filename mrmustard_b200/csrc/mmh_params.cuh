@@ -1,0 +1,45 @@
+// mmh_params.cuh — kernel parameter blocks and host-side launcher prototypes shared by the translation units.
+#pragma once
+#include "mmh_common.cuh"
+
+struct FwdParams {
+    LatticeDesc d;
+    const c128 *A;      // [batch, D, D]
+    const c128 *b;      // [batch, D]
+    const c128 *c;      // [batch]
+    c128 *G;            // [batch, N]
+    const double *sq;   // sqrt table  sq[n]  = RN(sqrt(n))      (SQRT, vanilla/core.py:22)
+    const double *rsq;  // reciprocal  rsq[n] = RN(1 / sq[n]),   rsq[0] unused
+    long long batch;
+    unsigned *barrier;   // grid-barrier counter (cooperative kernels)
+    int small_stage_lo;  // cooperative kernel: stages >= this are filled by CTA 0 alone
+};
+
+struct BinomParams {
+    LatticeDesc d;
+    const c128 *A, *b, *c;
+    c128 *G;
+    const double *sq, *rsq;
+    double max_l2;
+    long long global_cutoff;
+    double *norm_out;  // device scalar
+};
+
+struct VjpParams {
+    LatticeDesc d;
+    const c128 *G;       // [batch, N]
+    const c128 *g;       // [batch, N]  (dLdG)
+    const c128 *c;       // [batch]
+    c128 *partial;       // [batch, nblk, nacc]
+    c128 *dA, *db, *dc;  // outputs [batch, D, D], [batch, D], [batch]
+    const double *sq;
+    long long batch;
+    int nblk;
+    int nacc;
+};
+
+cudaError_t mmh_launch_fwd_cta(const FwdParams &p, bool stable, int grid, int block, size_t smem, cudaStream_t st);
+cudaError_t mmh_coop_max_blocks(bool stable, int block, size_t smem, int *per_sm);
+cudaError_t mmh_launch_fwd_coop(const FwdParams &p, bool stable, int grid, int block, size_t smem, cudaStream_t st);
+cudaError_t mmh_launch_binomial(const BinomParams &p, int block, size_t smem, cudaStream_t st);
+cudaError_t mmh_launch_vjp(const VjpParams &p, int grid_y, int block, cudaStream_t st);

@@ -1,0 +1,46 @@
+"""Install the B200 path behind a live MrMustard (`mrmustard.math`) — see INTEGRATION.md.
+
+The reference resolves `math.hermite_renormalized*` by name on the active backend object
+(BackendManager._apply, backend_manager.py:89-116) and the jax VJP rules call `strategies.*` by name
+(math/jax_vjps/hermite.py:60-74,86-102).  `install()` therefore (1) rebinds the three BackendNumpy
+methods this package implements and (2) rebinds the strategy functions in
+`mrmustard.math.lattice.strategies`.  `uninstall()` restores the originals.
+"""
+from __future__ import annotations
+
+from . import backend, strategies
+
+_saved: dict = {}
+
+_STRATEGY_NAMES = ["vanilla_numba", "stable_numba", "vanilla_batch_numba", "vanilla_vjp_numba",
+                   "vanilla_batch_vjp_numba", "binomial"]
+
+
+def install() -> None:
+    import mrmustard.math.lattice.strategies as ref_strategies
+    from mrmustard.math.backend_numpy import BackendNumpy
+
+    if _saved:
+        return
+    for name in _STRATEGY_NAMES:
+        _saved[("s", name)] = getattr(ref_strategies, name)
+        setattr(ref_strategies, name, getattr(strategies, name))
+    for name, fn in {
+        "hermite_renormalized": lambda self, A, b, c, shape, stable=False, out=None:
+            backend.hermite_renormalized_unbatched(A, b, c, shape, stable, out),
+        "hermite_renormalized_batched": lambda self, A, b, c, shape, stable=False, out=None:
+            backend.hermite_renormalized_batched(A, b, c, shape, stable, out),
+        "hermite_renormalized_binomial": lambda self, A, B, C, shape, max_l2, global_cutoff:
+            backend.hermite_renormalized_binomial(A, B, C, shape, max_l2, global_cutoff),
+    }.items():
+        _saved[("b", name)] = getattr(BackendNumpy, name)
+        setattr(BackendNumpy, name, fn)
+
+
+def uninstall() -> None:
+    import mrmustard.math.lattice.strategies as ref_strategies
+    from mrmustard.math.backend_numpy import BackendNumpy
+
+    for (kind, name), fn in _saved.items():
+        setattr(ref_strategies if kind == "s" else BackendNumpy, name, fn)
+    _saved.clear()

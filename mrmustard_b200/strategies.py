@@ -1,0 +1,156 @@
+"""Host-side mirror of the reference's `mrmustard.math.lattice.strategies` for the Gaussian-to-Fock path.
+
+Same function names, argument meaning, return types and `out` contract as the reference's numba
+strategies; the work is done by hand-written sm_100a kernels behind the C ABI (include/mmhermite.h).
+numpy in, numpy out: inputs are copied to the device, the lattice is computed there and copied back into
+page-locked host memory (or into `out`).  There is no CPU fallback.
+
+Reference: mrmustard/math/lattice/strategies/vanilla/{core,batch,gradients}.py, strategies/binomial.py.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib, shape_array
+
+__all__ = [
+    "vanilla_numba", "stable_numba", "vanilla_batch_numba", "vanilla_vjp_numba",
+    "vanilla_batch_vjp_numba", "binomial", "vanilla", "stable",
+]
+
+
+def _c128(x, shape=None) -> np.ndarray:
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.complex128))
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _p(a: np.ndarray) -> ctypes.c_void_p:
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _check_out(out, nelem: int) -> None:
+    # core.py:73 `out.ravel()` + `G.reshape(shape)`: out must be C-contiguous complex128 of exactly prod(shape) entries
+    if not isinstance(out, np.ndarray) or out.dtype != np.complex128 or not out.flags.c_contiguous:
+        raise TypeError("out must be a C-contiguous complex128 numpy array")
+    if out.size != nelem:
+        raise ValueError(f"cannot reshape array of size {out.size} into the requested lattice of {nelem} entries")
+
+
+def _check_shape(shape) -> tuple[int, ...]:
+    shape = tuple(int(s) for s in shape)
+    if any(s < 1 for s in shape):
+        raise ValueError(f"shape {shape} must have all entries >= 1")
+    return shape
+
+
+def _forward(shape, A, b, c, out, stable: bool) -> np.ndarray:
+    shape = _check_shape(shape)
+    A = _c128(A)
+    b = _c128(b)
+    D = b.shape[-1]                      # core.py:66 `D = b.shape[-1]`
+    if len(shape) != D:
+        raise ValueError(f"len(shape)={len(shape)} must equal b.shape[-1]={D}")
+    A = A.reshape(D, D)
+    b = b.reshape(D)
+    c = _c128(c, (1,))
+    n = int(np.prod(shape, dtype=np.int64))
+    if out is None:
+        G = _lib.pinned_empty(shape)
+    else:
+        _check_out(out, n)
+        G = out
+    check(lib.mmh_forward_host(D, shape_array(shape), _p(A), _p(b), _p(c), _p(G), int(bool(stable))))
+    if out is not None:
+        return out if out.shape == shape else out.reshape(shape)
+    return G
+
+
+def vanilla_numba(shape, A, b, c, out=None) -> np.ndarray:
+    """Fock lattice of the Bargmann triple, first-non-zero-index pivot (vanilla/core.py:25-124)."""
+    return _forward(shape, A, b, c, out, False)
+
+
+def stable_numba(shape, A, b, c, out=None) -> np.ndarray:
+    """Same, averaged over all valid pivots (vanilla/core.py:127-213)."""
+    return _forward(shape, A, b, c, out, True)
+
+
+vanilla = vanilla_numba
+stable = stable_numba
+
+
+def vanilla_batch_numba(shape, A, b, c, stable: bool = False, out=None) -> np.ndarray:
+    """Batch of independent lattices, batch on the first axis (vanilla/batch.py:27-61)."""
+    shape = _check_shape(shape)
+    b = _c128(b)
+    if b.ndim != 2:
+        raise ValueError("b must have shape (batch, D)")
+    B, D = b.shape                       # batch.py:52 `batch_size = b.shape[0]`
+    if len(shape) != D:
+        raise ValueError(f"len(shape)={len(shape)} must equal b.shape[-1]={D}")
+    A = _c128(A)
+    if A.shape != (B, D, D):
+        A = np.ascontiguousarray(np.broadcast_to(A, (B, D, D)))
+    c = _c128(c)
+    if c.shape != (B,):
+        c = np.ascontiguousarray(np.broadcast_to(c, (B,)))
+    n = int(np.prod(shape, dtype=np.int64))
+    if out is None:
+        G = _lib.pinned_empty((B, *shape))
+    else:
+        _check_out(out, B * n)
+        G = out
+    check(lib.mmh_forward_batched_host(B, D, shape_array(shape), _p(A), _p(b), _p(c), _p(G), int(bool(stable))))
+    return G
+
+
+def vanilla_vjp_numba(G, c, dLdG):
+    """(dL/dA, dL/db, dL/dc) from the forward lattice and its cotangent (vanilla/gradients.py:25-82)."""
+    G = _c128(G)
+    dLdG = _c128(dLdG)
+    if dLdG.shape != G.shape:
+        raise ValueError(f"dLdG.shape={dLdG.shape} must equal G.shape={G.shape}")
+    D = G.ndim
+    c = _c128(c, (1,))
+    dA = np.empty((D, D), np.complex128)
+    db = np.empty((D,), np.complex128)
+    dc = np.empty((1,), np.complex128)
+    check(lib.mmh_vjp_host(D, shape_array(G.shape), _p(G), _p(c), _p(dLdG), _p(dA), _p(db), _p(dc)))
+    return dA, db, complex(dc[0])
+
+
+def vanilla_batch_vjp_numba(G, c, dLdG):
+    """Per-triple VJP, batch on the first axis (vanilla/gradients.py:85-116)."""
+    G = _c128(G)
+    dLdG = _c128(dLdG)
+    if dLdG.shape != G.shape:
+        raise ValueError(f"dLdG.shape={dLdG.shape} must equal G.shape={G.shape}")
+    B = G.shape[0]
+    D = G.ndim - 1
+    c = _c128(c, (B,))
+    dA = np.empty((B, D, D), np.complex128)
+    db = np.empty((B, D), np.complex128)
+    dc = np.empty((B,), np.complex128)
+    if B:
+        check(lib.mmh_vjp_batched_host(B, D, shape_array(G.shape[1:]), _p(G), _p(c), _p(dLdG), _p(dA), _p(db), _p(dc)))
+    return dA, db, dc
+
+
+def binomial(local_cutoffs, A, b, c, max_l2, global_cutoff):
+    """Fill by total photon number with early stop; returns (G, norm) (strategies/binomial.py:30-72)."""
+    shape = _check_shape(local_cutoffs)
+    D = len(shape)
+    A = _c128(A, (D, D))
+    b = _c128(b, (D,))
+    c = _c128(c, (1,))
+    G = _lib.pinned_empty(shape)
+    norm = ctypes.c_double(0.0)
+    max_l2 = float("inf") if max_l2 is None else float(max_l2)   # binomial.py:68-69 (TypeError -> never stop)
+    check(lib.mmh_binomial_host(D, shape_array(shape), _p(A), _p(b), _p(c), max_l2, int(global_cutoff), _p(G),
+                                ctypes.byref(norm)))
+    return G, norm.value

@@ -117,6 +117,49 @@ static inline int round_up32(long long v) { return (int)((v + 31) / 32 * 32); }
 static const long long kSmallPanel = 1024;     // panels up to this size are filled by one CTA
 static const long long kSingleCtaN = 16384;    // lattices up to this size use the one-CTA kernel
 
+// K2 launch plan: L lattices per CTA, R panel points per thread, T threads (mmh_march.cu)
+static bool plan_batched_march(const LatticeDesc &d, long long batch, MarchParams *mp, int *R_out, int *T_out,
+                               size_t *smem_out) {
+    const int D = d.D;
+    if (D < 2 || D > 8) return false;
+    const long long P0 = d.strides[0];
+    if (P0 > 1024) return false;
+    int tab_len = 0;
+    memset(mp, 0, sizeof(*mp));
+    for (int j = 1; j < D; j++) { mp->tab_off[j] = tab_len; tab_len += d.shape[j]; }
+    if (tab_len > 4096) return false;
+    const char *eL = getenv("MMH_K2_L"), *eR = getenv("MMH_K2_R");
+    double best = -1.0;
+    int bL = 0, bR = 0, bT = 0;
+    size_t bsmem = 0;
+    const int Lmax = (int)(batch < 32 ? batch : 32);
+    for (int L = 1; L <= Lmax; L++) {
+        const long long slots = L * P0;
+        if (slots > 1024) break;
+        if (eL && atoi(eL) != L) continue;
+        const size_t smem = sizeof(c128) * (size_t)L * (D * D + D + tab_len + 2 * P0);
+        if (smem > 96 * 1024) break;
+        const int Rs[3] = { 1, 2, 4 };
+        for (int r = 0; r < 3; r++) {
+            const int R = Rs[r];
+            if (eR && atoi(eR) != R) continue;
+            const int Tmax = R == 4 ? 256 : 512;
+            int T = round_up32((slots + R - 1) / R);
+            if (T > Tmax) continue;
+            const double eff = (double)slots / ((double)T * R);
+            // prefer full warps, two points per thread (ILP), CTAs of a few hundred threads, many lattices per chain warp
+            double score = eff + 0.01 * L / 32.0 + (R == 2 ? 0.02 : 0.0) - (T < 128 ? 0.05 : 0.0);
+            if (score > best) { best = score; bL = L; bR = R; bT = T; bsmem = smem; }
+        }
+    }
+    if (best < 0) return false;
+    mp->d = d;
+    mp->L = bL;
+    mp->tab_len = tab_len;
+    *R_out = bR; *T_out = bT; *smem_out = bsmem;
+    return true;
+}
+
 static int forward_impl(long long batch, int ndim, const int64_t *shape, const void *dA, const void *db,
                         const void *dc, void *dG, int stable, cudaStream_t st) {
     if (batch < 0) return MMH_ERR_BAD_BATCH;
@@ -137,7 +180,24 @@ static int forward_impl(long long batch, int ndim, const int64_t *shape, const v
     p.batch = batch; p.barrier = nullptr; p.small_stage_lo = 0;
     const size_t smem = sizeof(c128) * (size_t)(ndim * ndim + ndim);
 
+    if (!stable && ndim == 1) {  // pure chain: one thread per lattice
+        g_launches++;
+        CK(mmh_launch_chain(p, st));
+        return MMH_OK;
+    }
     const bool per_cta = d.N <= kSingleCtaN || batch >= 2LL * ctx->sm_count;
+    if (!stable && per_cta) {
+        MarchParams mp;
+        int R, T;
+        size_t msmem;
+        if (plan_batched_march(d, batch, &mp, &R, &T, &msmem)) {
+            mp.A = p.A; mp.b = p.b; mp.c = p.c; mp.G = p.G; mp.sq = p.sq; mp.rsq = p.rsq; mp.batch = batch;
+            const long long grid = (batch + mp.L - 1) / mp.L;
+            g_launches++;
+            CK(mmh_launch_batched_march(mp, R, (int)grid, T, msmem, st));
+            return MMH_OK;
+        }
+    }
     if (per_cta) {
         long long maxpanel = stable ? d.N / d.shape[ndim - 1] : d.strides[0];
         int block = round_up32(maxpanel);

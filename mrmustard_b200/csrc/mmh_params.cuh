@@ -38,6 +38,19 @@ struct VjpParams {
     int nacc;
 };
 
+struct MarchParams {
+    LatticeDesc d;
+    const c128 *A, *b, *c;
+    c128 *G;
+    const double *sq, *rsq;
+    long long batch;
+    int L;                       // lattices marched in lock step by one CTA
+    int tab_len;                 // sum_{j>=1} shape[j]
+    int tab_off[MMH_MAX_DIM];    // tab_off[j]: start of dim j's coefficient table (j >= 1)
+};
+
+cudaError_t mmh_launch_batched_march(const MarchParams &p, int R, int grid, int block, size_t smem, cudaStream_t st);
+cudaError_t mmh_launch_chain(const FwdParams &p, cudaStream_t st);
 cudaError_t mmh_launch_fwd_cta(const FwdParams &p, bool stable, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t mmh_coop_max_blocks(bool stable, int block, size_t smem, int *per_sm);
 cudaError_t mmh_launch_fwd_coop(const FwdParams &p, bool stable, int grid, int block, size_t smem, cudaStream_t st);

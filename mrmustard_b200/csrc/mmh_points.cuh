@@ -1,0 +1,65 @@
+// mmh_points.cuh — per-amplitude update rules shared by the forward kernels.
+// The arithmetic (term order, separate roundings, IEEE division) is the reference's, core.py:97-104 / :183-211.
+#pragma once
+#include "mmh_common.cuh"
+
+// one amplitude of stage i, step s, panel offset f  (vanilla pivot rule)
+__device__ __forceinline__ c128 vanilla_point(const LatticeDesc &d, const c128 *sA, const c128 *sb,
+                                              const c128 *G, const double *__restrict__ sq,
+                                              const double *__restrict__ rsq, int i, int s, long long f) {
+    const int D = d.D;
+    const long long si = d.strides[i];
+    const long long pivot = (long long)(s - 1) * si + f;
+    c128 val = c_mul(sb[i], G[pivot]);                                                  // core.py:97
+    if (s >= 2) val = c_add(val, c_mul(c_scale(sA[i * D + i], sq[s - 1]), G[pivot - si]));  // :101
+    long long rem = f;
+    for (int j = i + 1; j < D; j++) {                                                   // :102-103
+        const long long sj = d.strides[j];
+        const int kj = (int)(rem / sj);
+        rem -= (long long)kj * sj;
+        if (kj > 0) val = c_add(val, c_mul(c_scale(sA[i * D + j], sq[kj]), G[pivot - sj]));
+    }
+    return c_div_table(val, sq[s], rsq[s]);                                             // :104
+}
+
+// 32-bit flavour of the same (N < 2^31): cheaper index arithmetic
+__device__ __forceinline__ c128 vanilla_point32(const LatticeDesc &d, const c128 *sA, const c128 *sb,
+                                                const c128 *G, const double *__restrict__ sq,
+                                                const double *__restrict__ rsq, int i, int s, unsigned f) {
+    const int D = d.D;
+    const unsigned si = (unsigned)d.strides[i];
+    const unsigned pivot = (unsigned)(s - 1) * si + f;
+    c128 val = c_mul(sb[i], G[pivot]);
+    if (s >= 2) val = c_add(val, c_mul(c_scale(sA[i * D + i], sq[s - 1]), G[pivot - si]));
+    unsigned rem = f;
+    for (int j = i + 1; j < D; j++) {
+        const unsigned sj = (unsigned)d.strides[j];
+        const unsigned kj = rem / sj;
+        rem -= kj * sj;
+        if (kj > 0) val = c_add(val, c_mul(c_scale(sA[i * D + j], sq[kj]), G[pivot - sj]));
+    }
+    return c_div_table(val, sq[s], rsq[s]);
+}
+
+// stable point (core.py:183-211): average of the update over every pivot i with k_i > 0
+static __device__ c128 stable_point(const LatticeDesc &d, const c128 *sA, const c128 *sb,
+                             const c128 *G, const double *__restrict__ sq, const int *k,
+                             long long flat) {
+    const int D = d.D;
+    c128 vals = c_make(0.0, 0.0);
+    int np = 0;
+    for (int i = 0; i < D; i++) {
+        if (k[i] == 0) continue;
+        np++;
+        const long long pivot = flat - d.strides[i];
+        c128 val = c_mul(sb[i], G[pivot]);
+        for (int j = 0; j < i; j++)
+            if (k[j] > 0) val = c_add(val, c_mul(c_scale(sA[i * D + j], sq[k[j]]), G[pivot - d.strides[j]]));
+        if (k[i] > 1) val = c_add(val, c_mul(c_scale(sA[i * D + i], sq[k[i] - 1]), G[pivot - d.strides[i]]));
+        for (int j = i + 1; j < D; j++)
+            if (k[j] > 0) val = c_add(val, c_mul(c_scale(sA[i * D + j], sq[k[j]]), G[pivot - d.strides[j]]));
+        vals = c_add(vals, c_div_real(val, sq[k[i]]));
+    }
+    return c_div_real(vals, (double)np);
+}
+

@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (vjp, batched)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -357,7 +358,7 @@ def main():
                      "avg_launch_ms": avg_kernel_ms},
     }
     if rank == 0:
-        line["cpu_baseline"] = cpu_baseline(w)
+        line["cpu_baseline"] = None if args.no_cpu else cpu_baseline(w)
         if not args.no_extras and world == 1:
             line["also"] = extras(torch, dev, lib, check, _lib, stream, sptr, flush)
         print(json.dumps(line))

@@ -117,47 +117,64 @@ static inline int round_up32(long long v) { return (int)((v + 31) / 32 * 32); }
 static const long long kSmallPanel = 1024;     // panels up to this size are filled by one CTA
 static const long long kSingleCtaN = 16384;    // lattices up to this size use the one-CTA kernel
 
-// K2 launch plan: L lattices per CTA, R panel points per thread, T threads (mmh_march.cu)
-static bool plan_batched_march(const LatticeDesc &d, long long batch, MarchParams *mp, int *R_out, int *T_out,
-                               size_t *smem_out) {
-    const int D = d.D;
-    if (D < 2 || D > 8) return false;
-    const long long P0 = d.strides[0];
-    if (P0 > 1024) return false;
-    int tab_len = 0;
-    memset(mp, 0, sizeof(*mp));
-    for (int j = 1; j < D; j++) { mp->tab_off[j] = tab_len; tab_len += d.shape[j]; }
-    if (tab_len > 4096) return false;
+// K2 launch plan for one stage: L lattices per CTA, R panel points per thread, T threads (mmh_march.cu)
+static bool plan_march_stage(const LatticeDesc &d, int stage, long long batch, int *L_out, int *R_out, int *T_out,
+                             size_t *smem_out) {
+    const int npd = d.D - 1 - stage;
+    if (npd < 1 || npd > 7) return false;
+    const long long P = d.strides[stage];
+    if (P > 1024) return false;
     const char *eL = getenv("MMH_K2_L"), *eR = getenv("MMH_K2_R");
     double best = -1.0;
     int bL = 0, bR = 0, bT = 0;
     size_t bsmem = 0;
-    const int Lmax = (int)(batch < 32 ? batch : 32);
+    const int Lmax = (int)(batch < 256 ? batch : 256);
     for (int L = 1; L <= Lmax; L++) {
-        const long long slots = L * P0;
+        const long long slots = L * P;
         if (slots > 1024) break;
-        if (eL && atoi(eL) != L) continue;
-        const size_t smem = sizeof(c128) * (size_t)L * (D * D + D + tab_len + 2 * P0);
-        if (smem > 96 * 1024) break;
+        if (eL && stage == 0 && atoi(eL) != L) continue;
+        const size_t smem = sizeof(c128) * (size_t)(2 * L + 2 * slots);
         const int Rs[3] = { 1, 2, 4 };
         for (int r = 0; r < 3; r++) {
             const int R = Rs[r];
-            if (eR && atoi(eR) != R) continue;
+            if (eR && stage == 0 && atoi(eR) != R) continue;
+            if (R > 1 && R * npd > 8) continue;   // per-slot coefficients live in registers
             const int Tmax = R == 4 ? 256 : 512;
             int T = round_up32((slots + R - 1) / R);
             if (T > Tmax) continue;
             const double eff = (double)slots / ((double)T * R);
-            // prefer full warps, two points per thread (ILP), CTAs of a few hundred threads, many lattices per chain warp
-            double score = eff + 0.01 * L / 32.0 + (R == 2 ? 0.02 : 0.0) - (T < 128 ? 0.05 : 0.0);
+            // prefer full warps, two points per thread (ILP), CTAs of ~128-256 threads
+            double score = eff + (R == 2 ? 0.02 : 0.0) - (T < 96 ? 0.05 : 0.0) - (T > 256 ? 0.03 : 0.0);
             if (score > best) { best = score; bL = L; bR = R; bT = T; bsmem = smem; }
         }
     }
     if (best < 0) return false;
-    mp->d = d;
-    mp->L = bL;
-    mp->tab_len = tab_len;
-    *R_out = bR; *T_out = bT; *smem_out = bsmem;
+    *L_out = bL; *R_out = bR; *T_out = bT; *smem_out = bsmem;
     return true;
+}
+
+// batched forward by stages: chain (stage D-1), then one march launch per stage D-2 .. 0
+static int forward_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st, bool *done) {
+    const LatticeDesc &d = p.d;
+    *done = false;
+    int L[MMH_MAX_DIM], R[MMH_MAX_DIM], T[MMH_MAX_DIM];
+    size_t sm[MMH_MAX_DIM];
+    for (int i = d.D - 2; i >= 0; i--)
+        if (!plan_march_stage(d, i, p.batch, &L[i], &R[i], &T[i], &sm[i])) return MMH_OK;
+    g_launches++;
+    CK(mmh_launch_chain(p, st));
+    for (int i = d.D - 2; i >= 0; i--) {
+        if (d.shape[i] == 1) continue;   // nothing to march
+        StageParams sp;
+        sp.d = d; sp.A = p.A; sp.b = p.b; sp.G = p.G; sp.sq = p.sq; sp.rsq = p.rsq;
+        sp.batch = p.batch; sp.lat_stride = d.N; sp.stage = i; sp.L = L[i];
+        const long long grid = (p.batch + L[i] - 1) / L[i];
+        g_launches++;
+        CK(mmh_launch_march_stage(sp, R[i], (int)grid, T[i], sm[i], st));
+    }
+    (void)ctx;
+    *done = true;
+    return MMH_OK;
 }
 
 static int forward_impl(long long batch, int ndim, const int64_t *shape, const void *dA, const void *db,
@@ -180,23 +197,11 @@ static int forward_impl(long long batch, int ndim, const int64_t *shape, const v
     p.batch = batch; p.barrier = nullptr; p.small_stage_lo = 0;
     const size_t smem = sizeof(c128) * (size_t)(ndim * ndim + ndim);
 
-    if (!stable && ndim == 1) {  // pure chain: one thread per lattice
-        g_launches++;
-        CK(mmh_launch_chain(p, st));
-        return MMH_OK;
-    }
     const bool per_cta = d.N <= kSingleCtaN || batch >= 2LL * ctx->sm_count;
-    if (!stable && per_cta) {
-        MarchParams mp;
-        int R, T;
-        size_t msmem;
-        if (plan_batched_march(d, batch, &mp, &R, &T, &msmem)) {
-            mp.A = p.A; mp.b = p.b; mp.c = p.c; mp.G = p.G; mp.sq = p.sq; mp.rsq = p.rsq; mp.batch = batch;
-            const long long grid = (batch + mp.L - 1) / mp.L;
-            g_launches++;
-            CK(mmh_launch_batched_march(mp, R, (int)grid, T, msmem, st));
-            return MMH_OK;
-        }
+    if (!stable && (ndim == 1 || per_cta)) {
+        bool done = false;
+        if ((rc = forward_staged(p, ctx, st, &done))) return rc;
+        if (done) return MMH_OK;
     }
     if (per_cta) {
         long long maxpanel = stable ? d.N / d.shape[ndim - 1] : d.strides[0];

@@ -42,16 +42,22 @@ __device__ __forceinline__ c128 c_add(c128 x, c128 y) {
 //   e1 = x - s q1 (exact);                      q2 = RN(q1 + e1 r)   -> RN(x/s)  (Markstein's theorem)
 // The exactness of e needs x away from the subnormal range, and inf/nan/0 need IEEE special-casing,
 // so anything outside 2^-900 < |x| < 2^900 takes the plain IEEE division.
+// true iff x needs the IEEE slow path: not (2^-899 <= |x| < 2^900) and not zero.  Integer pipe only.
+// (+-0 goes through the fast path: the value is exact, only the sign of the zero may differ.)
+__device__ __forceinline__ bool div_needs_slow(double x) {
+    const unsigned hi = (unsigned)__double2hiint(x) & 0x7fffffffu;
+    const bool inrange = hi - (124u << 20) < ((1923u - 124u) << 20);
+    return !inrange && ((hi | (unsigned)__double2loint(x)) != 0u);
+}
+__device__ __forceinline__ double div_fast(double x, double s, double r) {
+    double q = __dmul_rn(x, r);
+    double e = __fma_rn(-s, q, x);
+    q = __fma_rn(e, r, q);
+    e = __fma_rn(-s, q, x);
+    return __fma_rn(e, r, q);
+}
 __device__ __forceinline__ double div_by_table(double x, double s, double r) {
-    // biased exponent of x in [124, 1923)  <=>  2^-899 <= |x| < 2^900, tested on the integer pipe
-    unsigned hi = (unsigned)__double2hiint(x) & 0x7fffffffu;
-    if (hi - (124u << 20) < ((1923u - 124u) << 20)) {
-        double q = __dmul_rn(x, r);
-        double e = __fma_rn(-s, q, x);
-        q = __fma_rn(e, r, q);
-        e = __fma_rn(-s, q, x);
-        return __fma_rn(e, r, q);
-    }
+    if (!div_needs_slow(x)) return div_fast(x, s, r);
     return __ddiv_rn(x, s);
 }
 __device__ __forceinline__ c128 c_div_table(c128 v, double s, double r) {

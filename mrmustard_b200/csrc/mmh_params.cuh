@@ -38,18 +38,18 @@ struct VjpParams {
     int nacc;
 };
 
-struct MarchParams {
+struct StageParams {
     LatticeDesc d;
-    const c128 *A, *b, *c;
+    const c128 *A, *b;
     c128 *G;
     const double *sq, *rsq;
     long long batch;
+    long long lat_stride;        // elements between consecutive lattices in G (= N)
+    int stage;                   // i: the index being marched (k_<i = 0)
     int L;                       // lattices marched in lock step by one CTA
-    int tab_len;                 // sum_{j>=1} shape[j]
-    int tab_off[MMH_MAX_DIM];    // tab_off[j]: start of dim j's coefficient table (j >= 1)
 };
 
-cudaError_t mmh_launch_batched_march(const MarchParams &p, int R, int grid, int block, size_t smem, cudaStream_t st);
+cudaError_t mmh_launch_march_stage(const StageParams &p, int R, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t mmh_launch_chain(const FwdParams &p, cudaStream_t st);
 cudaError_t mmh_launch_fwd_cta(const FwdParams &p, bool stable, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t mmh_coop_max_blocks(bool stable, int block, size_t smem, int *per_sm);

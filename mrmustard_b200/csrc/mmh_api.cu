@@ -11,6 +11,8 @@
 
 #include "mmh_params.cuh"
 
+#define MMH_KRING_HOST 4  // must equal MMH_KRING in mmh_march.cu
+
 
 #define CK(call)                                   \
     do {                                           \
@@ -20,6 +22,8 @@
 
 static std::atomic<long long> g_launches{0};
 static std::mutex g_mutex;
+
+static const int kFlagWords = 1 << 16;
 
 // ---- per-device context ---------------------------------------------------------------------------
 struct Scratch {
@@ -34,6 +38,8 @@ struct DeviceCtx {
     int table_len = 0;
     unsigned *barrier = nullptr;  // 64 counters; one is consumed per cooperative launch (round robin)
     int barrier_next = 0;
+    unsigned *flags = nullptr;    // tile progress counters for the tiled march (kFlagWords, used round robin)
+    int flags_next = 0;
     Scratch partial;              // VJP partial sums
     Scratch norm;                 // binomial norm scalar
     Scratch host_slots[8];        // staging for the *_host entry points
@@ -84,6 +90,8 @@ static int get_ctx(DeviceCtx **out) {
         c.cc_major = prop.major;
         CK(cudaMalloc(&c.barrier, 64 * sizeof(unsigned)));
         CK(cudaMemset(c.barrier, 0, 64 * sizeof(unsigned)));
+        CK(cudaMalloc(&c.flags, kFlagWords * sizeof(unsigned)));
+        CK(cudaMemset(c.flags, 0, kFlagWords * sizeof(unsigned)));
         c.init = true;
     }
     *out = &c;
@@ -177,6 +185,104 @@ static int forward_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st, b
     return MMH_OK;
 }
 
+// K1 plan: tile grid over the first nt panel dims of `stage` (mmh_march.cu k_march_tiled)
+static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, TiledParams *tp, int *R_out,
+                             int *ntiles_out, size_t *smem_out) {
+    const int npd = d.D - 1 - stage;
+    if (npd < 1 || npd > 7) return false;
+    const long long P = d.strides[stage];
+    if (P >= (1LL << 31)) return false;
+    const int S = d.shape[stage];
+    const int nt = npd < 3 ? npd : 3;
+    const long long inner = d.strides[stage + nt];
+    int shp[3] = { 1, 1, 1 };
+    for (int m = 0; m < nt; m++) shp[m] = d.shape[stage + 1 + m];
+    int forced[3] = { 0, 0, 0 };
+    if (const char *eg = getenv("MMH_TILE_G")) sscanf(eg, "%d,%d,%d", &forced[0], &forced[1], &forced[2]);
+    double best = 1e300;
+    int bg[3] = { 0, 0, 0 }, bR = 0, bTC = 0, bLS = 0, bHC = 0;
+    for (int g0 = 1; g0 <= shp[0] && g0 <= sm_count; g0++)
+        for (int g1 = 1; g1 <= shp[1] && g0 * g1 <= sm_count; g1++)
+            for (int g2 = 1; g2 <= shp[2] && g0 * g1 * g2 <= sm_count; g2++) {
+                if (forced[0] && (g0 != forced[0] || g1 != (forced[1] ? forced[1] : 1) || g2 != (forced[2] ? forced[2] : 1)))
+                    continue;
+                const int g[3] = { g0, g1, g2 };
+                long long e[3], TS = inner, LS = inner;
+                for (int m = 0; m < 3; m++) {
+                    e[m] = (shp[m] + g[m] - 1) / g[m];
+                    TS *= e[m];
+                    LS *= e[m] + (g[m] > 1 ? 1 : 0);
+                }
+                if (TS > 1024) continue;
+                long long HC = 0;
+                for (int m = 0; m < 3; m++) if (g[m] > 1) HC += TS / e[m];
+                const long long HCs = HC > 0 ? HC : 1;   // the kernel lays the ring out with stride hc_max >= 1
+                const size_t smem = sizeof(c128) * (size_t)(2 * LS + MMH_KRING_HOST * HCs) + sizeof(int) * (size_t)(HCs + 4);
+                if (smem > 200 * 1024) continue;
+                int R = 0;
+                const int Rs[3] = { 1, 2, 4 };
+                for (int r = 0; r < 3; r++)
+                    if ((long long)Rs[r] * 256 >= TS && (Rs[r] == 1 || Rs[r] * npd <= 12)) { R = Rs[r]; break; }
+                if (!R) continue;
+                const int TC = round_up32((TS + R - 1) / R);
+                double step_us = (double)TS * 0.55e-3;          // ~0.55 ns per amplitude per SM (FP64 pipe)
+                if (step_us < 0.15) step_us = 0.15;             // dependent-chain floor of one panel step
+                const double cost = (S - 1) * step_us + (g0 + g1 + g2 - 3) * 0.7;
+                if (cost < best) {
+                    best = cost; bg[0] = g0; bg[1] = g1; bg[2] = g2; bR = R; bTC = TC; bLS = (int)LS; bHC = (int)HC;
+                    *smem_out = smem;
+                }
+            }
+    if (best > 1e299) return false;
+    memset(tp, 0, sizeof(*tp));
+    tp->d = d; tp->stage = stage; tp->nt = nt;
+    for (int m = 0; m < 3; m++) tp->g[m] = bg[m];
+    tp->tc = bTC; tp->ls_max = bLS; tp->hc_max = bHC > 0 ? bHC : 1;
+    *R_out = bR;
+    *ntiles_out = bg[0] * bg[1] * bg[2];
+    return true;
+}
+
+// one large lattice: chain, then per stage the smallest machinery that fits
+// (single-CTA march / tiled multi-CTA march / plain per-step launches for giant panels)
+static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st) {
+    const LatticeDesc &d = p.d;
+    const int D = d.D;
+    g_launches++;
+    CK(mmh_launch_chain(p, st));
+    const size_t absmem = sizeof(c128) * (size_t)(D * D + D);
+    for (int i = D - 2; i >= 0; i--) {
+        if (d.shape[i] == 1) continue;
+        int L, R, T, ntiles;
+        size_t sm;
+        TiledParams tp;
+        if (!getenv("MMH_FORCE_TILED") && plan_march_stage(d, i, 1, &L, &R, &T, &sm)) {
+            StageParams sp;
+            sp.d = d; sp.A = p.A; sp.b = p.b; sp.G = p.G; sp.sq = p.sq; sp.rsq = p.rsq;
+            sp.batch = 1; sp.lat_stride = d.N; sp.stage = i; sp.L = L;
+            g_launches++;
+            CK(mmh_launch_march_stage(sp, R, 1, T, sm, st));
+        } else if (plan_march_tiled(d, i, ctx->sm_count, &tp, &R, &ntiles, &sm)) {
+            tp.A = p.A; tp.b = p.b; tp.G = p.G; tp.sq = p.sq; tp.rsq = p.rsq;
+            if (ctx->flags_next + ntiles > kFlagWords) ctx->flags_next = 0;
+            tp.flags = ctx->flags + ctx->flags_next;
+            ctx->flags_next += ntiles;
+            CK(cudaMemsetAsync(tp.flags, 0, sizeof(unsigned) * ntiles, st));
+            g_launches++;
+            CK(mmh_launch_march_tiled(tp, R, ntiles, sm, st));
+        } else {
+            const long long P = d.strides[i];
+            long long grid = (P + 255) / 256;
+            if (grid > 8LL * ctx->sm_count) grid = 8LL * ctx->sm_count;
+            for (int s = 1; s < d.shape[i]; s++) {
+                g_launches++;
+                CK(mmh_launch_panel_step(p, i, s, (int)grid, absmem, st));
+            }
+        }
+    }
+    return MMH_OK;
+}
+
 static int forward_impl(long long batch, int ndim, const int64_t *shape, const void *dA, const void *db,
                         const void *dc, void *dG, int stable, cudaStream_t st) {
     if (batch < 0) return MMH_ERR_BAD_BATCH;
@@ -197,7 +303,7 @@ static int forward_impl(long long batch, int ndim, const int64_t *shape, const v
     p.batch = batch; p.barrier = nullptr; p.small_stage_lo = 0;
     const size_t smem = sizeof(c128) * (size_t)(ndim * ndim + ndim);
 
-    const bool per_cta = d.N <= kSingleCtaN || batch >= 2LL * ctx->sm_count;
+    const bool per_cta = (d.N <= kSingleCtaN && !getenv("MMH_FORCE_TILED")) || batch >= 2LL * ctx->sm_count;
     if (!stable && (ndim == 1 || per_cta)) {
         bool done = false;
         if ((rc = forward_staged(p, ctx, st, &done))) return rc;
@@ -214,7 +320,17 @@ static int forward_impl(long long batch, int ndim, const int64_t *shape, const v
         CK(mmh_launch_fwd_cta(p, stable != 0, (int)grid, block, smem, st));
         return MMH_OK;
     }
-    // large lattices: one cooperative launch per lattice, every SM on the same lattice
+    if (!stable && ndim >= 2 && ndim <= 8 && !getenv("MMH_FORCE_COOP")) {
+        // large lattices, vanilla rule: chain + per-stage march kernels, every SM on the same lattice
+        for (long long l = 0; l < batch; l++) {
+            FwdParams q = p;
+            q.A = p.A + l * ndim * ndim; q.b = p.b + l * ndim; q.c = p.c + l; q.G = p.G + l * d.N;
+            q.batch = 1;
+            if ((rc = forward_single_staged(q, ctx, st))) return rc;
+        }
+        return MMH_OK;
+    }
+    // stable rule (level wavefront) and D > 8: one cooperative launch per lattice
     const int block = 256;
     int per_sm = 0;
     CK(mmh_coop_max_blocks(stable != 0, block, smem, &per_sm));

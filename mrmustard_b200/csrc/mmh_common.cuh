@@ -86,3 +86,23 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
 __device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+
+// CTA-scope release/acquire on shared-memory words (halo warp <-> compute warps hand-off)
+__device__ __forceinline__ int ld_acquire_cta_shared(const int *p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cta_shared(int *p, int v) {
+    asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+// 16-byte asynchronous global -> shared copy, L2 only (.cg): never served from a stale L1 line
+__device__ __forceinline__ void cp_async_cg16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}

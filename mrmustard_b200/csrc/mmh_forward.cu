@@ -178,6 +178,22 @@ __global__ void __launch_bounds__(256) k_stable_coop(FwdParams p) {
     }
 }
 
+// One (stage, step) panel as a plain grid-stride kernel: used when the panel is too large for the tiled
+// march (e.g. the 35.8 M-point panels of an (12,)*8 lattice), where a launch per step costs nothing.
+__global__ void __launch_bounds__(256) k_panel_step(FwdParams p, int stage, int s) {
+    extern __shared__ c128 smem[];
+    c128 *sA = smem;
+    c128 *sb = smem + p.d.D * p.d.D;
+    load_Ab(p, 0, sA, sb);
+    __syncthreads();
+    const LatticeDesc &d = p.d;
+    const long long P = d.strides[stage];
+    c128 *G = p.G;
+    const long long base = (long long)s * P;
+    for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < P; f += (long long)gridDim.x * blockDim.x)
+        G[base + f] = vanilla_point(d, sA, sb, G, p.sq, p.rsq, stage, s, f);
+}
+
 // ---- binomial: level wavefront in one CTA with deterministic per-level norm and early stop ---------
 // (binomial.py:58-71, steps.py:208-235).  The vanilla update is used for every point of a level; the
 // reference additionally adds exact zeros for j < i (steps.py:63-64), which does not change the value.
@@ -260,6 +276,11 @@ cudaError_t mmh_launch_fwd_coop(const FwdParams &p, bool stable, int grid, int b
     void *args[] = { (void *)&p };
     if (stable) return cudaLaunchCooperativeKernel((void *)k_stable_coop, dim3(grid), dim3(block), args, smem, st);
     return cudaLaunchCooperativeKernel((void *)k_fwd_coop, dim3(grid), dim3(block), args, smem, st);
+}
+
+cudaError_t mmh_launch_panel_step(const FwdParams &p, int stage, int s, int grid, size_t smem, cudaStream_t st) {
+    k_panel_step<<<grid, 256, smem, st>>>(p, stage, s);
+    return cudaGetLastError();
 }
 
 cudaError_t mmh_launch_binomial(const BinomParams &p, int block, size_t smem, cudaStream_t st) {

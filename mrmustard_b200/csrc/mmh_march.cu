@@ -188,3 +188,279 @@ cudaError_t mmh_launch_chain(const FwdParams &p, cudaStream_t st) {
     k_fwd_chain<<<(unsigned)grid, block, 0, st>>>(p);
     return cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------------------------------
+// K1: tiled march of ONE lattice over many CTAs.
+//
+// The panel of stage i is cut into a grid of boxes over its first nt (<= 3) dims; CTA t owns box t for
+// the whole march.  A point k reads G[k - e_i - e_j] (j > i), i.e. the cell one lower in panel dim j of
+// panel s-1: either inside the box (shared memory, written by the CTA one step earlier) or in the one-
+// cell "low" halo that belongs to the lower neighbour box.  Dependencies only point to LOWER tiles, so
+// the exchange is a one-directional pipeline: a tile publishes `done[tile] = s` (release) after panel s
+// is in L2; warp 0 of every CTA is a dedicated halo prefetcher that watches the neighbours' counters
+// (acquire), pulls their boundary cells of panel u with cp.async.cg (L2 only) into a 4-deep shared-
+// memory ring, up to 3 panels ahead of the compute warps, and hands them over with CTA-scope
+// release/acquire words.  In steady state the lower neighbour runs a few panels ahead and no L2
+// latency is exposed; the skew costs one L2 round trip per tile-grid hop, once.
+// ---------------------------------------------------------------------------------------------------
+#define MMH_KRING 4
+
+template <int R, int NPD>
+__global__ void __launch_bounds__(288, 1) k_march_tiled(TiledParams p) {
+    extern __shared__ c128 smem[];
+    const LatticeDesc &d = p.d;
+    const int D = d.D;
+    const int i = p.stage;
+    const long long P = d.strides[i];
+    const int S = d.shape[i];
+    const int TC = p.tc;
+    const int tid = threadIdx.x;
+    const int tidc = tid - 32;
+    const int nt = p.nt;
+    const double *__restrict__ sq = p.sq;
+    const double *__restrict__ rsq = p.rsq;
+
+    // ---- tile geometry ----------------------------------------------------------------------------------
+    int g[3], t[3], lo[3], e[3], h[3], gst[3];
+#pragma unroll
+    for (int m = 0; m < 3; m++) g[m] = m < nt ? p.g[m] : 1;
+    const int tile = blockIdx.x;
+    t[2] = tile % g[2];
+    t[1] = (tile / g[2]) % g[1];
+    t[0] = tile / (g[1] * g[2]);
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        if (m < nt) {
+            const int sh = d.shape[i + 1 + m];
+            lo[m] = (int)(((long long)t[m] * sh) / g[m]);
+            e[m] = (int)(((long long)(t[m] + 1) * sh) / g[m]) - lo[m];
+            h[m] = lo[m] > 0 ? 1 : 0;
+            gst[m] = (int)d.strides[i + 1 + m];
+        } else { lo[m] = 0; e[m] = 1; h[m] = 0; gst[m] = 0; }
+    }
+    const int inner = (int)d.strides[i + nt];
+    int lst[3];
+    lst[2] = inner;
+    lst[1] = lst[2] * (e[2] + h[2]);
+    lst[0] = lst[1] * (e[1] + h[1]);
+    const int LS = lst[0] * (e[0] + h[0]);
+    const int TS = e[0] * e[1] * e[2] * inner;
+    int faceoff[3];
+    faceoff[0] = 0;
+    faceoff[1] = faceoff[0] + h[0] * (TS / e[0]);
+    faceoff[2] = faceoff[1] + h[1] * (TS / e[1]);
+    const int HC = faceoff[2] + h[2] * (TS / e[2]);
+
+    c128 *buf = smem;                         // [2][LS]
+    c128 *ring = smem + 2 * (size_t)p.ls_max; // [KRING][hc_max]
+    int *hal_gofs = (int *)(ring + MMH_KRING * (size_t)p.hc_max);
+    int *sync_words = hal_gofs + p.hc_max;    // [0] = hready, [1] = cdone
+    const int ringstride = p.hc_max;
+
+    // ---- halo cell table: global panel offset of every halo cell ---------------------------------------------
+    for (int c = tid; c < HC; c += blockDim.x) {
+        int m = 0;
+        if (c >= faceoff[2] && h[2]) m = 2;
+        else if (c >= faceoff[1] && h[1]) m = 1;
+        int cc = c - faceoff[m];
+        const int a = m == 0 ? 1 : 0, b = m == 2 ? 1 : 2;  // the two other tiled dims, in order
+        const int rr = cc % inner; cc /= inner;
+        const int xb = cc % e[b], xa = cc / e[b];
+        hal_gofs[c] = (lo[m] - 1) * gst[m] + (lo[a] + xa) * gst[a] + (lo[b] + xb) * gst[b] + rr;
+    }
+    if (tid == 0) { sync_words[0] = 0; sync_words[1] = 0; }
+    __syncthreads();
+    // panel 0 halo -> ring slot 0 (panel 0 is final: the previous stage's kernel has completed)
+    for (int c = tid; c < HC; c += blockDim.x) ring[c] = __ldcg(p.G + hal_gofs[c]);
+
+    const c128 b0 = p.b[i], a00 = p.A[i * D + i];
+
+    // ---- per-slot constants (compute warps) -----------------------------------------------------------------
+    bool act[R];
+    unsigned hm[R];             // bit jj: neighbour jj lives in the halo ring
+    int loc[R];
+    int nbi[R][NPD];
+    c128 coef[R][NPD];
+    c128 *gp[R];
+    c128 h0[R], h1[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int q = r * TC + tidc;
+        act[r] = tidc >= 0 && q < TS;
+        hm[r] = 0u;
+        const int qq = act[r] ? q : 0;
+        const int rr = qq % inner;
+        int q1 = qq / inner;
+        int x[3];
+        x[2] = q1 % e[2]; q1 /= e[2];
+        x[1] = q1 % e[1];
+        x[0] = q1 / e[1];
+        loc[r] = (x[0] + h[0]) * lst[0] + (x[1] + h[1]) * lst[1] + (x[2] + h[2]) * lst[2] + rr;
+        const int f = (lo[0] + x[0]) * gst[0] + (lo[1] + x[1]) * gst[1] + (lo[2] + x[2]) * gst[2] + rr;
+        gp[r] = p.G + f;
+        int rem = rr;
+#pragma unroll
+        for (int jj = 0; jj < NPD; jj++) {
+            const int j = i + 1 + jj;
+            int k, nb;
+            bool halo = false;
+            if (jj < nt) {
+                k = lo[jj] + x[jj];
+                if (x[jj] > 0) nb = loc[r] - lst[jj];
+                else {  // lower neighbour is a halo cell (or does not exist when k == 0)
+                    halo = true;
+                    const int a = jj == 0 ? 1 : 0, b = jj == 2 ? 1 : 2;
+                    nb = faceoff[jj] + (x[a] * e[b] + x[b]) * inner + rr;
+                }
+            } else {
+                const int sj = (int)d.strides[j];
+                k = rem / sj;
+                rem -= k * sj;
+                nb = loc[r] - sj;
+            }
+            const bool has = act[r] && k > 0;
+            if (!has) { nb = loc[r]; halo = false; }
+            nbi[r][jj] = nb;
+            if (halo) hm[r] |= 1u << jj;
+            coef[r][jj] = has ? c_scale(p.A[i * D + j], sq[k]) : c_make(0.0, 0.0);
+        }
+        h0[r] = c_make(0.0, 0.0);
+        h1[r] = act[r] ? __ldcg(gp[r]) : c_make(0.0, 0.0);
+        if (act[r]) buf[loc[r]] = h1[r];
+    }
+    __syncthreads();
+
+    if (tid < 32) {
+        // ================= halo prefetch warp =================
+        if (HC == 0) return;
+        const int lane = tid;
+        unsigned *myflag = nullptr;
+        if (lane < 3 && h[lane]) {
+            int nb_tile = tile;
+            nb_tile -= lane == 0 ? g[1] * g[2] : (lane == 1 ? g[2] : 1);
+            myflag = p.flags + nb_tile;
+        }
+        unsigned seen = 0;
+        for (int u = 1; u <= S - 2; u++) {
+            if (u - MMH_KRING + 1 >= 1) {   // ring slot of panel u-KRING must have been consumed
+                if (lane == 0) while (ld_acquire_cta_shared(&sync_words[1]) < u - MMH_KRING + 1) { }
+                __syncwarp();
+            }
+            if (myflag) while (seen < (unsigned)u) seen = ld_acquire_u32(myflag);
+            __syncwarp();
+            c128 *dst = ring + (size_t)(u % MMH_KRING) * ringstride;
+            const c128 *src = p.G + (long long)u * P;
+            for (int c = lane; c < HC; c += 32) cp_async_cg16(dst + c, src + hal_gofs[c]);
+            cp_async_commit();
+            cp_async_wait<1>();
+            __syncwarp();
+            if (lane == 0 && u >= 2) st_release_cta_shared(&sync_words[0], u - 1);
+        }
+        cp_async_wait<0>();
+        __syncwarp();
+        if (lane == 0 && S - 2 >= 1) st_release_cta_shared(&sync_words[0], S - 2);
+        return;
+    }
+
+    // ================= compute warps =================
+#define MMH_TILED_STEP(P1, P2, OFFP, OFFC, OFFH)                                                      \
+    {                                                                                                 \
+        c128 v[R], qq[R];                                                                             \
+        _Pragma("unroll") for (int r = 0; r < R; r++) {                                               \
+            v[r] = c_mul(b0, P1[r]);                                                                  \
+            v[r] = c_add(v[r], c_mul(c_scale(a00, sqm), P2[r]));                                      \
+            _Pragma("unroll") for (int jj = 0; jj < NPD; jj++) {                                      \
+                const c128 *src = ((hm[r] >> jj) & 1u) ? ring + (OFFH) : buf + (OFFP);                \
+                v[r] = c_add(v[r], c_mul(coef[r][jj], src[nbi[r][jj]]));                              \
+            }                                                                                         \
+        }                                                                                             \
+        bool slow = false;                                                                            \
+        _Pragma("unroll") for (int r = 0; r < R; r++) {                                               \
+            qq[r] = c_make(div_fast(v[r].x, sqs, rsqs), div_fast(v[r].y, sqs, rsqs));                 \
+            slow |= div_needs_slow(v[r].x) | div_needs_slow(v[r].y);                                  \
+        }                                                                                             \
+        if (slow) {                                                                                   \
+            _Pragma("unroll") for (int r = 0; r < R; r++) {                                           \
+                if (div_needs_slow(v[r].x)) qq[r].x = __ddiv_rn(v[r].x, sqs);                         \
+                if (div_needs_slow(v[r].y)) qq[r].y = __ddiv_rn(v[r].y, sqs);                         \
+            }                                                                                         \
+        }                                                                                             \
+        _Pragma("unroll") for (int r = 0; r < R; r++) {                                               \
+            P2[r] = qq[r];                                                                            \
+            if (act[r]) {                                                                             \
+                gp[r] += P;                                                                           \
+                *gp[r] = qq[r];                                                                       \
+                buf[(OFFC) + loc[r]] = qq[r];                                                         \
+            }                                                                                         \
+        }                                                                                             \
+    }
+#define MMH_TILED_SYNC(SDONE)                                                                         \
+    {                                                                                                 \
+        named_barrier_sync(1, TC);                                                                    \
+        if (tidc == 0) {                                                                              \
+            st_release_cta_shared(&sync_words[1], (SDONE));                                           \
+            __threadfence();                                                                          \
+            st_release_u32(p.flags + tile, (unsigned)(SDONE));                                        \
+        }                                                                                             \
+    }
+#define MMH_TILED_WAIT(SNEED)                                                                         \
+    if (HC > 0 && (SNEED) >= 1) { while (ld_acquire_cta_shared(&sync_words[0]) < (SNEED)) { } }
+
+    double sqm = 0.0, sqs = sq[S > 1 ? 1 : 0], rsqs = rsq[S > 1 ? 1 : 0];
+    const int LSm = p.ls_max;
+    int s = 1;
+    for (; s + 1 < S; s += 2) {
+        const double sq1 = sq[s + 1], rsq1 = rsq[s + 1];
+        const int s2 = s + 2 < S ? s + 2 : s + 1;
+        const double sq2 = sq[s2], rsq2 = rsq[s2];
+        MMH_TILED_WAIT(s - 1)
+        MMH_TILED_STEP(h1, h0, 0, LSm, ((s - 1) % MMH_KRING) * ringstride)
+        MMH_TILED_SYNC(s)
+        sqm = sqs; sqs = sq1; rsqs = rsq1;
+        MMH_TILED_WAIT(s)
+        MMH_TILED_STEP(h0, h1, LSm, 0, (s % MMH_KRING) * ringstride)
+        MMH_TILED_SYNC(s + 1)
+        sqm = sqs; sqs = sq2; rsqs = rsq2;
+    }
+    if (s < S) {
+        MMH_TILED_WAIT(s - 1)
+        MMH_TILED_STEP(h1, h0, 0, LSm, ((s - 1) % MMH_KRING) * ringstride)
+        MMH_TILED_SYNC(s)
+    }
+#undef MMH_TILED_STEP
+#undef MMH_TILED_SYNC
+#undef MMH_TILED_WAIT
+}
+
+template <int R>
+static cudaError_t launch_tiled_R(const TiledParams &p, int ntiles, size_t smem, cudaStream_t st) {
+    const int block = p.tc + 32;
+#define MMH_CASE(N)                                                                                   \
+    case N:                                                                                           \
+        if (smem > 48 * 1024)                                                                         \
+            cudaFuncSetAttribute(k_march_tiled<R, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        k_march_tiled<R, N><<<ntiles, block, smem, st>>>(p);                                          \
+        return cudaGetLastError();
+    const int npd = p.d.D - 1 - p.stage;
+    switch (npd) {
+        MMH_CASE(1) MMH_CASE(2) MMH_CASE(3)
+        default: break;
+    }
+    if constexpr (R <= 2) {
+        switch (npd) { MMH_CASE(4) MMH_CASE(5) MMH_CASE(6) default: break; }
+    }
+    if constexpr (R == 1) {
+        switch (npd) { MMH_CASE(7) default: break; }
+    }
+#undef MMH_CASE
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t mmh_launch_march_tiled(const TiledParams &p, int R, int ntiles, size_t smem, cudaStream_t st) {
+    switch (R) {
+        case 1: return launch_tiled_R<1>(p, ntiles, smem, st);
+        case 2: return launch_tiled_R<2>(p, ntiles, smem, st);
+        case 4: return launch_tiled_R<4>(p, ntiles, smem, st);
+        default: return cudaErrorInvalidValue;
+    }
+}

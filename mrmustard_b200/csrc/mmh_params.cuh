@@ -49,10 +49,26 @@ struct StageParams {
     int L;                       // lattices marched in lock step by one CTA
 };
 
+struct TiledParams {
+    LatticeDesc d;
+    const c128 *A, *b;           // one triple
+    c128 *G;                     // one lattice
+    const double *sq, *rsq;
+    unsigned *flags;             // [ntiles] progress counters, zeroed before the launch
+    int stage;                   // i: the index being marched
+    int nt;                      // number of tiled panel dims (1..3): dims stage+1 .. stage+nt
+    int g[3];                    // tile grid
+    int tc;                      // compute threads (multiple of 32); the CTA has tc + 32 threads
+    int ls_max;                  // shared-memory stride of one panel buffer (>= local box size of any tile)
+    int hc_max;                  // shared-memory stride of one halo ring slot (>= halo cells of any tile)
+};
+
+cudaError_t mmh_launch_march_tiled(const TiledParams &p, int R, int ntiles, size_t smem, cudaStream_t st);
 cudaError_t mmh_launch_march_stage(const StageParams &p, int R, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t mmh_launch_chain(const FwdParams &p, cudaStream_t st);
 cudaError_t mmh_launch_fwd_cta(const FwdParams &p, bool stable, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t mmh_coop_max_blocks(bool stable, int block, size_t smem, int *per_sm);
 cudaError_t mmh_launch_fwd_coop(const FwdParams &p, bool stable, int grid, int block, size_t smem, cudaStream_t st);
+cudaError_t mmh_launch_panel_step(const FwdParams &p, int stage, int s, int grid, size_t smem, cudaStream_t st);
 cudaError_t mmh_launch_binomial(const BinomParams &p, int block, size_t smem, cudaStream_t st);
 cudaError_t mmh_launch_vjp(const VjpParams &p, int grid_y, int block, cudaStream_t st);

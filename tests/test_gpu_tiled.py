@@ -1,0 +1,63 @@
+"""GPU parity tests of the tiled multi-CTA march (k_march_tiled): one lattice cut into tile-owner CTAs that
+exchange one-cell halos through L2 with release/acquire progress counters.  Small lattices are forced through
+that path (MMH_FORCE_TILED, MMH_TILE_G are test hooks read by the library at call time) with many tile-grid
+shapes, and must be bit-identical to the oracle."""
+import numpy as np
+import pytest
+
+from conftest import random_triple, sha
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def S():
+    from mrmustard_b200 import strategies
+    return strategies
+
+
+@pytest.fixture(scope="module")
+def O():
+    import oracle
+    return oracle
+
+
+CASES = [
+    ((9, 8, 7, 6), ["1,1,1", "2,2,2", "3,1,2", "1,1,3", "2,4,1", "4,3,3"]),
+    ((7, 20, 19), ["1,1", "2,2", "5,1", "1,6", "7,7"]),
+    ((12, 33), ["1", "2", "5", "11"]),
+    ((5, 6, 5, 4, 3), ["2,2,2", "3,1,1", "1,2,3"]),
+    ((3, 4, 3, 2, 3, 2), ["2,2,1", "1,3,2"]),
+    ((2, 3, 2, 3, 2, 3, 2, 3), ["2,1,2"]),
+    ((6, 1, 5, 1, 4), ["1,2,1", "1,5,1"]),
+]
+
+
+@pytest.mark.parametrize("shape,grids", CASES)
+def test_forced_tiled_vs_oracle(S, O, monkeypatch, shape, grids):
+    A, b, c = random_triple(len(shape), (), seed=7 + len(shape))
+    want = O.vanilla(shape, A, b, complex(c))
+    monkeypatch.setenv("MMH_FORCE_TILED", "1")
+    for g in grids:
+        monkeypatch.setenv("MMH_TILE_G", g)
+        got = S.vanilla_numba(shape, A, b, complex(c))
+        assert np.array_equal(got, want), f"shape {shape} tile grid {g}"
+    monkeypatch.delenv("MMH_TILE_G")
+    assert np.array_equal(S.vanilla_numba(shape, A, b, complex(c)), want)   # planner's own choice
+
+
+def test_default_path_large_lattices(S, O, golden):
+    # default planner on lattices large enough for the multi-CTA path
+    for shape, seed in [((40, 41, 42), 1), ((24, 25, 26, 27), 2), ((300, 300), 3), ((8,) * 6, 4), ((50, 3000), 5)]:
+        A, b, c = random_triple(len(shape), (), seed=seed)
+        assert np.array_equal(S.vanilla_numba(shape, A, b, complex(c)), O.vanilla(shape, A, b, complex(c))), shape
+    A, b, c = golden["cfg2_A"], golden["cfg2_b"], complex(golden["cfg2_c"])
+    for _ in range(3):   # repeated launches reuse/rotate the flag words
+        assert sha(S.vanilla_numba((50,) * 4, A, b, c)) == str(golden["cfg2_G50_sha"])
+
+
+def test_giant_panel_fallback(S, O):
+    # stage-0 panel of 1.77 M points: too large for the tiled march -> per-step launches (k_panel_step)
+    shape = (3, 11, 11, 11, 11, 11, 11)
+    A, b, c = random_triple(len(shape), (), seed=9)
+    assert np.array_equal(S.vanilla_numba(shape, A, b, complex(c)), O.vanilla(shape, A, b, complex(c)))

@@ -23,8 +23,6 @@
 static std::atomic<long long> g_launches{0};
 static std::mutex g_mutex;
 
-static const int kFlagWords = 1 << 16;
-
 // ---- per-device context ---------------------------------------------------------------------------
 struct Scratch {
     void *ptr = nullptr;
@@ -38,8 +36,7 @@ struct DeviceCtx {
     int table_len = 0;
     unsigned *barrier = nullptr;  // 64 counters; one is consumed per cooperative launch (round robin)
     int barrier_next = 0;
-    unsigned *flags = nullptr;    // tile progress counters for the tiled march (kFlagWords, used round robin)
-    int flags_next = 0;
+    Scratch xbuf;                 // halo exchange buffer of the tiled march; all-ones sentinel between launches
     Scratch partial;              // VJP partial sums
     Scratch norm;                 // binomial norm scalar
     Scratch host_slots[8];        // staging for the *_host entry points
@@ -90,8 +87,6 @@ static int get_ctx(DeviceCtx **out) {
         c.cc_major = prop.major;
         CK(cudaMalloc(&c.barrier, 64 * sizeof(unsigned)));
         CK(cudaMemset(c.barrier, 0, 64 * sizeof(unsigned)));
-        CK(cudaMalloc(&c.flags, kFlagWords * sizeof(unsigned)));
-        CK(cudaMemset(c.flags, 0, kFlagWords * sizeof(unsigned)));
         c.init = true;
     }
     *out = &c;
@@ -217,12 +212,16 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
                 long long HC = 0;
                 for (int m = 0; m < 3; m++) if (g[m] > 1) HC += TS / e[m];
                 const long long HCs = HC > 0 ? HC : 1;   // the kernel lays the ring out with stride hc_max >= 1
-                const size_t smem = sizeof(c128) * (size_t)(2 * LS + MMH_KRING_HOST * HCs) + sizeof(int) * (size_t)(HCs + 4);
+                const size_t smem = sizeof(c128) * (size_t)(2 * LS + MMH_KRING_HOST * HCs) + sizeof(int) * (size_t)(HCs + 16);
                 if (smem > 200 * 1024) continue;
                 int R = 0;
                 const int Rs[3] = { 1, 2, 4 };
-                for (int r = 0; r < 3; r++)
-                    if ((long long)Rs[r] * 256 >= TS && (Rs[r] == 1 || Rs[r] * npd <= 12)) { R = Rs[r]; break; }
+                const char *eR = getenv("MMH_TILE_R");
+                for (int r = 0; r < 3; r++) {
+                    const int tcmax = Rs[r] == 4 ? 256 : 512;
+                    if (eR && atoi(eR) != Rs[r]) continue;
+                    if ((long long)Rs[r] * tcmax >= TS && (Rs[r] == 1 || Rs[r] * npd <= 12)) { R = Rs[r]; break; }
+                }
                 if (!R) continue;
                 const int TC = round_up32((TS + R - 1) / R);
                 double step_us = (double)TS * 0.55e-3;          // ~0.55 ns per amplitude per SM (FP64 pipe)
@@ -251,6 +250,7 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
     g_launches++;
     CK(mmh_launch_chain(p, st));
     const size_t absmem = sizeof(c128) * (size_t)(D * D + D);
+    int rc;
     for (int i = D - 2; i >= 0; i--) {
         if (d.shape[i] == 1) continue;
         int L, R, T, ntiles;
@@ -264,12 +264,36 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
             CK(mmh_launch_march_stage(sp, R, 1, T, sm, st));
         } else if (plan_march_tiled(d, i, ctx->sm_count, &tp, &R, &ntiles, &sm)) {
             tp.A = p.A; tp.b = p.b; tp.G = p.G; tp.sq = p.sq; tp.rsq = p.rsq;
-            if (ctx->flags_next + ntiles > kFlagWords) ctx->flags_next = 0;
-            tp.flags = ctx->flags + ctx->flags_next;
-            ctx->flags_next += ntiles;
-            CK(cudaMemsetAsync(tp.flags, 0, sizeof(unsigned) * ntiles, st));
+            {   // exchange buffer: grow-only scratch, (re)filled with the sentinel whenever it is (re)allocated
+                const size_t xbytes = sizeof(c128) * (size_t)ntiles * d.shape[i] * tp.hc_max;
+                if (ctx->xbuf.bytes < xbytes || !ctx->xbuf.ptr) {
+                    if ((rc = ensure_scratch(ctx->xbuf, xbytes))) return rc;
+                    CK(cudaMemset(ctx->xbuf.ptr, 0xFF, ctx->xbuf.bytes));
+                }
+                tp.X = (c128 *)ctx->xbuf.ptr;
+            }
+            const char *trace_file = getenv("MMH_TRACE_FILE");   // debug timeline of the tile pipeline
+            const size_t trace_words = (size_t)ntiles * d.shape[i] * 4;
+            if (trace_file) {
+                CK(cudaMalloc(&tp.trace, trace_words * 8));
+                CK(cudaMemset(tp.trace, 0, trace_words * 8));
+            }
             g_launches++;
             CK(mmh_launch_march_tiled(tp, R, ntiles, sm, st));
+            if (trace_file) {
+                std::vector<unsigned long long> h(trace_words);
+                CK(cudaStreamSynchronize(st));
+                CK(cudaMemcpy(h.data(), tp.trace, trace_words * 8, cudaMemcpyDeviceToHost));
+                CK(cudaFree(tp.trace));
+                char name[512];
+                snprintf(name, sizeof(name), "%s.stage%d.bin", trace_file, i);
+                if (FILE *fp = fopen(name, "wb")) {
+                    const int hdr[8] = { ntiles, d.shape[i], tp.g[0], tp.g[1], tp.g[2], R, tp.tc, 0 };
+                    fwrite(hdr, sizeof(int), 8, fp);
+                    fwrite(h.data(), 8, trace_words, fp);
+                    fclose(fp);
+                }
+            }
         } else {
             const long long P = d.strides[i];
             long long grid = (P + 255) / 256;

@@ -196,17 +196,34 @@ cudaError_t mmh_launch_chain(const FwdParams &p, cudaStream_t st) {
 // the whole march.  A point k reads G[k - e_i - e_j] (j > i), i.e. the cell one lower in panel dim j of
 // panel s-1: either inside the box (shared memory, written by the CTA one step earlier) or in the one-
 // cell "low" halo that belongs to the lower neighbour box.  Dependencies only point to LOWER tiles, so
-// the exchange is a one-directional pipeline: a tile publishes `done[tile] = s` (release) after panel s
-// is in L2; warp 0 of every CTA is a dedicated halo prefetcher that watches the neighbours' counters
-// (acquire), pulls their boundary cells of panel u with cp.async.cg (L2 only) into a 4-deep shared-
-// memory ring, up to 3 panels ahead of the compute warps, and hands them over with CTA-scope
-// release/acquire words.  In steady state the lower neighbour runs a few panels ahead and no L2
-// latency is exposed; the skew costs one L2 round trip per tile-grid hop, once.
+// the exchange is a one-directional pipeline with no global barrier.
+//
+// Halo exchange without fences or flags: besides its lattice entry, a producer stores every amplitude
+// on a high face of its box into an exchange buffer X[consumer tile][panel][cell].  X is kept filled
+// with a sentinel (all-ones bit pattern, a NaN no FP64 instruction can produce); the consumer's halo
+// warps poll their cells with L1-bypassing loads until both 64-bit words of a cell differ from the
+// sentinel (64-bit stores are single-copy atomic, so every word validates itself), move the cell into a
+// 4-deep shared-memory ring, and write the sentinel back (self-cleaning).  One hop of the tile pipeline
+// therefore costs one L2 write + one L2 read instead of fence + flag + poll + fetch.
 // ---------------------------------------------------------------------------------------------------
 #define MMH_KRING 4
+#define MMH_NHW 2   // halo warps per CTA (panel u is served by warp u % MMH_NHW)
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void ld_relaxed_v2_u64(const void *p, unsigned long long &a, unsigned long long &b) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_v2_u64(void *p, unsigned long long a, unsigned long long b) {
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+#define MMH_SENTINEL 0xFFFFFFFFFFFFFFFFull
 
 template <int R, int NPD>
-__global__ void __launch_bounds__(288, 1) k_march_tiled(TiledParams p) {
+__global__ void __launch_bounds__((R >= 4 ? 256 : 512) + 32 * MMH_NHW, 1) k_march_tiled(TiledParams p) {
     extern __shared__ c128 smem[];
     const LatticeDesc &d = p.d;
     const int D = d.D;
@@ -215,13 +232,13 @@ __global__ void __launch_bounds__(288, 1) k_march_tiled(TiledParams p) {
     const int S = d.shape[i];
     const int TC = p.tc;
     const int tid = threadIdx.x;
-    const int tidc = tid - 32;
+    const int tidc = tid - 32 * MMH_NHW;
     const int nt = p.nt;
     const double *__restrict__ sq = p.sq;
     const double *__restrict__ rsq = p.rsq;
 
     // ---- tile geometry ----------------------------------------------------------------------------------
-    int g[3], t[3], lo[3], e[3], h[3], gst[3];
+    int g[3], t[3], lo[3], e[3], h[3], gst[3], shp[3];
 #pragma unroll
     for (int m = 0; m < 3; m++) g[m] = m < nt ? p.g[m] : 1;
     const int tile = blockIdx.x;
@@ -231,19 +248,18 @@ __global__ void __launch_bounds__(288, 1) k_march_tiled(TiledParams p) {
 #pragma unroll
     for (int m = 0; m < 3; m++) {
         if (m < nt) {
-            const int sh = d.shape[i + 1 + m];
-            lo[m] = (int)(((long long)t[m] * sh) / g[m]);
-            e[m] = (int)(((long long)(t[m] + 1) * sh) / g[m]) - lo[m];
+            shp[m] = d.shape[i + 1 + m];
+            lo[m] = (int)(((long long)t[m] * shp[m]) / g[m]);
+            e[m] = (int)(((long long)(t[m] + 1) * shp[m]) / g[m]) - lo[m];
             h[m] = lo[m] > 0 ? 1 : 0;
             gst[m] = (int)d.strides[i + 1 + m];
-        } else { lo[m] = 0; e[m] = 1; h[m] = 0; gst[m] = 0; }
+        } else { shp[m] = 1; lo[m] = 0; e[m] = 1; h[m] = 0; gst[m] = 0; }
     }
     const int inner = (int)d.strides[i + nt];
     int lst[3];
     lst[2] = inner;
     lst[1] = lst[2] * (e[2] + h[2]);
     lst[0] = lst[1] * (e[1] + h[1]);
-    const int LS = lst[0] * (e[0] + h[0]);
     const int TS = e[0] * e[1] * e[2] * inner;
     int faceoff[3];
     faceoff[0] = 0;
@@ -251,13 +267,14 @@ __global__ void __launch_bounds__(288, 1) k_march_tiled(TiledParams p) {
     faceoff[2] = faceoff[1] + h[1] * (TS / e[1]);
     const int HC = faceoff[2] + h[2] * (TS / e[2]);
 
-    c128 *buf = smem;                         // [2][LS]
+    c128 *buf = smem;                         // [2][ls_max]
     c128 *ring = smem + 2 * (size_t)p.ls_max; // [KRING][hc_max]
     int *hal_gofs = (int *)(ring + MMH_KRING * (size_t)p.hc_max);
-    int *sync_words = hal_gofs + p.hc_max;    // [0] = hready, [1] = cdone
+    int *sync_words = hal_gofs + p.hc_max;    // [0..KRING) = panel held by ring slot k ; [KRING] = cdone
     const int ringstride = p.hc_max;
+    const size_t xtile = (size_t)S * p.hc_max;   // X elements per consumer tile
 
-    // ---- halo cell table: global panel offset of every halo cell ---------------------------------------------
+    // ---- halo cell table: global panel offset of every halo cell (panel 0 is read from G itself) ---------------
     for (int c = tid; c < HC; c += blockDim.x) {
         int m = 0;
         if (c >= faceoff[2] && h[2]) m = 2;
@@ -268,7 +285,7 @@ __global__ void __launch_bounds__(288, 1) k_march_tiled(TiledParams p) {
         const int xb = cc % e[b], xa = cc / e[b];
         hal_gofs[c] = (lo[m] - 1) * gst[m] + (lo[a] + xa) * gst[a] + (lo[b] + xb) * gst[b] + rr;
     }
-    if (tid == 0) { sync_words[0] = 0; sync_words[1] = 0; }
+    if (tid <= MMH_KRING) sync_words[tid] = 0;
     __syncthreads();
     // panel 0 halo -> ring slot 0 (panel 0 is final: the previous stage's kernel has completed)
     for (int c = tid; c < HC; c += blockDim.x) ring[c] = __ldcg(p.G + hal_gofs[c]);
@@ -280,9 +297,17 @@ __global__ void __launch_bounds__(288, 1) k_march_tiled(TiledParams p) {
     unsigned hm[R];             // bit jj: neighbour jj lives in the halo ring
     int loc[R];
     int nbi[R][NPD];
+    int xo[R][3];               // offset of this amplitude inside the exchange block of the upper neighbour in
+                                // tiled dim m (panel 0), or -1 when the slot is not on that high face
     c128 coef[R][NPD];
     c128 *gp[R];
     c128 h0[R], h1[R];
+    c128 *xbase[3];             // exchange block of the upper neighbour tile in dim m
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        const int up = tile + (m == 0 ? g[1] * g[2] : (m == 1 ? g[2] : 1));
+        xbase[m] = p.X + (size_t)up * xtile;
+    }
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int q = r * TC + tidc;
@@ -324,46 +349,70 @@ __global__ void __launch_bounds__(288, 1) k_march_tiled(TiledParams p) {
             if (halo) hm[r] |= 1u << jj;
             coef[r][jj] = has ? c_scale(p.A[i * D + j], sq[k]) : c_make(0.0, 0.0);
         }
+        // high faces: where does the upper neighbour in dim m expect this amplitude?
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            xo[r][m] = -1;
+            if (act[r] && m < nt && t[m] + 1 < g[m] && x[m] == e[m] - 1) {
+                // the consumer box: same extents except in dim m
+                const int lo_up = (int)(((long long)(t[m] + 1) * shp[m]) / g[m]);
+                const int e_up = (int)(((long long)(t[m] + 2) * shp[m]) / g[m]) - lo_up;
+                int ec[3] = { e[0], e[1], e[2] }, hc[3] = { h[0], h[1], h[2] };
+                ec[m] = e_up; hc[m] = 1;
+                const int TSc = ec[0] * ec[1] * ec[2] * inner;
+                int fo = 0;
+                for (int mm = 0; mm < m; mm++) fo += hc[mm] * (TSc / ec[mm]);
+                const int a = m == 0 ? 1 : 0, b = m == 2 ? 1 : 2;
+                xo[r][m] = fo + (x[a] * ec[b] + x[b]) * inner + rr;
+            }
+        }
         h0[r] = c_make(0.0, 0.0);
         h1[r] = act[r] ? __ldcg(gp[r]) : c_make(0.0, 0.0);
         if (act[r]) buf[loc[r]] = h1[r];
     }
     __syncthreads();
 
-    if (tid < 32) {
-        // ================= halo prefetch warp =================
+    if (tid < 32 * MMH_NHW) {
+        // ================= halo warps: panel u is served by warp u % NHW =================
         if (HC == 0) return;
-        const int lane = tid;
-        unsigned *myflag = nullptr;
-        if (lane < 3 && h[lane]) {
-            int nb_tile = tile;
-            nb_tile -= lane == 0 ? g[1] * g[2] : (lane == 1 ? g[2] : 1);
-            myflag = p.flags + nb_tile;
-        }
-        unsigned seen = 0;
-        for (int u = 1; u <= S - 2; u++) {
+        const int lane = tid & 31, hw = tid >> 5;
+        c128 *xin = p.X + (size_t)tile * xtile;
+        for (int u = 1 + hw; u <= S - 2; u += MMH_NHW) {
             if (u - MMH_KRING + 1 >= 1) {   // ring slot of panel u-KRING must have been consumed
-                if (lane == 0) while (ld_acquire_cta_shared(&sync_words[1]) < u - MMH_KRING + 1) { }
+                if (lane == 0) while (ld_acquire_cta_shared(&sync_words[MMH_KRING]) < u - MMH_KRING + 1) { }
                 __syncwarp();
             }
-            if (myflag) while (seen < (unsigned)u) seen = ld_acquire_u32(myflag);
-            __syncwarp();
             c128 *dst = ring + (size_t)(u % MMH_KRING) * ringstride;
-            const c128 *src = p.G + (long long)u * P;
-            for (int c = lane; c < HC; c += 32) cp_async_cg16(dst + c, src + hal_gofs[c]);
-            cp_async_commit();
-            cp_async_wait<1>();
+            c128 *src = xin + (size_t)u * p.hc_max;
+            for (int c0 = lane; c0 < HC; c0 += 32 * 4) {
+                unsigned long long a[4], b[4];
+                bool need[4];
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const int c = c0 + 32 * w;
+                    need[w] = c < HC;
+                    if (need[w]) ld_relaxed_v2_u64(src + c, a[w], b[w]);
+                }
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const int c = c0 + 32 * w;
+                    if (!need[w]) continue;
+                    unsigned spins = 0;
+                    while ((a[w] == MMH_SENTINEL || b[w] == MMH_SENTINEL) && ++spins < (1u << 26))
+                        ld_relaxed_v2_u64(src + c, a[w], b[w]);
+                    dst[c] = make_double2(__longlong_as_double((long long)a[w]), __longlong_as_double((long long)b[w]));
+                    st_relaxed_v2_u64(src + c, MMH_SENTINEL, MMH_SENTINEL);   // self-cleaning
+                }
+            }
             __syncwarp();
-            if (lane == 0 && u >= 2) st_release_cta_shared(&sync_words[0], u - 1);
+            if (lane == 0) st_release_cta_shared(&sync_words[u % MMH_KRING], u);
+            if (p.trace && lane == 0) p.trace[((size_t)tile * S + u) * 4 + 3] = globaltimer_ns();
         }
-        cp_async_wait<0>();
-        __syncwarp();
-        if (lane == 0 && S - 2 >= 1) st_release_cta_shared(&sync_words[0], S - 2);
         return;
     }
 
     // ================= compute warps =================
-#define MMH_TILED_STEP(P1, P2, OFFP, OFFC, OFFH)                                                      \
+#define MMH_TILED_STEP(P1, P2, OFFP, OFFC, OFFH, SCUR)                                                \
     {                                                                                                 \
         c128 v[R], qq[R];                                                                             \
         _Pragma("unroll") for (int r = 0; r < R; r++) {                                               \
@@ -385,12 +434,18 @@ __global__ void __launch_bounds__(288, 1) k_march_tiled(TiledParams p) {
                 if (div_needs_slow(v[r].y)) qq[r].y = __ddiv_rn(v[r].y, sqs);                         \
             }                                                                                         \
         }                                                                                             \
+        const bool xch = (SCUR) <= S - 2;   /* the last panel has no consumer */                      \
         _Pragma("unroll") for (int r = 0; r < R; r++) {                                               \
             P2[r] = qq[r];                                                                            \
             if (act[r]) {                                                                             \
                 gp[r] += P;                                                                           \
                 *gp[r] = qq[r];                                                                       \
                 buf[(OFFC) + loc[r]] = qq[r];                                                         \
+                _Pragma("unroll") for (int m = 0; m < 3; m++)                                         \
+                    if (xch && xo[r][m] >= 0)                                                         \
+                        st_relaxed_v2_u64(xbase[m] + (size_t)(SCUR) * p.hc_max + xo[r][m],            \
+                                          (unsigned long long)__double_as_longlong(qq[r].x),          \
+                                          (unsigned long long)__double_as_longlong(qq[r].y));         \
             }                                                                                         \
         }                                                                                             \
     }
@@ -398,13 +453,16 @@ __global__ void __launch_bounds__(288, 1) k_march_tiled(TiledParams p) {
     {                                                                                                 \
         named_barrier_sync(1, TC);                                                                    \
         if (tidc == 0) {                                                                              \
-            st_release_cta_shared(&sync_words[1], (SDONE));                                           \
-            __threadfence();                                                                          \
-            st_release_u32(p.flags + tile, (unsigned)(SDONE));                                        \
+            if (p.trace) p.trace[((size_t)tile * S + (SDONE)) * 4 + 1] = globaltimer_ns();            \
+            st_release_cta_shared(&sync_words[MMH_KRING], (SDONE));                                   \
         }                                                                                             \
     }
 #define MMH_TILED_WAIT(SNEED)                                                                         \
-    if (HC > 0 && (SNEED) >= 1) { while (ld_acquire_cta_shared(&sync_words[0]) < (SNEED)) { } }
+    if (HC > 0 && (SNEED) >= 1) {                                                                     \
+        unsigned spins = 0;                                                                           \
+        while (ld_acquire_cta_shared(&sync_words[(SNEED) % MMH_KRING]) < (SNEED) && ++spins < (1u << 28)) { } \
+    }                                                                                                 \
+    if (p.trace && tidc == 0) p.trace[((size_t)tile * S + (SNEED) + 1) * 4 + 0] = globaltimer_ns();
 
     double sqm = 0.0, sqs = sq[S > 1 ? 1 : 0], rsqs = rsq[S > 1 ? 1 : 0];
     const int LSm = p.ls_max;
@@ -414,17 +472,17 @@ __global__ void __launch_bounds__(288, 1) k_march_tiled(TiledParams p) {
         const int s2 = s + 2 < S ? s + 2 : s + 1;
         const double sq2 = sq[s2], rsq2 = rsq[s2];
         MMH_TILED_WAIT(s - 1)
-        MMH_TILED_STEP(h1, h0, 0, LSm, ((s - 1) % MMH_KRING) * ringstride)
+        MMH_TILED_STEP(h1, h0, 0, LSm, ((s - 1) % MMH_KRING) * ringstride, s)
         MMH_TILED_SYNC(s)
         sqm = sqs; sqs = sq1; rsqs = rsq1;
         MMH_TILED_WAIT(s)
-        MMH_TILED_STEP(h0, h1, LSm, 0, (s % MMH_KRING) * ringstride)
+        MMH_TILED_STEP(h0, h1, LSm, 0, (s % MMH_KRING) * ringstride, s + 1)
         MMH_TILED_SYNC(s + 1)
         sqm = sqs; sqs = sq2; rsqs = rsq2;
     }
     if (s < S) {
         MMH_TILED_WAIT(s - 1)
-        MMH_TILED_STEP(h1, h0, 0, LSm, ((s - 1) % MMH_KRING) * ringstride)
+        MMH_TILED_STEP(h1, h0, 0, LSm, ((s - 1) % MMH_KRING) * ringstride, s)
         MMH_TILED_SYNC(s)
     }
 #undef MMH_TILED_STEP
@@ -434,7 +492,7 @@ __global__ void __launch_bounds__(288, 1) k_march_tiled(TiledParams p) {
 
 template <int R>
 static cudaError_t launch_tiled_R(const TiledParams &p, int ntiles, size_t smem, cudaStream_t st) {
-    const int block = p.tc + 32;
+    const int block = p.tc + 32 * MMH_NHW;
 #define MMH_CASE(N)                                                                                   \
     case N:                                                                                           \
         if (smem > 48 * 1024)                                                                         \

@@ -54,13 +54,14 @@ struct TiledParams {
     const c128 *A, *b;           // one triple
     c128 *G;                     // one lattice
     const double *sq, *rsq;
-    unsigned *flags;             // [ntiles] progress counters, zeroed before the launch
+    c128 *X;                     // halo exchange buffer [ntiles][shape[stage]][hc_max], all-sentinel between launches
     int stage;                   // i: the index being marched
     int nt;                      // number of tiled panel dims (1..3): dims stage+1 .. stage+nt
     int g[3];                    // tile grid
-    int tc;                      // compute threads (multiple of 32); the CTA has tc + 32 threads
+    int tc;                      // compute threads (multiple of 32); the CTA adds its halo warps on top
     int ls_max;                  // shared-memory stride of one panel buffer (>= local box size of any tile)
     int hc_max;                  // shared-memory stride of one halo ring slot (>= halo cells of any tile)
+    unsigned long long *trace;   // debug timeline [tile][step][4] of %globaltimer stamps (MMH_TRACE_FILE), else NULL
 };
 
 cudaError_t mmh_launch_march_tiled(const TiledParams &p, int R, int ntiles, size_t smem, cudaStream_t st);

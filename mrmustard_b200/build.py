@@ -49,7 +49,7 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return SO
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", SO, *sources()]
+    cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("MMH_NVCC_EXTRA", "").split(), "-o", SO, *sources()]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(CSRC, "build.log"), "w") as f:

@@ -36,6 +36,7 @@ struct DeviceCtx {
     int table_len = 0;
     unsigned *barrier = nullptr;  // 64 counters; one is consumed per cooperative launch (round robin)
     int barrier_next = 0;
+    int cslot_next = 0;           // ring of constant-memory slots for the tiled march (MMH_CSLOTS)
     Scratch xbuf;                 // halo exchange buffer of the tiled march; all-ones sentinel between launches
     Scratch partial;              // VJP partial sums
     Scratch norm;                 // binomial norm scalar
@@ -195,7 +196,7 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
     int forced[3] = { 0, 0, 0 };
     if (const char *eg = getenv("MMH_TILE_G")) sscanf(eg, "%d,%d,%d", &forced[0], &forced[1], &forced[2]);
     double best = 1e300;
-    int bg[3] = { 0, 0, 0 }, bR = 0, bTC = 0, bLS = 0, bHC = 0;
+    int bg[3] = { 0, 0, 0 }, bR = 0, bTC = 0, bLS = 0, bHC = 0, bSq = 0;
     for (int g0 = 1; g0 <= shp[0] && g0 <= sm_count; g0++)
         for (int g1 = 1; g1 <= shp[1] && g0 * g1 <= sm_count; g1++)
             for (int g2 = 1; g2 <= shp[2] && g0 * g1 * g2 <= sm_count; g2++) {
@@ -212,8 +213,7 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
                 long long HC = 0;
                 for (int m = 0; m < 3; m++) if (g[m] > 1) HC += TS / e[m];
                 const long long HCs = HC > 0 ? HC : 1;   // the kernel lays the ring out with stride hc_max >= 1
-                const size_t smem = sizeof(c128) * (size_t)(2 * LS + MMH_KRING_HOST * HCs) + sizeof(int) * (size_t)(HCs + 16);
-                if (smem > 200 * 1024) continue;
+                size_t smem = sizeof(c128) * (size_t)(2 * LS + MMH_KRING_HOST * HCs) + sizeof(int) * (size_t)(HCs + 16);
                 int R = 0;
                 const int Rs[3] = { 1, 2, 4 };
                 const char *eR = getenv("MMH_TILE_R");
@@ -224,11 +224,17 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
                 }
                 if (!R) continue;
                 const int TC = round_up32((TS + R - 1) / R);
+                smem += sizeof(int) * 3 * (size_t)R * TC;   // export offsets
+                smem = (smem + 15) / 16 * 16;
+                const size_t sqtab_off = smem / 16;
+                smem += sizeof(c128) * (size_t)(S + 2);     // (sqrt, 1/sqrt) table + (b_i, A_ii)
+                if (smem > 200 * 1024) continue;
                 double step_us = (double)TS * 0.55e-3;          // ~0.55 ns per amplitude per SM (FP64 pipe)
                 if (step_us < 0.15) step_us = 0.15;             // dependent-chain floor of one panel step
                 const double cost = (S - 1) * step_us + (g0 + g1 + g2 - 3) * 0.7;
                 if (cost < best) {
                     best = cost; bg[0] = g0; bg[1] = g1; bg[2] = g2; bR = R; bTC = TC; bLS = (int)LS; bHC = (int)HC;
+                    bSq = (int)sqtab_off;
                     *smem_out = smem;
                 }
             }
@@ -236,7 +242,7 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
     memset(tp, 0, sizeof(*tp));
     tp->d = d; tp->stage = stage; tp->nt = nt;
     for (int m = 0; m < 3; m++) tp->g[m] = bg[m];
-    tp->tc = bTC; tp->ls_max = bLS; tp->hc_max = bHC > 0 ? bHC : 1;
+    tp->tc = bTC; tp->ls_max = bLS; tp->hc_max = bHC > 0 ? bHC : 1; tp->sqtab_off = bSq;
     *R_out = bR;
     *ntiles_out = bg[0] * bg[1] * bg[2];
     return true;
@@ -271,6 +277,11 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
                     CK(cudaMemset(ctx->xbuf.ptr, 0xFF, ctx->xbuf.bytes));
                 }
                 tp.X = (c128 *)ctx->xbuf.ptr;
+            }
+            tp.cslot = 0;
+            if (R == 4) {   // only the R == 4 variant reads A_i. and b_i from constant memory
+                g_launches++;
+                CK(mmh_stage_constants(p.A, p.b, D, i, tp.cslot, st));
             }
             const char *trace_file = getenv("MMH_TRACE_FILE");   // debug timeline of the tile pipeline
             const size_t trace_words = (size_t)ntiles * d.shape[i] * 4;

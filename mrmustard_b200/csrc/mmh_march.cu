@@ -14,6 +14,25 @@
 #include "mmh_params.cuh"
 #include "mmh_points.cuh"
 
+
+// Divide all R numerators by sqrt(s) in place.  The IEEE slow path (inf/nan/subnormal-range numerators) is a
+// single warp-level branch for the whole step, so the common path stays branch-free and v's registers are reused.
+template <int R>
+__device__ __forceinline__ void div_all_inplace(c128 (&v)[R], double sqs, double rsqs) {
+    bool slow = false;
+#pragma unroll
+    for (int r = 0; r < R; r++) slow |= div_needs_slow(v[r].x) | div_needs_slow(v[r].y);
+    if (!slow) {
+#pragma unroll
+        for (int r = 0; r < R; r++) v[r] = c_make(div_fast(v[r].x, sqs, rsqs), div_fast(v[r].y, sqs, rsqs));
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            v[r] = c_make(div_needs_slow(v[r].x) ? __ddiv_rn(v[r].x, sqs) : div_fast(v[r].x, sqs, rsqs),
+                          div_needs_slow(v[r].y) ? __ddiv_rn(v[r].y, sqs) : div_fast(v[r].y, sqs, rsqs));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K2: batched stage march.  One launch per stage i (i = D-2 .. 0); stage D-1 is k_fwd_chain.
 // The CTA marches L lattices in lock step; a thread owns R fixed panel positions ("slots").
@@ -84,7 +103,7 @@ __global__ void __launch_bounds__(R >= 4 ? 256 : 512, R >= 4 ? 2 : 1) k_march_st
     // path (inf/nan/subnormal-range numerators) is checked once per step for all slots.
 #define MMH_MARCH_STEP(P1, P2, OFFP, OFFC)                                                            \
     {                                                                                                 \
-        c128 v[R], qq[R];                                                                             \
+        c128 v[R];                                                                                    \
         _Pragma("unroll") for (int r = 0; r < R; r++) {                                               \
             const c128 b0 = sba[isb[r]], a00 = sba[isb[r] + 1];                                       \
             v[r] = c_mul(b0, P1[r]);                                                                  \
@@ -92,23 +111,13 @@ __global__ void __launch_bounds__(R >= 4 ? 256 : 512, R >= 4 ? 2 : 1) k_march_st
             _Pragma("unroll") for (int jj = 0; jj < NPD; jj++)                                        \
                 v[r] = c_add(v[r], c_mul(coef[r][jj], buf[(OFFP) + nbi[r][jj]]));                     \
         }                                                                                             \
-        bool slow = false;                                                                            \
+        div_all_inplace<R>(v, sqs, rsqs);                                                             \
         _Pragma("unroll") for (int r = 0; r < R; r++) {                                               \
-            qq[r] = c_make(div_fast(v[r].x, sqs, rsqs), div_fast(v[r].y, sqs, rsqs));                 \
-            slow |= div_needs_slow(v[r].x) | div_needs_slow(v[r].y);                                  \
-        }                                                                                             \
-        if (slow) {                                                                                   \
-            _Pragma("unroll") for (int r = 0; r < R; r++) {                                           \
-                if (div_needs_slow(v[r].x)) qq[r].x = __ddiv_rn(v[r].x, sqs);                         \
-                if (div_needs_slow(v[r].y)) qq[r].y = __ddiv_rn(v[r].y, sqs);                         \
-            }                                                                                         \
-        }                                                                                             \
-        _Pragma("unroll") for (int r = 0; r < R; r++) {                                               \
-            P2[r] = qq[r];                                                                            \
+            P2[r] = v[r];                                                                             \
             if (act[r]) {                                                                             \
                 gp[r] += P;                                                                           \
-                *gp[r] = qq[r];                                                                       \
-                buf[(OFFC) + loc[r]] = qq[r];                                                         \
+                *gp[r] = v[r];                                                                        \
+                buf[(OFFC) + loc[r]] = v[r];                                                          \
             }                                                                                         \
         }                                                                                             \
     }
@@ -221,6 +230,39 @@ __device__ __forceinline__ void st_relaxed_v2_u64(void *p, unsigned long long a,
     asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 #define MMH_SENTINEL 0xFFFFFFFFFFFFFFFFull
+#ifndef MMH_XSTORE_MODE
+#define MMH_XSTORE_MODE 1
+#endif
+#if MMH_XSTORE_MODE == 0      // experiment: no export at all (results invalid)
+#define MMH_XSTORE(ptr, val) do { } while (0)
+#elif MMH_XSTORE_MODE == 1    // weak L2-only store; every 64-bit word is single-copy atomic and self-validating
+#define MMH_XSTORE(ptr, val) __stcg((ptr), (val))
+#else                         // strong relaxed store at gpu scope
+#define MMH_XSTORE(ptr, val) st_relaxed_v2_u64((ptr), (unsigned long long)__double_as_longlong((val).x), (unsigned long long)__double_as_longlong((val).y))
+#endif
+
+// A_i,i.. row and b_i of the lattice being marched, staged in constant memory (stream-ordered device->constant
+// copy before each tiled launch) so that they are immediate constant-bank operands of the DMULs, not registers.
+// One slot: launches of the tiled march on one device are serialised on a single stream.
+__constant__ c128 c_triple[9];      // [0] = A_ii, [1 + jj] = A_i,i+1+jj, [8] = b_i
+__device__ c128 g_triple_stage[9];  // global staging area
+
+__global__ void k_stage_constants(const c128 *A, const c128 *b, int D, int stage) {
+    const int t = threadIdx.x;
+    if (t < 8) g_triple_stage[t] = (stage + t < D) ? A[stage * D + stage + t] : make_double2(0.0, 0.0);
+    if (t == 8) g_triple_stage[8] = b[stage];
+}
+
+cudaError_t mmh_stage_constants(const c128 *A, const c128 *b, int D, int stage, int slot, cudaStream_t st) {
+    (void)slot;
+    k_stage_constants<<<1, 32, 0, st>>>(A, b, D, stage);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    void *src = nullptr;
+    e = cudaGetSymbolAddress(&src, g_triple_stage);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbolAsync(c_triple, src, sizeof(c128) * 9, 0, cudaMemcpyDeviceToDevice, st);
+}
 
 template <int R, int NPD>
 __global__ void __launch_bounds__((R >= 4 ? 256 : 512) + 32 * MMH_NHW, 1) k_march_tiled(TiledParams p) {
@@ -271,6 +313,8 @@ __global__ void __launch_bounds__((R >= 4 ? 256 : 512) + 32 * MMH_NHW, 1) k_marc
     c128 *ring = smem + 2 * (size_t)p.ls_max; // [KRING][hc_max]
     int *hal_gofs = (int *)(ring + MMH_KRING * (size_t)p.hc_max);
     int *sync_words = hal_gofs + p.hc_max;    // [0..KRING) = panel held by ring slot k ; [KRING] = cdone
+    int *xo_s = sync_words + 8;               // [3][R * TC] export offsets (consumer tile block + cell)
+    double2 *sqtab = (double2 *)(smem + p.sqtab_off);   // [S] (sqrt(s), 1/sqrt(s))
     const int ringstride = p.hc_max;
     const size_t xtile = (size_t)S * p.hc_max;   // X elements per consumer tile
 
@@ -286,28 +330,34 @@ __global__ void __launch_bounds__((R >= 4 ? 256 : 512) + 32 * MMH_NHW, 1) k_marc
         hal_gofs[c] = (lo[m] - 1) * gst[m] + (lo[a] + xa) * gst[a] + (lo[b] + xb) * gst[b] + rr;
     }
     if (tid <= MMH_KRING) sync_words[tid] = 0;
+    for (int s_ = tid; s_ < S; s_ += blockDim.x) sqtab[s_] = make_double2(sq[s_], rsq[s_]);
     __syncthreads();
     // panel 0 halo -> ring slot 0 (panel 0 is final: the previous stage's kernel has completed)
     for (int c = tid; c < HC; c += blockDim.x) ring[c] = __ldcg(p.G + hal_gofs[c]);
 
-    const c128 b0 = p.b[i], a00 = p.A[i * D + i];
+    // uniform operands straight from the constant bank: crow[0] = A_ii, crow[1 + jj] = A_i,i+1+jj, crow[8] = b_i
+    // (b_i, A_ii): R == 4 takes them (and A_ij) from the constant bank staged by mmh_stage_constants; R <= 2 keeps the
+    // coefficients in registers and re-reads (b_i, A_ii) from shared memory, so no constant staging launch is needed.
+    c128 *sba2 = (c128 *)(sqtab + S);
+    if (tid == 0) { sba2[0] = p.b[i]; sba2[1] = p.A[i * D + i]; }
+#define crow (p.A + i * D + i)
+#define b0 (COEF_REG ? sba2[0] : c_triple[8])
+#define a00 (COEF_REG ? sba2[1] : c_triple[0])
 
     // ---- per-slot constants (compute warps) -----------------------------------------------------------------
     bool act[R];
     unsigned hm[R];             // bit jj: neighbour jj lives in the halo ring
     int loc[R];
     int nbi[R][NPD];
-    int xo[R][3];               // offset of this amplitude inside the exchange block of the upper neighbour in
-                                // tiled dim m (panel 0), or -1 when the slot is not on that high face
-    c128 coef[R][NPD];
-    c128 *gp[R];
+    unsigned xm[R];             // bit m: the slot is on the high face of tiled dim m (its amplitude is exported);
+                                // the offset inside the upper neighbour's exchange block is kept in shared memory
+    // coefficient A_ij sqrt(k_j) of every neighbour: R <= 2 keeps the complex product in registers; R == 4 keeps only
+    // sqrt(k_j) (0 when the neighbour does not exist) and multiplies by A_ij from the constant bank each step
+    constexpr bool COEF_REG = R <= 2;
+    c128 coef[COEF_REG ? R : 1][NPD];
+    double sqk[COEF_REG ? 1 : R][NPD];
+    int gofs[R];                // panel offset f of the slot: G index = s * P + f
     c128 h0[R], h1[R];
-    c128 *xbase[3];             // exchange block of the upper neighbour tile in dim m
-#pragma unroll
-    for (int m = 0; m < 3; m++) {
-        const int up = tile + (m == 0 ? g[1] * g[2] : (m == 1 ? g[2] : 1));
-        xbase[m] = p.X + (size_t)up * xtile;
-    }
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int q = r * TC + tidc;
@@ -322,7 +372,7 @@ __global__ void __launch_bounds__((R >= 4 ? 256 : 512) + 32 * MMH_NHW, 1) k_marc
         x[0] = q1 / e[1];
         loc[r] = (x[0] + h[0]) * lst[0] + (x[1] + h[1]) * lst[1] + (x[2] + h[2]) * lst[2] + rr;
         const int f = (lo[0] + x[0]) * gst[0] + (lo[1] + x[1]) * gst[1] + (lo[2] + x[2]) * gst[2] + rr;
-        gp[r] = p.G + f;
+        gofs[r] = f;
         int rem = rr;
 #pragma unroll
         for (int jj = 0; jj < NPD; jj++) {
@@ -347,12 +397,13 @@ __global__ void __launch_bounds__((R >= 4 ? 256 : 512) + 32 * MMH_NHW, 1) k_marc
             if (!has) { nb = loc[r]; halo = false; }
             nbi[r][jj] = nb;
             if (halo) hm[r] |= 1u << jj;
-            coef[r][jj] = has ? c_scale(p.A[i * D + j], sq[k]) : c_make(0.0, 0.0);
+            if constexpr (COEF_REG) coef[r][jj] = has ? c_scale(crow[1 + jj], sq[k]) : c_make(0.0, 0.0);
+            else sqk[r][jj] = has ? sq[k] : 0.0;
         }
         // high faces: where does the upper neighbour in dim m expect this amplitude?
+        xm[r] = 0u;
 #pragma unroll
         for (int m = 0; m < 3; m++) {
-            xo[r][m] = -1;
             if (act[r] && m < nt && t[m] + 1 < g[m] && x[m] == e[m] - 1) {
                 // the consumer box: same extents except in dim m
                 const int lo_up = (int)(((long long)(t[m] + 1) * shp[m]) / g[m]);
@@ -363,11 +414,13 @@ __global__ void __launch_bounds__((R >= 4 ? 256 : 512) + 32 * MMH_NHW, 1) k_marc
                 int fo = 0;
                 for (int mm = 0; mm < m; mm++) fo += hc[mm] * (TSc / ec[mm]);
                 const int a = m == 0 ? 1 : 0, b = m == 2 ? 1 : 2;
-                xo[r][m] = fo + (x[a] * ec[b] + x[b]) * inner + rr;
+                xm[r] |= 1u << m;
+                const int up = tile + (m == 0 ? g[1] * g[2] : (m == 1 ? g[2] : 1));   // the consumer tile
+                xo_s[m * (R * TC) + q] = (int)(up * xtile) + fo + (x[a] * ec[b] + x[b]) * inner + rr;
             }
         }
         h0[r] = c_make(0.0, 0.0);
-        h1[r] = act[r] ? __ldcg(gp[r]) : c_make(0.0, 0.0);
+        h1[r] = act[r] ? __ldcg(p.G + gofs[r]) : c_make(0.0, 0.0);
         if (act[r]) buf[loc[r]] = h1[r];
     }
     __syncthreads();
@@ -377,6 +430,7 @@ __global__ void __launch_bounds__((R >= 4 ? 256 : 512) + 32 * MMH_NHW, 1) k_marc
         if (HC == 0) return;
         const int lane = tid & 31, hw = tid >> 5;
         c128 *xin = p.X + (size_t)tile * xtile;
+#pragma unroll 1
         for (int u = 1 + hw; u <= S - 2; u += MMH_NHW) {
             if (u - MMH_KRING + 1 >= 1) {   // ring slot of panel u-KRING must have been consumed
                 if (lane == 0) while (ld_acquire_cta_shared(&sync_words[MMH_KRING]) < u - MMH_KRING + 1) { }
@@ -384,6 +438,7 @@ __global__ void __launch_bounds__((R >= 4 ? 256 : 512) + 32 * MMH_NHW, 1) k_marc
             }
             c128 *dst = ring + (size_t)(u % MMH_KRING) * ringstride;
             c128 *src = xin + (size_t)u * p.hc_max;
+#pragma unroll 1
             for (int c0 = lane; c0 < HC; c0 += 32 * 4) {
                 unsigned long long a[4], b[4];
                 bool need[4];
@@ -398,6 +453,7 @@ __global__ void __launch_bounds__((R >= 4 ? 256 : 512) + 32 * MMH_NHW, 1) k_marc
                     const int c = c0 + 32 * w;
                     if (!need[w]) continue;
                     unsigned spins = 0;
+#pragma unroll 1
                     while ((a[w] == MMH_SENTINEL || b[w] == MMH_SENTINEL) && ++spins < (1u << 26))
                         ld_relaxed_v2_u64(src + c, a[w], b[w]);
                     dst[c] = make_double2(__longlong_as_double((long long)a[w]), __longlong_as_double((long long)b[w]));
@@ -414,43 +470,38 @@ __global__ void __launch_bounds__((R >= 4 ? 256 : 512) + 32 * MMH_NHW, 1) k_marc
     // ================= compute warps =================
 #define MMH_TILED_STEP(P1, P2, OFFP, OFFC, OFFH, SCUR)                                                \
     {                                                                                                 \
-        c128 v[R], qq[R];                                                                             \
+        const double2 st_ = sqtab[(SCUR)];                                                            \
+        const double sqs = st_.x, rsqs = st_.y;                                                       \
+        c128 v[R];                                                                                    \
         _Pragma("unroll") for (int r = 0; r < R; r++) {                                               \
             v[r] = c_mul(b0, P1[r]);                                                                  \
             v[r] = c_add(v[r], c_mul(c_scale(a00, sqm), P2[r]));                                      \
             _Pragma("unroll") for (int jj = 0; jj < NPD; jj++) {                                      \
                 const c128 *src = ((hm[r] >> jj) & 1u) ? ring + (OFFH) : buf + (OFFP);                \
-                v[r] = c_add(v[r], c_mul(coef[r][jj], src[nbi[r][jj]]));                              \
+                const c128 cf = COEF_REG ? coef[COEF_REG ? r : 0][jj]                                 \
+                                         : c_scale(c_triple[1 + jj], sqk[COEF_REG ? 0 : r][jj]);          \
+                v[r] = c_add(v[r], c_mul(cf, src[nbi[r][jj]]));                                       \
             }                                                                                         \
         }                                                                                             \
-        bool slow = false;                                                                            \
-        _Pragma("unroll") for (int r = 0; r < R; r++) {                                               \
-            qq[r] = c_make(div_fast(v[r].x, sqs, rsqs), div_fast(v[r].y, sqs, rsqs));                 \
-            slow |= div_needs_slow(v[r].x) | div_needs_slow(v[r].y);                                  \
-        }                                                                                             \
-        if (slow) {                                                                                   \
-            _Pragma("unroll") for (int r = 0; r < R; r++) {                                           \
-                if (div_needs_slow(v[r].x)) qq[r].x = __ddiv_rn(v[r].x, sqs);                         \
-                if (div_needs_slow(v[r].y)) qq[r].y = __ddiv_rn(v[r].y, sqs);                         \
-            }                                                                                         \
-        }                                                                                             \
+        div_all_inplace<R>(v, sqs, rsqs);                                                             \
+        sqm = sqs;                                                                                    \
         const bool xch = (SCUR) <= S - 2;   /* the last panel has no consumer */                      \
+        c128 *gpan = p.G + (long long)(SCUR) * P;                                                     \
+        c128 *xpan = p.X + (size_t)(SCUR) * p.hc_max;                                                 \
         _Pragma("unroll") for (int r = 0; r < R; r++) {                                               \
-            P2[r] = qq[r];                                                                            \
+            P2[r] = v[r];                                                                             \
             if (act[r]) {                                                                             \
-                gp[r] += P;                                                                           \
-                *gp[r] = qq[r];                                                                       \
-                buf[(OFFC) + loc[r]] = qq[r];                                                         \
+                gpan[gofs[r]] = v[r];                                                                 \
+                buf[(OFFC) + loc[r]] = v[r];                                                          \
                 _Pragma("unroll") for (int m = 0; m < 3; m++)                                         \
-                    if (xch && xo[r][m] >= 0)                                                         \
-                        st_relaxed_v2_u64(xbase[m] + (size_t)(SCUR) * p.hc_max + xo[r][m],            \
-                                          (unsigned long long)__double_as_longlong(qq[r].x),          \
-                                          (unsigned long long)__double_as_longlong(qq[r].y));         \
+                    if (xch && ((xm[r] >> m) & 1u))                                                   \
+                        MMH_XSTORE(xpan + xo_s[m * (R * TC) + r * TC + tidc], v[r]);                  \
             }                                                                                         \
         }                                                                                             \
     }
 #define MMH_TILED_SYNC(SDONE)                                                                         \
     {                                                                                                 \
+        if (p.trace && tidc == 0) p.trace[((size_t)tile * S + (SDONE)) * 4 + 2] = globaltimer_ns();   \
         named_barrier_sync(1, TC);                                                                    \
         if (tidc == 0) {                                                                              \
             if (p.trace) p.trace[((size_t)tile * S + (SDONE)) * 4 + 1] = globaltimer_ns();            \
@@ -464,21 +515,16 @@ __global__ void __launch_bounds__((R >= 4 ? 256 : 512) + 32 * MMH_NHW, 1) k_marc
     }                                                                                                 \
     if (p.trace && tidc == 0) p.trace[((size_t)tile * S + (SNEED) + 1) * 4 + 0] = globaltimer_ns();
 
-    double sqm = 0.0, sqs = sq[S > 1 ? 1 : 0], rsqs = rsq[S > 1 ? 1 : 0];
+    double sqm = 0.0;
     const int LSm = p.ls_max;
     int s = 1;
     for (; s + 1 < S; s += 2) {
-        const double sq1 = sq[s + 1], rsq1 = rsq[s + 1];
-        const int s2 = s + 2 < S ? s + 2 : s + 1;
-        const double sq2 = sq[s2], rsq2 = rsq[s2];
         MMH_TILED_WAIT(s - 1)
         MMH_TILED_STEP(h1, h0, 0, LSm, ((s - 1) % MMH_KRING) * ringstride, s)
         MMH_TILED_SYNC(s)
-        sqm = sqs; sqs = sq1; rsqs = rsq1;
         MMH_TILED_WAIT(s)
         MMH_TILED_STEP(h0, h1, LSm, 0, (s % MMH_KRING) * ringstride, s + 1)
         MMH_TILED_SYNC(s + 1)
-        sqm = sqs; sqs = sq2; rsqs = rsq2;
     }
     if (s < S) {
         MMH_TILED_WAIT(s - 1)
@@ -488,6 +534,9 @@ __global__ void __launch_bounds__((R >= 4 ? 256 : 512) + 32 * MMH_NHW, 1) k_marc
 #undef MMH_TILED_STEP
 #undef MMH_TILED_SYNC
 #undef MMH_TILED_WAIT
+#undef crow
+#undef b0
+#undef a00
 }
 
 template <int R>

@@ -51,7 +51,9 @@ struct StageParams {
 
 struct TiledParams {
     LatticeDesc d;
-    const c128 *A, *b;           // one triple
+    int cslot;                   // reserved
+    int sqtab_off;               // offset (c128 units) of the (sqrt, 1/sqrt) table in shared memory
+    const c128 *A, *b;           // one triple (device)
     c128 *G;                     // one lattice
     const double *sq, *rsq;
     c128 *X;                     // halo exchange buffer [ntiles][shape[stage]][hc_max], all-sentinel between launches
@@ -64,6 +66,7 @@ struct TiledParams {
     unsigned long long *trace;   // debug timeline [tile][step][4] of %globaltimer stamps (MMH_TRACE_FILE), else NULL
 };
 
+cudaError_t mmh_stage_constants(const c128 *A, const c128 *b, int D, int stage, int slot, cudaStream_t st);
 cudaError_t mmh_launch_march_tiled(const TiledParams &p, int R, int ntiles, size_t smem, cudaStream_t st);
 cudaError_t mmh_launch_march_stage(const StageParams &p, int R, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t mmh_launch_chain(const FwdParams &p, cudaStream_t st);

@@ -26,4 +26,5 @@ for stage in (1, 0):
         for s in steps:
             if s < S: print(f"    s={s:2d}  {start[s]/1e3:8.2f} {end[s]/1e3:8.2f} {seen[s]/1e3:8.2f} {pub[s]/1e3:8.2f}")
         d = np.diff(end[1:])
-        print(f"    mean step {d.mean()/1e3:.3f} us, compute (end-start) mean {np.mean(end[1:]-start[1:])/1e3:.3f} us")
+        print(f"    mean step {d.mean()/1e3:.3f} us, compute (end-start) mean {np.mean(end[1:]-start[1:])/1e3:.3f} us, "
+              f"thread0 math+stores {np.mean(seen[1:]-start[1:])/1e3:.3f} us, barrier wait {np.mean(end[1:]-seen[1:])/1e3:.3f} us")

@@ -101,6 +101,29 @@ int mmh_binomial(int ndim, const int64_t *shape, const void *dA, const void *db,
 int mmh_binomial_host(int ndim, const int64_t *shape, const void *A, const void *b, const void *c,
                       double max_l2, int64_t global_cutoff, void *G, double *norm_out);
 
+/* compactFock "diagonal": PNR detection amplitudes of all modes -----------------------------------------
+ * replaces: hermite_multidimensional_diagonal(A, B, G0, cutoffs)[0]
+ *           (strategies/compactFock/inputValidation.py:61-79 -> diagonal_amps.py:145-248), reached through
+ *           BackendNumpy.hermite_renormalized_diagonal (math/backend_numpy.py:423-432) after reorder_AB_bargmann.
+ * A[2M,2M], B[2M] (nbatch = 0) or B[2M, nbatch] (batch on the LAST axis), both in the interleaved order
+ * [m0,m0,m1,m1,...]; G0[1]; cutoffs[M]  ->  arr0[cutoffs...(, nbatch)] = G[a,a,b,b,...].
+ * M <= 8.  Auxiliary arrays (arr1, arr2, arr1010, arr1001) live in library scratch.                   */
+int mmh_diagonal(int M, const int64_t *cutoffs, const void *dA, const void *dB, int64_t nbatch,
+                 const void *dG0, void *darr0_out, void *stream);
+int mmh_diagonal_host(int M, const int64_t *cutoffs, const void *A, const void *B, int64_t nbatch,
+                      const void *G0, void *arr0_out);
+
+/* compactFock "one leftover mode": density matrix of mode 0 conditioned on PNR outcomes of the others ----
+ * replaces: hermite_multidimensional_1leftoverMode(A, B, G0, cutoffs)[0]
+ *           (inputValidation.py:103-122 -> singleLeftoverMode_amps.py:290-475); the numpy backend computes
+ *           the same quantity with strategies.fast_diagonal (fast_diagonal.py:32-77; backend_numpy.py:434-446).
+ * A[2M,2M], B[2M] interleaved (indices 0,1 = the undetected mode); cutoffs[M] = (c0, tail...), M >= 2
+ * -> arr0[c0, c0, tail...].                                                                              */
+int mmh_1leftover(int M, const int64_t *cutoffs, const void *dA, const void *dB, const void *dG0,
+                  void *darr0_out, void *stream);
+int mmh_1leftover_host(int M, const int64_t *cutoffs, const void *A, const void *B, const void *G0,
+                       void *arr0_out);
+
 #ifdef __cplusplus
 }
 #endif

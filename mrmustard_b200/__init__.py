@@ -14,7 +14,9 @@ from . import _lib, strategies  # noqa: F401
 from .backend import (  # noqa: F401
     hermite_renormalized,
     hermite_renormalized_batched,
+    hermite_renormalized_1leftoverMode,
     hermite_renormalized_binomial,
+    hermite_renormalized_diagonal,
 )
 
 __version__ = "0.1.0"

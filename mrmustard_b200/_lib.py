@@ -27,6 +27,7 @@ SYMBOLS = [
     "mmh_forward", "mmh_forward_host", "mmh_forward_batched", "mmh_forward_batched_host",
     "mmh_vjp", "mmh_vjp_host", "mmh_vjp_batched", "mmh_vjp_batched_host",
     "mmh_binomial", "mmh_binomial_host",
+    "mmh_diagonal", "mmh_diagonal_host", "mmh_1leftover", "mmh_1leftover_host",
 ]
 
 
@@ -61,6 +62,10 @@ def _load() -> ctypes.CDLL:
         "mmh_vjp_batched_host": ([i64, ci, p64, vp, vp, vp, vp, vp, vp], ci),
         "mmh_binomial": ([ci, p64, vp, vp, vp, dbl, i64, vp, ctypes.POINTER(dbl), vp], ci),
         "mmh_binomial_host": ([ci, p64, vp, vp, vp, dbl, i64, vp, ctypes.POINTER(dbl)], ci),
+        "mmh_diagonal": ([ci, p64, vp, vp, i64, vp, vp, vp], ci),
+        "mmh_diagonal_host": ([ci, p64, vp, vp, i64, vp, vp], ci),
+        "mmh_1leftover": ([ci, p64, vp, vp, vp, vp, vp], ci),
+        "mmh_1leftover_host": ([ci, p64, vp, vp, vp, vp], ci),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)

@@ -52,6 +52,32 @@ def hermite_renormalized_binomial(A, B, C, shape, max_l2=None, global_cutoff=Non
     )[0]
 
 
+def reorder_AB_bargmann(A, B):
+    """BackendNumpy.reorder_AB_bargmann (backend_numpy.py:367-377): [m0..,m0..] -> [m0,m0,m1,m1,..]."""
+    A = np.asarray(A)
+    B = np.asarray(B)
+    ordering = np.arange(2 * A.shape[0] // 2).reshape(2, -1).T.flatten()
+    A = np.take(np.take(A, ordering, axis=1), ordering, axis=0)
+    B = np.take(B, ordering, axis=0)
+    return A, B
+
+
+def hermite_renormalized_diagonal(A, B, C, cutoffs, reorderedAB=True):
+    """BackendNumpy.hermite_renormalized_diagonal (backend_numpy.py:423-432)."""
+    A, B = reorder_AB_bargmann(A, B) if reorderedAB else (np.asarray(A), np.asarray(B))
+    return strategies.hermite_multidimensional_diagonal(np.ascontiguousarray(A), B, C, cutoffs)
+
+
+def hermite_renormalized_1leftoverMode(A, b, c, output_cutoff, pnr_cutoffs, stable=False, reorderedAB=True):
+    """BackendNumpy.hermite_renormalized_1leftoverMode (backend_numpy.py:434-446): fast_diagonal + transpose to
+    (out+1, out+1, *(pnr+1)).  As on the numpy backend the inputs are always taken in bargmann order and permuted
+    (fast_diagonal.py:56-58); `stable`/`reorderedAB` are accepted for call compatibility (see SURVEY.md §3.4 for the
+    reference's positional-argument slip)."""
+    pnr_cutoffs = tuple(pnr_cutoffs)
+    return strategies.fast_diagonal(A, b, c, output_cutoff, pnr_cutoffs, stable).transpose(
+        (-2, -1, *tuple(range(len(pnr_cutoffs)))))
+
+
 def hermite_renormalized(A, b, c, shape, stable=False, out=None):
     """BackendManager.hermite_renormalized (backend_manager.py:643-727)."""
     A = np.asarray(A)

@@ -37,6 +37,7 @@ struct DeviceCtx {
     unsigned *barrier = nullptr;  // 64 counters; one is consumed per cooperative launch (round robin)
     int barrier_next = 0;
     int cslot_next = 0;           // ring of constant-memory slots for the tiled march (MMH_CSLOTS)
+    Scratch diag_ws;              // auxiliary arrays of the compactFock sweeps
     Scratch xbuf;                 // halo exchange buffer of the tiled march; all-ones sentinel between launches
     Scratch partial;              // VJP partial sums
     Scratch norm;                 // binomial norm scalar
@@ -460,6 +461,82 @@ static int binomial_impl(int ndim, const int64_t *shape, const void *dA, const v
     return MMH_OK;
 }
 
+// ---- compactFock diagonal / one leftover mode ----------------------------------------------------------
+static int stage_in(DeviceCtx &c, int slot, const void *host, size_t bytes, void **dev);
+static int diagonal_impl(int M, const int64_t *cutoffs, int L0, const void *dA, const void *dB, long long nbatch,
+                         const void *dG0, void *dout, cudaStream_t st) {
+    if (!cutoffs) return MMH_ERR_NULL_POINTER;
+    const int Md = M - L0;
+    if (M < 1 + L0 || Md < 1 || Md > 8) return MMH_ERR_BAD_NDIM;
+    if (nbatch < 0) return MMH_ERR_BAD_BATCH;
+    if (!dA || !dB || !dG0 || !dout) return MMH_ERR_NULL_POINTER;
+    DiagParams q;
+    memset(&q, 0, sizeof(q));
+    q.Md = Md; q.L0 = L0;
+    q.c0 = L0 ? (int)cutoffs[0] : 1;
+    q.nb = nbatch > 0 ? (int)nbatch : 1;
+    int mx = q.c0, nlevels = 1;
+    long long P = 1;
+    for (int j = 0; j < M; j++) if (cutoffs[j] < 1 || cutoffs[j] > (1 << 20)) return MMH_ERR_BAD_SHAPE;
+    for (int j = 0; j < Md; j++) {
+        q.cut[j] = (int)cutoffs[j + L0];
+        if (q.cut[j] > mx) mx = q.cut[j];
+        nlevels += q.cut[j] - 1;
+        if (P > (1LL << 40) / q.cut[j]) return MMH_ERR_TOO_LARGE;
+        P *= q.cut[j];
+    }
+    q.pst[Md - 1] = 1;
+    for (int j = Md - 1; j > 0; j--) q.pst[j - 1] = q.pst[j] * q.cut[j];
+    q.P = P;
+    q.E = (long long)q.c0 * q.c0 * P * q.nb;
+    DeviceCtx *ctx;
+    int rc;
+    if ((rc = get_ctx(&ctx))) return rc;
+    if ((rc = ensure_tables(*ctx, mx + 3))) return rc;
+    const long long naux = 2LL * Md + Md + 2LL * Md * (Md > 1 ? Md - 1 : 1);
+    const size_t bytes = sizeof(c128) * (size_t)naux * (size_t)q.E;
+    if (bytes > (size_t)160 << 30) return MMH_ERR_TOO_LARGE;   // reference layout; rolling level buffers are future work
+    if ((rc = ensure_scratch(ctx->diag_ws, bytes))) return rc;
+    CK(cudaMemsetAsync(ctx->diag_ws.ptr, 0, bytes, st));
+    c128 *w = (c128 *)ctx->diag_ws.ptr;
+    q.arr1 = w;                      w += 2LL * Md * q.E;
+    q.arr2 = w;                      w += (long long)Md * q.E;
+    q.arr1010 = w;                   w += (long long)Md * (Md > 1 ? Md - 1 : 1) * q.E;
+    q.arr1001 = w;
+    q.arr0 = (c128 *)dout;
+    q.A = (const c128 *)dA; q.B = (const c128 *)dB; q.sq = ctx->sq;
+    long long launches = 0;
+    CK(mmh_launch_diagonal(q, (const c128 *)dG0, nlevels, &launches, st));
+    g_launches += launches;
+    return MMH_OK;
+}
+
+static int diagonal_host_impl(int M, const int64_t *cutoffs, int L0, const void *A, const void *B, long long nbatch,
+                              const void *G0, void *out) {
+    if (!cutoffs) return MMH_ERR_NULL_POINTER;
+    if (M < 1 + L0 || M - L0 > 8) return MMH_ERR_BAD_NDIM;
+    if (nbatch < 0) return MMH_ERR_BAD_BATCH;
+    if (!A || !B || !G0 || !out) return MMH_ERR_NULL_POINTER;
+    size_t n = nbatch > 0 ? (size_t)nbatch : 1;
+    for (int j = 0; j < M; j++) {
+        if (cutoffs[j] < 1) return MMH_ERR_BAD_SHAPE;
+        n *= (size_t)cutoffs[j] * ((L0 && j == 0) ? (size_t)cutoffs[j] : 1);
+    }
+    DeviceCtx *ctx;
+    int rc;
+    if ((rc = get_ctx(&ctx))) return rc;
+    const size_t n2 = 2 * (size_t)M;
+    void *dA, *dB, *dG0, *dout;
+    if ((rc = stage_in(*ctx, 0, A, sizeof(c128) * n2 * n2, &dA))) return rc;
+    if ((rc = stage_in(*ctx, 1, B, sizeof(c128) * n2 * (nbatch > 0 ? (size_t)nbatch : 1), &dB))) return rc;
+    if ((rc = stage_in(*ctx, 2, G0, sizeof(c128), &dG0))) return rc;
+    if ((rc = stage_in(*ctx, 3, nullptr, sizeof(c128) * n, &dout))) return rc;
+    if ((rc = diagonal_impl(M, cutoffs, L0, dA, dB, nbatch, dG0, dout, 0))) return rc;
+    CK(cudaMemcpyAsync(out, dout, sizeof(c128) * n, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    return MMH_OK;
+}
+
 // ---- host staging ---------------------------------------------------------------------------------
 static int stage_in(DeviceCtx &c, int slot, const void *host, size_t bytes, void **dev) {
     int rc = ensure_scratch(c.host_slots[slot], bytes);
@@ -588,6 +665,28 @@ int mmh_vjp_batched_host(int64_t batch, int ndim, const int64_t *shape, const vo
 int mmh_vjp_host(int ndim, const int64_t *shape, const void *G, const void *c, const void *dLdG, void *oA,
                  void *ob, void *oc) {
     return mmh_vjp_batched_host(1, ndim, shape, G, c, dLdG, oA, ob, oc);
+}
+
+int mmh_diagonal(int M, const int64_t *cutoffs, const void *dA, const void *dB, int64_t nbatch, const void *dG0,
+                 void *dout, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return diagonal_impl(M, cutoffs, 0, dA, dB, nbatch, dG0, dout, (cudaStream_t)stream);
+}
+int mmh_diagonal_host(int M, const int64_t *cutoffs, const void *A, const void *B, int64_t nbatch, const void *G0,
+                      void *out) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return diagonal_host_impl(M, cutoffs, 0, A, B, nbatch, G0, out);
+}
+int mmh_1leftover(int M, const int64_t *cutoffs, const void *dA, const void *dB, const void *dG0, void *dout,
+                  void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (M < 2) return MMH_ERR_BAD_NDIM;
+    return diagonal_impl(M, cutoffs, 1, dA, dB, 0, dG0, dout, (cudaStream_t)stream);
+}
+int mmh_1leftover_host(int M, const int64_t *cutoffs, const void *A, const void *B, const void *G0, void *out) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (M < 2) return MMH_ERR_BAD_NDIM;
+    return diagonal_host_impl(M, cutoffs, 1, A, B, 0, G0, out);
 }
 
 int mmh_binomial(int ndim, const int64_t *shape, const void *dA, const void *db, const void *dc,

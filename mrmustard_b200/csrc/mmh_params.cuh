@@ -76,3 +76,24 @@ cudaError_t mmh_launch_fwd_coop(const FwdParams &p, bool stable, int grid, int b
 cudaError_t mmh_launch_panel_step(const FwdParams &p, int stage, int s, int grid, size_t smem, cudaStream_t st);
 cudaError_t mmh_launch_binomial(const BinomParams &p, int block, size_t smem, cudaStream_t st);
 cudaError_t mmh_launch_vjp(const VjpParams &p, int grid_y, int block, cudaStream_t st);
+
+// compactFock diagonal / one-leftover-mode sweep (mmh_diagonal.cu)
+struct DiagParams {
+    int Md;              // PNR-detected modes
+    int L0;              // 0 = diagonal, 1 = one leftover (undetected) mode occupying A/B indices 0, 1
+    int c0;              // cutoff of the leftover mode (1 for the diagonal case)
+    int nb;              // batch entries of B (last axis); 1 when B is a vector
+    int level;           // weight level being swept
+    int cut[8];          // cutoffs of the detected modes
+    long long pst[8];    // row-major strides over `cut`
+    long long P;         // prod(cut)
+    long long E;         // elements of one sub-array: c0 * c0 * P * nb
+    const c128 *A;       // [2(Md+L0)]^2, interleaved order [m0,m0,m1,m1,...]
+    const c128 *B;       // [2(Md+L0)][nb]
+    c128 *arr0;          // [c0][c0][cut...][nb]          (the result)
+    c128 *arr1;          // [2 Md] x that
+    c128 *arr2;          // [Md] x that
+    c128 *arr1010, *arr1001;   // [Md][Md-1] x that
+    const double *sq;
+};
+cudaError_t mmh_launch_diagonal(DiagParams q, const c128 *G0, int nlevels, long long *launches, cudaStream_t st);

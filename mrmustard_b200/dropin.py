@@ -2,7 +2,7 @@
 
 The reference resolves `math.hermite_renormalized*` by name on the active backend object
 (BackendManager._apply, backend_manager.py:89-116) and the jax VJP rules call `strategies.*` by name
-(math/jax_vjps/hermite.py:60-74,86-102).  `install()` therefore (1) rebinds the three BackendNumpy
+(math/jax_vjps/hermite.py:60-74,86-102).  `install()` therefore (1) rebinds the five BackendNumpy
 methods this package implements and (2) rebinds the strategy functions in
 `mrmustard.math.lattice.strategies`.  `uninstall()` restores the originals.
 """
@@ -13,7 +13,7 @@ from . import backend, strategies
 _saved: dict = {}
 
 _STRATEGY_NAMES = ["vanilla_numba", "stable_numba", "vanilla_batch_numba", "vanilla_vjp_numba",
-                   "vanilla_batch_vjp_numba", "binomial"]
+                   "vanilla_batch_vjp_numba", "binomial", "fast_diagonal"]
 
 
 def install() -> None:
@@ -32,6 +32,10 @@ def install() -> None:
             backend.hermite_renormalized_batched(A, b, c, shape, stable, out),
         "hermite_renormalized_binomial": lambda self, A, B, C, shape, max_l2, global_cutoff:
             backend.hermite_renormalized_binomial(A, B, C, shape, max_l2, global_cutoff),
+        "hermite_renormalized_diagonal": lambda self, A, B, C, cutoffs, reorderedAB:
+            backend.hermite_renormalized_diagonal(A, B, C, cutoffs, reorderedAB),
+        "hermite_renormalized_1leftoverMode": lambda self, A, b, c, output_cutoff, pnr_cutoffs, stable=False, reorderedAB=True:
+            backend.hermite_renormalized_1leftoverMode(A, b, c, output_cutoff, pnr_cutoffs, stable, reorderedAB),
     }.items():
         _saved[("b", name)] = getattr(BackendNumpy, name)
         setattr(BackendNumpy, name, fn)

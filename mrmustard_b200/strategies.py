@@ -19,6 +19,7 @@ from ._lib import check, lib, shape_array
 __all__ = [
     "vanilla_numba", "stable_numba", "vanilla_batch_numba", "vanilla_vjp_numba",
     "vanilla_batch_vjp_numba", "binomial", "vanilla", "stable",
+    "hermite_multidimensional_diagonal", "hermite_multidimensional_1leftoverMode", "fast_diagonal",
 ]
 
 
@@ -154,3 +155,88 @@ def binomial(local_cutoffs, A, b, c, max_l2, global_cutoff):
     check(lib.mmh_binomial_host(D, shape_array(shape), _p(A), _p(b), _p(c), max_l2, int(global_cutoff), _p(G),
                                 ctypes.byref(norm)))
     return G, norm.value
+
+
+# ---- compactFock: diagonal / one leftover mode -------------------------------------------------------------
+def _input_validation(A, rtol=1e-05, atol=1e-08):
+    """compactFock/inputValidation.py:29-56 (same exception types and messages)."""
+    if not isinstance(A, np.ndarray):
+        raise TypeError("Input matrix must be a NumPy array.")
+    n = A.shape
+    if n[0] != n[1]:
+        raise ValueError("Input matrix must be square.")
+    if np.isnan(A).any():
+        raise ValueError("Input matrix must not contain NaNs.")
+    if not np.allclose(A, A.T, rtol=rtol, atol=atol):
+        raise ValueError("Input matrix must be symmetric.")
+    return True
+
+
+def hermite_multidimensional_diagonal(A, B, G0, cutoffs, rtol=1e-05, atol=1e-08):
+    """PNR-diagonal amplitudes G[a,a,b,b,...]; A, B in interleaved order (compactFock/inputValidation.py:61-79).
+
+    Returns arr0 only (the reference returns the tuple (arr0, arr2, arr1010, arr1001, arr1) and every caller keeps
+    [0]); B may be (2M,) or (2M, batch) with the batch on the LAST axis of B and of the result."""
+    _input_validation(A, atol=atol, rtol=rtol)
+    B = np.asarray(B)
+    if B.ndim > 2:
+        raise ValueError("B should be either unbactched or two dimensional (vector and batch dimension)")
+    if A.shape[0] != B.shape[0]:
+        raise ValueError("The matrix A and vector B have incompatible dimensions")
+    try:
+        cutoffs = tuple(int(c) for c in cutoffs)
+    except TypeError:
+        raise ValueError("cutoffs should be array like of length M") from None
+    M = len(cutoffs)
+    if A.shape[0] // 2 != M:
+        raise ValueError("The matrix A and cutoffs have incompatible dimensions")
+    cutoffs = _check_shape(cutoffs)
+    A = _c128(A)
+    B = _c128(B)
+    G0 = _c128(G0, (1,))
+    nb = 0 if B.ndim == 1 else B.shape[1]
+    out = _lib.pinned_empty(cutoffs + ((nb,) if B.ndim == 2 else ()))
+    if out.size:
+        check(lib.mmh_diagonal_host(M, shape_array(cutoffs), _p(A), _p(B), nb, _p(G0), _p(out)))
+    return out
+
+
+def hermite_multidimensional_1leftoverMode(A, B, G0, cutoffs, rtol=1e-05, atol=1e-08):
+    """Density matrix of the first (undetected) mode for every PNR pattern of the others; A, B interleaved
+    (compactFock/inputValidation.py:103-122).  Returns arr0[c0, c0, *cutoffs[1:]]."""
+    _input_validation(A, atol=atol, rtol=rtol)
+    B = np.asarray(B)
+    if A.shape[0] != B.shape[0]:
+        raise ValueError("The matrix A and vector B have incompatible dimensions")
+    try:
+        cutoffs = tuple(int(c) for c in cutoffs)
+    except TypeError:
+        raise ValueError("cutoffs should be array like of length M") from None
+    M = len(cutoffs)
+    if A.shape[0] // 2 != M:
+        raise ValueError("The matrix A and cutoffs have incompatible dimensions")
+    if M <= 1:
+        raise ValueError("The number of modes should be greater than 1.")
+    cutoffs = _check_shape(cutoffs)
+    A = _c128(A)
+    B = _c128(B, (2 * M,))
+    G0 = _c128(G0, (1,))
+    out = _lib.pinned_empty((cutoffs[0], cutoffs[0]) + cutoffs[1:])
+    check(lib.mmh_1leftover_host(M, shape_array(cutoffs), _p(A), _p(B), _p(G0), _p(out)))
+    return out
+
+
+def fast_diagonal(A, b, c, output_cutoff, pnr_cutoffs, stable=False):
+    """Conditional density matrices, output [*(pnr+1), out+1, out+1]; A, b in bargmann order [m0.. | m0..]
+    (strategies/fast_diagonal.py:32-77).  `stable` only changed the rounding of the reference's seed block and is
+    accepted for call compatibility.  For output_cutoff < 2 the reference's weight loop (fast_diagonal.py:68) stops
+    one level early and leaves the top-weight entries wrong; this implementation returns the correct amplitudes
+    (equal to the compactFock path and to the diagonal of the full vanilla lattice)."""
+    pnr_cutoffs = tuple(int(p) for p in pnr_cutoffs)
+    L = len(pnr_cutoffs) + 1
+    perm = [i for m in range(L) for i in (m, m + L)]
+    A = np.asarray(A)[perm, :][:, perm]
+    b = np.asarray(b)[perm]
+    cut = (int(output_cutoff) + 1,) + tuple(p + 1 for p in pnr_cutoffs)
+    out = hermite_multidimensional_1leftoverMode(np.ascontiguousarray(A), b, c, cut)
+    return out.transpose(tuple(range(2, 2 + L - 1)) + (0, 1))

@@ -1,0 +1,88 @@
+"""GPU parity tests for the compactFock diagonal / one-leftover-mode paths (through the C ABI).
+
+Gate: 1e-10 relative / 1e-14 absolute against the reference's golden vectors (the reference evaluates A[i] @ G_in
+with BLAS, so summation order — and therefore the last bits — are not defined by the reference itself)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, assert_parity, random_triple
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gd():
+    return np.load(os.path.join(GOLDEN, "diagonal_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def mm():
+    import mrmustard_b200
+    return mrmustard_b200
+
+
+def test_diagonal_golden(mm, gd):
+    for name in gd["diag_cases"]:
+        A, b, c = gd[f"{name}_A"], gd[f"{name}_b"], complex(gd[f"{name}_c"])
+        cut = tuple(int(x) for x in gd[f"{name}_cut"])
+        G = mm.hermite_renormalized_diagonal(A, b, c, cut)
+        assert_parity(G, gd[f"{name}_G"], name)
+        A2, b2 = mm.backend.reorder_AB_bargmann(A, b)
+        G2 = mm.hermite_renormalized_diagonal(A2, b2, c, cut, reorderedAB=False)
+        assert np.array_equal(G, G2)
+
+
+def test_diagonal_b_batched(mm, gd):
+    # reference test_diagonalbatchNumba_vs_diagonalNumba (tests/test_math/test_lattice/test_lattice_functions.py:66-84)
+    G = mm.hermite_renormalized_diagonal(gd["db_A"], gd["db_b"], complex(gd["db_c"]), tuple(int(x) for x in gd["db_cut"]))
+    assert G.shape == gd["db_G"].shape
+    assert_parity(G, gd["db_G"], "b-batched")
+    G0 = mm.hermite_renormalized_diagonal(gd["db_A"], gd["db_b"][:, 0].copy(), complex(gd["db_c"]), tuple(int(x) for x in gd["db_cut"]))
+    assert np.allclose(G0, G[..., 0], rtol=1e-12, atol=1e-15)
+
+
+def test_diagonal_equals_diagonal_of_vanilla(mm, gd):
+    # reference test_compactFock_diagonal (tests/test_math/test_compactFock.py:19-44)
+    A, b, c = gd["d3_A"], gd["d3_b"], complex(gd["d3_c"])
+    cut = (5, 5, 5)
+    G_ref = mm.hermite_renormalized(A, b, c, cut * 2)
+    ref = np.array([G_ref[tuple(list(i) + list(i))] for i in np.ndindex(*cut)]).reshape(cut)
+    assert np.allclose(ref, mm.hermite_renormalized_diagonal(A, b, c, cut))
+
+
+def test_leftover_golden(mm, gd):
+    for name in gd["leftover_cases"]:
+        A, b, c = gd[f"{name}_A"], gd[f"{name}_b"], complex(gd[f"{name}_c"])
+        oc, pnr = int(gd[f"{name}_oc"]), tuple(int(x) for x in gd[f"{name}_pnr"])
+        G = mm.hermite_renormalized_1leftoverMode(A, b, c, oc, pnr)
+        assert G.shape == (oc + 1, oc + 1) + tuple(p + 1 for p in pnr)
+        assert_parity(np.ascontiguousarray(G), gd[f"{name}_Gcompact"], name + " vs compactFock")
+        assert np.allclose(G, gd[f"{name}_G"], rtol=1e-9, atol=1e-12), name + " vs numpy backend"
+        F = mm.strategies.fast_diagonal(A, b, c, oc, pnr)
+        assert np.allclose(F, gd[f"{name}_Gfast"], rtol=1e-9, atol=1e-12), name + " fast_diagonal layout"
+
+
+def test_leftover_equals_diagonals_of_vanilla(mm, gd):
+    # reference test_compactFock_1leftover (tests/test_math/test_compactFock.py:47-71)
+    A, b, c = gd["l3_A"], gd["l3_b"], complex(gd["l3_c"])
+    G_left = mm.hermite_renormalized_1leftoverMode(A, b, c, output_cutoff=3, pnr_cutoffs=(1, 2))
+    G_ref = mm.hermite_renormalized(A, b, c, (4, 2, 3, 4, 2, 3))
+    expected = np.diagonal(np.diagonal(G_ref, axis1=1, axis2=4), axis1=1, axis2=3)
+    assert np.allclose(expected, G_left)
+
+
+def test_validation_errors(mm):
+    A = np.eye(4, dtype=complex) * 0.1
+    b = np.zeros(4, complex)
+    with pytest.raises(TypeError):
+        mm.strategies.hermite_multidimensional_diagonal([[0.1]], b, 1.0, (3,))
+    with pytest.raises(ValueError):
+        mm.strategies.hermite_multidimensional_diagonal(A[:, :3].copy(), b, 1.0, (3, 3))
+    with pytest.raises(ValueError):
+        mm.strategies.hermite_multidimensional_diagonal(A + np.triu(np.ones((4, 4)), 1), b, 1.0, (3, 3))
+    with pytest.raises(ValueError):
+        mm.strategies.hermite_multidimensional_diagonal(A, b, 1.0, (3, 3, 3))
+    with pytest.raises(ValueError):
+        mm.strategies.hermite_multidimensional_1leftoverMode(np.eye(2, dtype=complex), np.zeros(2, complex), 1.0, (3,))

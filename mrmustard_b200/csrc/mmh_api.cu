@@ -410,9 +410,15 @@ static int vjp_impl(long long batch, int ndim, const int64_t *shape, const void 
     p.sq = ctx->sq;
     p.batch = batch;
     p.nacc = ndim + ndim * (ndim + 1) / 2 + 1;
-    const int block = 256;
+    // batched small lattices: few warps per lattice (long per-thread walks amortise the reduction); one large lattice:
+    // 256-thread CTAs, ~8 per SM
+    int block = 256;
+    if (batch >= 4LL * ctx->sm_count && d.N <= 8192) block = d.N >= 4096 ? 128 : 64;
+    else block = 128;
+    if (const char *e = getenv("MMH_VJP_BLOCK")) block = atoi(e);
     long long want = (d.N + block * 4 - 1) / (block * 4);   // ~4 points per thread
-    long long cap = (8LL * ctx->sm_count + batch - 1) / batch; // ~8 CTAs per SM over the whole batch
+    long long cap = (4LL * ctx->sm_count + batch - 1) / batch; // ~4 CTAs per SM over the whole batch
+    if (const char *e = getenv("MMH_VJP_CTAS_PER_SM")) cap = ((long long)atoi(e) * ctx->sm_count + batch - 1) / batch;
     if (cap < 1) cap = 1;
     if (want > cap) want = cap;
     if (want < 1) want = 1;

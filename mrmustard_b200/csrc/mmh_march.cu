@@ -438,6 +438,20 @@ __global__ void __launch_bounds__((R >= 4 ? 256 : 512) + 32 * MMH_NHW, 1) k_marc
             }
             c128 *dst = ring + (size_t)(u % MMH_KRING) * ringstride;
             c128 *src = xin + (size_t)u * p.hc_max;
+            // canary: the exports of one producer step land within one L2 write latency of each other, so first
+            // watch a single cell per face with back-off instead of hammering L2 with the whole face
+            if (lane < 3 && h[lane]) {
+                const int cc = faceoff[lane];
+                unsigned long long a_, b_;
+                unsigned spins = 0;
+                ld_relaxed_v2_u64(src + cc, a_, b_);
+#pragma unroll 1
+                while ((a_ == MMH_SENTINEL || b_ == MMH_SENTINEL) && ++spins < (1u << 24)) {
+                    __nanosleep(64);
+                    ld_relaxed_v2_u64(src + cc, a_, b_);
+                }
+            }
+            __syncwarp();
 #pragma unroll 1
             for (int c0 = lane; c0 < HC; c0 += 32 * 4) {
                 unsigned long long a[4], b[4];
@@ -454,8 +468,10 @@ __global__ void __launch_bounds__((R >= 4 ? 256 : 512) + 32 * MMH_NHW, 1) k_marc
                     if (!need[w]) continue;
                     unsigned spins = 0;
 #pragma unroll 1
-                    while ((a[w] == MMH_SENTINEL || b[w] == MMH_SENTINEL) && ++spins < (1u << 26))
+                    while ((a[w] == MMH_SENTINEL || b[w] == MMH_SENTINEL) && ++spins < (1u << 24)) {
+                        __nanosleep(32);
                         ld_relaxed_v2_u64(src + c, a[w], b[w]);
+                    }
                     dst[c] = make_double2(__longlong_as_double((long long)a[w]), __longlong_as_double((long long)b[w]));
                     st_relaxed_v2_u64(src + c, MMH_SENTINEL, MMH_SENTINEL);   // self-cleaning
                 }

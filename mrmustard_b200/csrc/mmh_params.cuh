@@ -36,6 +36,7 @@ struct VjpParams {
     long long batch;
     int nblk;
     int nacc;
+    int stride_digits[8];  // mixed-radix digits (radices = shape) of the per-thread walking stride, D <= 8
 };
 
 struct StageParams {

@@ -11,6 +11,9 @@
 // atomics).  HBM traffic is one read of G and one of dLdG (32 B per amplitude); the neighbour reads of G
 // are served by L1/L2.
 #include "mmh_params.cuh"
+#ifndef MMH_VJP_MINB
+#define MMH_VJP_MINB 1
+#endif
 
 
 // accumulator layout: [0, D) = db ; then upper triangle row-major (i, j>=i) ; last = dc
@@ -25,42 +28,67 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-template <int DT>
-__global__ void __launch_bounds__(256) k_vjp_partial(VjpParams p) {
+// numba complex_div_impl (Smith) — only the dLdc = sum / c division uses it
+__device__ __forceinline__ c128 c_div_smith(c128 a, c128 b) {
+    if (fabs(b.x) >= fabs(b.y)) {
+        const double ratio = b.y / b.x, denom = b.x + b.y * ratio;
+        return c_make((a.x + a.y * ratio) / denom, (a.y - a.x * ratio) / denom);
+    }
+    const double ratio = b.x / b.y, denom = b.x * ratio + b.y;
+    return c_make((a.x * ratio + a.y) / denom, (a.y * ratio - a.x) / denom);
+}
+
+// write the final gradients of one lattice from its fully reduced accumulators (layout: db | upper triangle | dc):
+// symmetrisation (dLdA + dLdA^T)/2 (gradients.py:82) and dLdc = sum / c (:80)
+__device__ __forceinline__ void vjp_write_entry(const VjpParams &p, long long lat, int e, c128 s) {
+    const int D = p.d.D;
+    if (e < D) { p.db[lat * D + e] = s; return; }
+    if (e == p.nacc - 1) { p.dc[lat] = c_div_smith(s, p.c[lat]); return; }
+    int r = e - D, i = 0;
+    while (r >= D - i) { r -= D - i; i++; }
+    const int j = i + r;
+    c128 *dA = p.dA + lat * D * D;
+    if (i == j) dA[i * D + i] = s;
+    else { const c128 h = c_make(0.5 * s.x, 0.5 * s.y); dA[i * D + j] = h; dA[j * D + i] = h; }
+}
+
+// IT = unsigned (N < 2^31) or long long.  Threads walk the lattice with a fixed stride; the multi-index is advanced
+// by adding the mixed-radix digits of the stride (precomputed on the host) with carries — no division in the loop.
+template <int DT, typename IT>
+__global__ void __launch_bounds__(256, MMH_VJP_MINB) k_vjp_partial(VjpParams p) {
     constexpr int NACC = VjpAcc<DT>::NACC;
     const LatticeDesc &d = p.d;
-    const long long N = d.N;
+    const IT N = (IT)d.N;
     const long long lat = blockIdx.x;
-    const c128 *G = p.G + lat * N;
-    const c128 *g = p.g + lat * N;
+    const c128 *G = p.G + lat * d.N;
+    const c128 *g = p.g + lat * d.N;
     const double *__restrict__ sq = p.sq;
 
-    long long st[DT];
-    int sh[DT];
+    IT st[DT];
+    int sh[DT], dig[DT];
 #pragma unroll
-    for (int i = 0; i < DT; i++) { st[i] = d.strides[i]; sh[i] = d.shape[i]; }
+    for (int i = 0; i < DT; i++) { st[i] = (IT)d.strides[i]; sh[i] = d.shape[i]; dig[i] = p.stride_digits[i]; }
 
     c128 acc[NACC];
 #pragma unroll
     for (int e = 0; e < NACC; e++) acc[e] = c_make(0.0, 0.0);
 
-    for (long long f = (long long)blockIdx.y * blockDim.x + threadIdx.x; f < N;
-         f += (long long)gridDim.y * blockDim.x) {
-        int k[DT];
-        long long rem = f;
+    const IT stride = (IT)gridDim.y * blockDim.x;
+    IT f = (IT)blockIdx.y * blockDim.x + threadIdx.x;
+    int k[DT];
+    {
+        IT rem = f < N ? f : 0;
 #pragma unroll
-        for (int i = 0; i < DT; i++) {
-            k[i] = (int)(rem / st[i]);
-            rem -= (long long)k[i] * st[i];
-        }
-        (void)sh;
+        for (int i = 0; i < DT; i++) { k[i] = (int)(rem / st[i]); rem -= (IT)k[i] * st[i]; }
+    }
+    for (; f < N; f += stride) {
         const c128 gk = g[f];
         c_fma(acc[NACC - 1], G[f], gk);  // dLdc numerator (gradients.py:80)
         int e = DT;
 #pragma unroll
         for (int i = 0; i < DT; i++) {
             if (k[i] >= 1) {
-                const long long pivot = f - st[i];
+                const IT pivot = f - st[i];
                 const double wi = sq[k[i]];
                 c_fma(acc[i], c_scale(G[pivot], wi), gk);                                   // :68
                 if (k[i] > 1) c_fma(acc[e], c_scale(G[pivot - st[i]], 0.5 * wi * sq[k[i] - 1]), gk);  // :69-73
@@ -69,6 +97,15 @@ __global__ void __launch_bounds__(256) k_vjp_partial(VjpParams p) {
                     if (k[j] >= 1) c_fma(acc[e + (j - i)], c_scale(G[pivot - st[j]], wi * sq[k[j]]), gk);  // :74-75
             }
             e += DT - i;
+        }
+        // advance the multi-index by `stride` (mixed-radix add with carry, last mode first)
+        int carry = 0;
+#pragma unroll
+        for (int i = DT - 1; i >= 0; i--) {
+            int t = k[i] + dig[i] + carry;
+            carry = 0;
+            if (i > 0) { while (t >= sh[i]) { t -= sh[i]; carry++; } }
+            k[i] = t;
         }
     }
 
@@ -82,6 +119,14 @@ __global__ void __launch_bounds__(256) k_vjp_partial(VjpParams p) {
     }
     __syncthreads();
     const int nwarps = (blockDim.x + 31) >> 5;
+    if (p.nblk == 1) {   // the CTA holds the whole lattice: write the gradients directly
+        for (int e = threadIdx.x; e < NACC; e += blockDim.x) {
+            c128 s = c_make(0.0, 0.0);
+            for (int w = 0; w < nwarps; w++) { s.x += red[w][2 * e]; s.y += red[w][2 * e + 1]; }
+            vjp_write_entry(p, lat, e, s);
+        }
+        return;
+    }
     for (int t = threadIdx.x; t < 2 * NACC; t += blockDim.x) {
         double s = 0.0;
         for (int w = 0; w < nwarps; w++) s += red[w][t];
@@ -137,56 +182,58 @@ __global__ void __launch_bounds__(256) k_vjp_partial_generic(VjpParams p) {
     }
 }
 
-// numba complex_div_impl (Smith) — only the dLdc = sum / c division uses it
-__device__ __forceinline__ c128 c_div_smith(c128 a, c128 b) {
-    if (fabs(b.x) >= fabs(b.y)) {
-        const double ratio = b.y / b.x, denom = b.x + b.y * ratio;
-        return c_make((a.x + a.y * ratio) / denom, (a.y - a.x * ratio) / denom);
-    }
-    const double ratio = b.x / b.y, denom = b.x * ratio + b.y;
-    return c_make((a.x * ratio + a.y) / denom, (a.y * ratio - a.x) / denom);
-}
-
-// one thread per (lattice, accumulator entry): fixed-order sum over the per-CTA partials, then the
-// symmetrisation (dLdA + dLdA^T)/2 (gradients.py:82) and dLdc = sum / c (:80)
-__global__ void k_vjp_finish(VjpParams p) {
-    const int D = p.d.D;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= p.batch * p.nacc) return;
-    const long long lat = t / p.nacc;
-    const int e = (int)(t - lat * p.nacc);
+// one warp per (lattice, accumulator entry): lanes sum the per-CTA partials with a fixed stride, then a fixed
+// shuffle tree (deterministic), then the symmetrisation / division epilogue
+__global__ void __launch_bounds__(128) k_vjp_finish(VjpParams p) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= p.batch * p.nacc) return;
+    const long long lat = w / p.nacc;
+    const int e = (int)(w - lat * p.nacc);
     const c128 *part = p.partial + lat * p.nblk * (long long)p.nacc + e;
     c128 s = c_make(0.0, 0.0);
-    for (int blk = 0; blk < p.nblk; blk++) { const c128 v = part[(long long)blk * p.nacc]; s.x += v.x; s.y += v.y; }
-    if (e < D) { p.db[lat * D + e] = s; return; }
-    if (e == p.nacc - 1) { p.dc[lat] = c_div_smith(s, p.c[lat]); return; }
-    int r = e - D, i = 0;
-    while (r >= D - i) { r -= D - i; i++; }
-    const int j = i + r;
-    c128 *dA = p.dA + lat * D * D;
-    if (i == j) dA[i * D + i] = s;
-    else { const c128 h = c_make(0.5 * s.x, 0.5 * s.y); dA[i * D + j] = h; dA[j * D + i] = h; }
+    for (int blk = lane; blk < p.nblk; blk += 32) { const c128 v = part[(long long)blk * p.nacc]; s.x += v.x; s.y += v.y; }
+    s.x = warp_sum(s.x); s.y = warp_sum(s.y);
+    if (lane == 0) vjp_write_entry(p, lat, e, s);
 }
 
-cudaError_t mmh_launch_vjp(const VjpParams &p, int grid_x, int block, cudaStream_t st) {
-    dim3 grid((unsigned)p.batch, grid_x, 1);  // x = lattice (may exceed 65535), y = CTA within the lattice
+template <typename IT>
+static void launch_partial(const VjpParams &p, dim3 grid, int block, cudaStream_t st) {
     switch (p.d.D) {
-        case 1: k_vjp_partial<1><<<grid, block, 0, st>>>(p); break;
-        case 2: k_vjp_partial<2><<<grid, block, 0, st>>>(p); break;
-        case 3: k_vjp_partial<3><<<grid, block, 0, st>>>(p); break;
-        case 4: k_vjp_partial<4><<<grid, block, 0, st>>>(p); break;
-        case 5: k_vjp_partial<5><<<grid, block, 0, st>>>(p); break;
-        case 6: k_vjp_partial<6><<<grid, block, 0, st>>>(p); break;
-        case 7: k_vjp_partial<7><<<grid, block, 0, st>>>(p); break;
-        case 8: k_vjp_partial<8><<<grid, block, 0, st>>>(p); break;
-        default: {
-            grid.z = p.nacc;
-            k_vjp_partial_generic<<<grid, block, 0, st>>>(p);
+        case 1: k_vjp_partial<1, IT><<<grid, block, 0, st>>>(p); break;
+        case 2: k_vjp_partial<2, IT><<<grid, block, 0, st>>>(p); break;
+        case 3: k_vjp_partial<3, IT><<<grid, block, 0, st>>>(p); break;
+        case 4: k_vjp_partial<4, IT><<<grid, block, 0, st>>>(p); break;
+        case 5: k_vjp_partial<5, IT><<<grid, block, 0, st>>>(p); break;
+        case 6: k_vjp_partial<6, IT><<<grid, block, 0, st>>>(p); break;
+        case 7: k_vjp_partial<7, IT><<<grid, block, 0, st>>>(p); break;
+        case 8: k_vjp_partial<8, IT><<<grid, block, 0, st>>>(p); break;
+        default: break;
+    }
+}
+
+cudaError_t mmh_launch_vjp(const VjpParams &p_in, int grid_y, int block, cudaStream_t st) {
+    VjpParams p = p_in;
+    dim3 grid((unsigned)p.batch, grid_y, 1);  // x = lattice (may exceed 65535), y = CTA within the lattice
+    // mixed-radix digits of the per-thread stride grid_y * block
+    {
+        long long s = (long long)grid_y * block;
+        for (int i = p.d.D - 1; i >= 0; i--) {
+            if (i > 0) { p.stride_digits[i] = (int)(s % p.d.shape[i]); s /= p.d.shape[i]; }
+            else p.stride_digits[0] = (int)(s < (1 << 30) ? s : (1 << 30));
         }
+    }
+    if (p.d.D <= 8) {
+        if (p.d.N < 0x7fffffffLL) launch_partial<unsigned>(p, grid, block, st);
+        else launch_partial<long long>(p, grid, block, st);
+    } else {
+        grid.z = p.nacc;
+        k_vjp_partial_generic<<<grid, block, 0, st>>>(p);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const long long total = p.batch * p.nacc;
-    k_vjp_finish<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(p);
+    if (p.nblk == 1 && p.d.D <= 8) return cudaSuccess;   // gradients were written by the partial kernel
+    const long long warps = p.batch * p.nacc;
+    k_vjp_finish<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, st>>>(p);
     return cudaGetLastError();
 }

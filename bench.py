@@ -331,10 +331,16 @@ def main():
     achieved = ALGO_BYTES_PER_AMP_FWD * amps_per_step / (avg_kernel_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    kernel_name = "k_fwd_coop" if w["batch"] is None else "k_fwd_cta<false>"
+    # one step = one mmh_forward[_batched] call = the launches listed here; the roofline figure is the whole step's
+    # algorithmic bytes over the whole step's device time (a lower bound of the dominant kernel's own figure)
+    kernel_name = ("mmh_forward: k_fwd_chain + k_march_stage<2,1> + k_march_tiled<1,2> + k_march_tiled<2,3> (dominant, ~62% of the step)"
+                   if w["batch"] is None else "mmh_forward_batched: k_fwd_chain + k_march_stage<2,1> (dominant, >95% of the step)")
+    traffic_note = None
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(args.workload, {}).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath)).get(args.workload, {})
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_note = f"dram__bytes_read+write of {tj.get('kernel')} from profiles/{tj.get('source')} (ncu --set full), per launch"
         except Exception:
             traffic = None
 
@@ -353,7 +359,7 @@ def main():
                 "api": "mrmustard_b200.strategies.vanilla_numba -> mmh_forward_host (pinned result buffer)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ALGO_BYTES_PER_AMP_FWD * amps_per_step,
                      "avg_launch_ms": avg_kernel_ms},
     }

@@ -195,12 +195,18 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
     int shp[3] = { 1, 1, 1 };
     for (int m = 0; m < nt; m++) shp[m] = d.shape[stage + 1 + m];
     int forced[3] = { 0, 0, 0 };
-    if (const char *eg = getenv("MMH_TILE_G")) sscanf(eg, "%d,%d,%d", &forced[0], &forced[1], &forced[2]);
+    if (const char *eg = getenv("MMH_TILE_G"))   // test / tuning hook; MMH_TILE_STAGE restricts it to one stage
+        if (!getenv("MMH_TILE_STAGE") || atoi(getenv("MMH_TILE_STAGE")) == stage)
+            sscanf(eg, "%d,%d,%d", &forced[0], &forced[1], &forced[2]);
     double best = 1e300;
     int bg[3] = { 0, 0, 0 }, bR = 0, bTC = 0, bLS = 0, bHC = 0, bSq = 0;
-    for (int g0 = 1; g0 <= shp[0] && g0 <= sm_count; g0++)
-        for (int g1 = 1; g1 <= shp[1] && g0 * g1 <= sm_count; g1++)
-            for (int g2 = 1; g2 <= shp[2] && g0 * g1 * g2 <= sm_count; g2++) {
+    // up to two tile-owner CTAs per SM (R <= 2 CTAs of <= 320 threads fit twice in the register file and overlap one
+    // tile's dependent FP64 chain with the other's issue); all tiles must be co-resident
+    // (measured on cfg2: two CTAs per SM give no gain over one, 177 vs 176 us, so the default stays one per SM)
+    const int maxt = getenv("MMH_TILE_MAXT") ? atoi(getenv("MMH_TILE_MAXT")) : sm_count;
+    for (int g0 = 1; g0 <= shp[0] && g0 <= maxt; g0++)
+        for (int g1 = 1; g1 <= shp[1] && g0 * g1 <= maxt; g1++)
+            for (int g2 = 1; g2 <= shp[2] && g0 * g1 * g2 <= maxt; g2++) {
                 if (forced[0] && (g0 != forced[0] || g1 != (forced[1] ? forced[1] : 1) || g2 != (forced[2] ? forced[2] : 1)))
                     continue;
                 const int g[3] = { g0, g1, g2 };
@@ -218,9 +224,13 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
                 int R = 0;
                 const int Rs[3] = { 1, 2, 4 };
                 const char *eR = getenv("MMH_TILE_R");
+                const int ntl = g0 * g1 * g2;
+                const bool two_per_sm = ntl > sm_count;
                 for (int r = 0; r < 3; r++) {
-                    const int tcmax = Rs[r] == 4 ? 256 : 512;
+                    // two CTAs per SM: 2 x (256 + 64) threads x 96 registers
+                    const int tcmax = two_per_sm ? 256 : (Rs[r] == 4 ? 256 : 512);
                     if (eR && atoi(eR) != Rs[r]) continue;
+                    if (two_per_sm && Rs[r] == 4) continue;
                     if ((long long)Rs[r] * tcmax >= TS && (Rs[r] == 1 || Rs[r] * npd <= 12)) { R = Rs[r]; break; }
                 }
                 if (!R) continue;
@@ -229,8 +239,8 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
                 smem = (smem + 15) / 16 * 16;
                 const size_t sqtab_off = smem / 16;
                 smem += sizeof(c128) * (size_t)(S + 2);     // (sqrt, 1/sqrt) table + (b_i, A_ii)
-                if (smem > 200 * 1024) continue;
-                double step_us = (double)TS * 0.55e-3;          // ~0.55 ns per amplitude per SM (FP64 pipe)
+                if (smem > (two_per_sm ? 100 : 200) * 1024) continue;
+                double step_us = (double)TS * 0.55e-3;          // issue time of one panel step of the tile
                 if (step_us < 0.15) step_us = 0.15;             // dependent-chain floor of one panel step
                 const double cost = (S - 1) * step_us + (g0 + g1 + g2 - 3) * 0.7;
                 if (cost < best) {

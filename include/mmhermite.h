@@ -113,6 +113,18 @@ int mmh_diagonal(int M, const int64_t *cutoffs, const void *dA, const void *dB, 
 int mmh_diagonal_host(int M, const int64_t *cutoffs, const void *A, const void *B, int64_t nbatch,
                       const void *G0, void *arr0_out);
 
+/* Jacobians of the diagonal amplitudes (forward mode) ------------------------------------------------------
+ * replaces: grad_hermite_multidimensional_diagonal(A, B, G0, arr0, arr2, arr1010, arr1001, arr1)
+ *           (compactFock/inputValidation.py:82-100 -> diagonal_grad.py:19-354), called from the jax bwd rule
+ *           (math/jax_vjps/hermite.py:292-329).  The forward arrays are recomputed on the device.
+ * A[2M,2M], B[2M] interleaved, G0[1], cutoffs[M] ->
+ *   arr0_dA[cutoffs..., 2M, 2M] (entries of A treated as independent), arr0_dB[cutoffs..., 2M],
+ *   arr0_dG0[cutoffs...] = arr0 / G0.  M <= 8.                                                             */
+int mmh_diagonal_grad(int M, const int64_t *cutoffs, const void *dA, const void *dB, const void *dG0,
+                      void *darr0_dG0_out, void *darr0_dA_out, void *darr0_dB_out, void *stream);
+int mmh_diagonal_grad_host(int M, const int64_t *cutoffs, const void *A, const void *B, const void *G0,
+                           void *arr0_dG0_out, void *arr0_dA_out, void *arr0_dB_out);
+
 /* compactFock "one leftover mode": density matrix of mode 0 conditioned on PNR outcomes of the others ----
  * replaces: hermite_multidimensional_1leftoverMode(A, B, G0, cutoffs)[0]
  *           (inputValidation.py:103-122 -> singleLeftoverMode_amps.py:290-475); the numpy backend computes

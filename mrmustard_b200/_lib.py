@@ -28,15 +28,18 @@ SYMBOLS = [
     "mmh_vjp", "mmh_vjp_host", "mmh_vjp_batched", "mmh_vjp_batched_host",
     "mmh_binomial", "mmh_binomial_host",
     "mmh_diagonal", "mmh_diagonal_host", "mmh_1leftover", "mmh_1leftover_host",
+    "mmh_diagonal_grad", "mmh_diagonal_grad_host",
 ]
 
 
 def _load() -> ctypes.CDLL:
-    if not os.path.exists(SO_PATH):
-        try:  # build in-tree if a toolchain is present; never fall back to a CPU implementation
-            from . import build as _build
+    from . import build as _build
+    if not os.path.exists(SO_PATH) or (_build.is_stale() and _build.have_nvcc()):
+        try:  # (re)build in-tree if a toolchain is present; never fall back to a CPU implementation
             _build.build()
         except Exception as e:  # pragma: no cover
+            if os.path.exists(SO_PATH):
+                raise
             raise ImportError(
                 f"mrmustard_b200: CUDA library {SO_PATH} is missing and could not be built ({e}). "
                 "Run `python -m mrmustard_b200.build`; there is no CPU fallback.") from e
@@ -64,6 +67,8 @@ def _load() -> ctypes.CDLL:
         "mmh_binomial_host": ([ci, p64, vp, vp, vp, dbl, i64, vp, ctypes.POINTER(dbl)], ci),
         "mmh_diagonal": ([ci, p64, vp, vp, i64, vp, vp, vp], ci),
         "mmh_diagonal_host": ([ci, p64, vp, vp, i64, vp, vp], ci),
+        "mmh_diagonal_grad": ([ci, p64, vp, vp, vp, vp, vp, vp, vp], ci),
+        "mmh_diagonal_grad_host": ([ci, p64, vp, vp, vp, vp, vp, vp], ci),
         "mmh_1leftover": ([ci, p64, vp, vp, vp, vp, vp], ci),
         "mmh_1leftover_host": ([ci, p64, vp, vp, vp, vp], ci),
     }

@@ -33,17 +33,36 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+def have_nvcc() -> bool:
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
 def sources() -> list[str]:
     return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
-def is_stale() -> bool:
-    if not os.path.exists(SO):
-        return True
-    t = os.path.getmtime(SO)
-    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+def _source_hash() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")])
     deps.append(os.path.join(os.path.dirname(HERE), "include", "mmhermite.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        h.update(open(d, "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def is_stale() -> bool:
+    """Content-based (not mtime-based): a copied tree (gpurun snapshot) never triggers a spurious rebuild."""
+    stamp = SO + ".srchash"
+    if not os.path.exists(SO) or not os.path.exists(stamp):
+        return True
+    return open(stamp).read().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -57,6 +76,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if res.returncode != 0:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building libmmhermite.so")
+    with open(SO + ".srchash", "w") as f:
+        f.write(_source_hash())
     if verbose:
         print(log)
     return SO

@@ -527,6 +527,81 @@ static int diagonal_impl(int M, const int64_t *cutoffs, int L0, const void *dA, 
     return MMH_OK;
 }
 
+// Jacobian kernels need the value arrays -> run the value sweep into scratch, then the tangent sweep
+__global__ void k_diag_split_jacobian(const c128 *t0, const c128 *arr0, const c128 *G0, long long P, int n2,
+                                      c128 *dG0_out, c128 *dA_out, c128 *dB_out) {
+    const int nt = n2 * n2 + n2;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= P * (nt + 1)) return;
+    const long long p = gid / (nt + 1);
+    const int th = (int)(gid - p * (nt + 1));
+    if (th == nt) {   // arr0_dG0 = arr0 / G0 (inputValidation.py:99)
+        const c128 a = arr0[p], b = G0[0];
+        const double den = b.x * b.x + b.y * b.y;
+        dG0_out[p] = make_double2((a.x * b.x + a.y * b.y) / den, (a.y * b.x - a.x * b.y) / den);
+    } else if (th < n2 * n2) dA_out[p * n2 * n2 + th] = t0[p * nt + th];
+    else dB_out[p * n2 + (th - n2 * n2)] = t0[p * nt + th];
+}
+
+static int diagonal_grad_impl(int M, const int64_t *cutoffs, const void *dA, const void *dB, const void *dG0,
+                              void *o_dG0, void *o_dA, void *o_dB, cudaStream_t st) {
+    if (!cutoffs) return MMH_ERR_NULL_POINTER;
+    if (M < 1 || M > 8) return MMH_ERR_BAD_NDIM;
+    if (!dA || !dB || !dG0 || !o_dG0 || !o_dA || !o_dB) return MMH_ERR_NULL_POINTER;
+    DiagTanParams tp;
+    memset(&tp, 0, sizeof(tp));
+    DiagParams &q = tp.q;
+    q.Md = M; q.L0 = 0; q.c0 = 1; q.nb = 1;
+    int mx = 1, nlevels = 1;
+    long long P = 1;
+    for (int j = 0; j < M; j++) {
+        if (cutoffs[j] < 1 || cutoffs[j] > (1 << 20)) return MMH_ERR_BAD_SHAPE;
+        q.cut[j] = (int)cutoffs[j];
+        if (q.cut[j] > mx) mx = q.cut[j];
+        nlevels += q.cut[j] - 1;
+        if (P > (1LL << 34) / q.cut[j]) return MMH_ERR_TOO_LARGE;
+        P *= q.cut[j];
+    }
+    q.pst[M - 1] = 1;
+    for (int j = M - 1; j > 0; j--) q.pst[j - 1] = q.pst[j] * q.cut[j];
+    q.P = P; q.E = P;
+    const int n2 = 2 * M;
+    tp.ntheta = n2 * n2 + n2;
+    DeviceCtx *ctx;
+    int rc;
+    if ((rc = get_ctx(&ctx))) return rc;
+    if ((rc = ensure_tables(*ctx, mx + 3))) return rc;
+    const long long naux = 2LL * M + M + 2LL * M * (M > 1 ? M - 1 : 1);   // arr1, arr2, arr1010, arr1001
+    const size_t nval = (size_t)(naux + 1) * (size_t)P;
+    const size_t bytes = sizeof(c128) * nval * (size_t)(1 + tp.ntheta);
+    if (bytes > (size_t)120 << 30) return MMH_ERR_TOO_LARGE;
+    if ((rc = ensure_scratch(ctx->diag_ws, bytes))) return rc;
+    CK(cudaMemsetAsync(ctx->diag_ws.ptr, 0, bytes, st));
+    c128 *w = (c128 *)ctx->diag_ws.ptr;
+    q.arr0 = w;    w += P;
+    q.arr1 = w;    w += 2LL * M * P;
+    q.arr2 = w;    w += (long long)M * P;
+    q.arr1010 = w; w += (long long)M * (M > 1 ? M - 1 : 1) * P;
+    q.arr1001 = w; w += (long long)M * (M > 1 ? M - 1 : 1) * P;
+    const long long nt = tp.ntheta;
+    tp.t0 = w;     w += P * nt;
+    tp.t1 = w;     w += 2LL * M * P * nt;
+    tp.t2 = w;     w += (long long)M * P * nt;
+    tp.t1010 = w;  w += (long long)M * (M > 1 ? M - 1 : 1) * P * nt;
+    tp.t1001 = w;
+    q.A = (const c128 *)dA; q.B = (const c128 *)dB; q.sq = ctx->sq;
+    long long launches = 0;
+    CK(mmh_launch_diagonal(q, (const c128 *)dG0, nlevels, &launches, st));
+    g_launches += launches;
+    CK(mmh_launch_diagonal_tangent(tp, nlevels, &launches, st));
+    g_launches += launches + 1;
+    const long long total = P * (nt + 1);
+    k_diag_split_jacobian<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tp.t0, q.arr0, (const c128 *)dG0, P, n2,
+                                                                         (c128 *)o_dG0, (c128 *)o_dA, (c128 *)o_dB);
+    CK(cudaGetLastError());
+    return MMH_OK;
+}
+
 static int diagonal_host_impl(int M, const int64_t *cutoffs, int L0, const void *A, const void *B, long long nbatch,
                               const void *G0, void *out) {
     if (!cutoffs) return MMH_ERR_NULL_POINTER;
@@ -692,6 +767,37 @@ int mmh_diagonal_host(int M, const int64_t *cutoffs, const void *A, const void *
                       void *out) {
     std::lock_guard<std::mutex> lk(g_mutex);
     return diagonal_host_impl(M, cutoffs, 0, A, B, nbatch, G0, out);
+}
+int mmh_diagonal_grad(int M, const int64_t *cutoffs, const void *dA, const void *dB, const void *dG0, void *o_dG0,
+                      void *o_dA, void *o_dB, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return diagonal_grad_impl(M, cutoffs, dA, dB, dG0, o_dG0, o_dA, o_dB, (cudaStream_t)stream);
+}
+int mmh_diagonal_grad_host(int M, const int64_t *cutoffs, const void *A, const void *B, const void *G0, void *o_dG0,
+                           void *o_dA, void *o_dB) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (!cutoffs) return MMH_ERR_NULL_POINTER;
+    if (M < 1 || M > 8) return MMH_ERR_BAD_NDIM;
+    if (!A || !B || !G0 || !o_dG0 || !o_dA || !o_dB) return MMH_ERR_NULL_POINTER;
+    size_t P = 1;
+    for (int j = 0; j < M; j++) { if (cutoffs[j] < 1) return MMH_ERR_BAD_SHAPE; P *= (size_t)cutoffs[j]; }
+    DeviceCtx *ctx;
+    int rc;
+    if ((rc = get_ctx(&ctx))) return rc;
+    const size_t n2 = 2 * (size_t)M;
+    void *dA, *dB, *dG0, *d0, *d1, *d2;
+    if ((rc = stage_in(*ctx, 0, A, sizeof(c128) * n2 * n2, &dA))) return rc;
+    if ((rc = stage_in(*ctx, 1, B, sizeof(c128) * n2, &dB))) return rc;
+    if ((rc = stage_in(*ctx, 2, G0, sizeof(c128), &dG0))) return rc;
+    if ((rc = stage_in(*ctx, 4, nullptr, sizeof(c128) * P, &d0))) return rc;
+    if ((rc = stage_in(*ctx, 5, nullptr, sizeof(c128) * P * n2 * n2, &d1))) return rc;
+    if ((rc = stage_in(*ctx, 6, nullptr, sizeof(c128) * P * n2, &d2))) return rc;
+    if ((rc = diagonal_grad_impl(M, cutoffs, dA, dB, dG0, d0, d1, d2, 0))) return rc;
+    CK(cudaMemcpyAsync(o_dG0, d0, sizeof(c128) * P, cudaMemcpyDeviceToHost, 0));
+    CK(cudaMemcpyAsync(o_dA, d1, sizeof(c128) * P * n2 * n2, cudaMemcpyDeviceToHost, 0));
+    CK(cudaMemcpyAsync(o_dB, d2, sizeof(c128) * P * n2, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    return MMH_OK;
 }
 int mmh_1leftover(int M, const int64_t *cutoffs, const void *dA, const void *dB, const void *dG0, void *dout,
                   void *stream) {

@@ -182,3 +182,128 @@ cudaError_t mmh_launch_diagonal(DiagParams q, const c128 *G0, int nlevels, long 
     }
     return cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Forward-mode Jacobians of the diagonal sweep (diagonal_grad.py:19-354): every stored amplitude X carries the
+// tangents dX/dA[i,l] (4 M^2 of them, A entries treated as independent) and dX/dB[i] (2 M).  The tangent index
+// theta is the innermost thread dimension, so the tangent sweep is the value sweep with a batch of 4M^2 + 2M
+// "directions" and two injection terms (calc_dA_dB, diagonal_grad.py:19-37):
+//     dX = ( dpiv * B[i] + [theta == B_i] piv + sum_l A[i,l] K_l dG_in[l] + [theta == A_il] K_l G_in[l] ) / K_i
+// The value arrays (nb == 1) must have been filled by mmh_launch_diagonal first.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool tan_decode(const DiagTanParams &tp, long long gid, DiagIdx &x, int &theta) {
+    const DiagParams &q = tp.q;
+    const long long Et = q.E * tp.ntheta;
+    if (gid >= Et) return false;
+    theta = (int)(gid % tp.ntheta);
+    long long p = gid / tp.ntheta;     // value-array index (c0 = nb = 1 for the diagonal case)
+    x.idx = p;
+    x.m = x.n = x.t = 0;
+    int sum = 0;
+    for (int j = 0; j < q.Md; j++) {
+        x.params[j] = (int)(p / q.pst[j]);
+        p -= (long long)x.params[j] * q.pst[j];
+        sum += x.params[j];
+    }
+    x.sum = sum;
+    return sum == q.level;
+}
+
+__device__ __forceinline__ c128 tan_write_value(const DiagTanParams &tp, int ii, c128 piv, c128 dpiv, const c128 *G_in,
+                                                const c128 *dG_in, int l_lo, int theta, double K) {
+    const DiagParams &q = tp.q;
+    const int n2 = 2 * q.Md;
+    const c128 *Arow = q.A + (long long)ii * n2;
+    c128 v = cmulf(dpiv, q.B[ii]);
+    if (theta == n2 * n2 + ii) v = caddf(v, piv);                       // dB[i] += pivot_val
+    for (int l = l_lo; l < n2; l++) v = caddf(v, cmulf(Arow[l], dG_in[l]));
+    if (theta < n2 * n2 && theta / n2 == ii) v = caddf(v, G_in[theta % n2]);   // dA[i, l] += K_l G_in[l]
+    return make_double2(v.x / K, v.y / K);
+}
+
+__global__ void __launch_bounds__(256) k_diag_pivot_tan(DiagTanParams tp) {
+    const DiagParams &q = tp.q;
+    DiagIdx x;
+    int theta;
+    if (!tan_decode(tp, (long long)blockIdx.x * blockDim.x + threadIdx.x, x, theta)) return;
+    if (!(q.cut[0] == 1 || x.params[0] < q.cut[0] - 1)) return;
+    const double *__restrict__ sq = q.sq;
+    const int Md = q.Md, nt = tp.ntheta;
+    const long long E = q.E;
+    c128 G_in[2 * MMH_DIAG_MAXMD], dG_in[2 * MMH_DIAG_MAXMD];
+    for (int l = 0; l < 2 * Md; l++) {
+        const int j = l >> 1;
+        G_in[l] = dG_in[l] = make_double2(0.0, 0.0);
+        if (x.params[j] > 0) {
+            const long long o = (long long)(l ^ 1) * E + x.idx - q.pst[j];
+            G_in[l] = cscalef(q.arr1[o], sq[x.params[j]]);
+            dG_in[l] = cscalef(tp.t1[o * nt + theta], sq[x.params[j]]);
+        }
+    }
+    const c128 piv = q.arr0[x.idx], dpiv = tp.t0[x.idx * nt + theta];
+    for (int i = 0; i < 2 * Md; i++) {
+        const int j = i >> 1;
+        if (x.params[j] + 1 < q.cut[j] && (i != 1 || x.params[0] + 2 < q.cut[0]))
+            tp.t1[((long long)i * E + x.idx) * nt + theta] =
+                tan_write_value(tp, i, piv, dpiv, G_in, dG_in, 0, theta, sq[x.params[j] + 1]);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_diag_offdiag_tan(DiagTanParams tp) {
+    const DiagParams &q = tp.q;
+    DiagIdx x;
+    int theta;
+    if (!tan_decode(tp, (long long)blockIdx.x * blockDim.x + threadIdx.x, x, theta)) return;
+    const double *__restrict__ sq = q.sq;
+    const int Md = q.Md, nt = tp.ntheta;
+    const long long E = q.E;
+    c128 G_in[2 * MMH_DIAG_MAXMD], dG_in[2 * MMH_DIAG_MAXMD];
+    for (int d = 0; d < Md; d++) {
+        if (x.params[d] < q.cut[d] - 1) {
+            for (int l = 0; l < 2 * Md; l++) G_in[l] = dG_in[l] = make_double2(0.0, 0.0);
+            G_in[2 * d] = cscalef(q.arr0[x.idx], sq[x.params[d] + 1]);
+            dG_in[2 * d] = cscalef(tp.t0[x.idx * nt + theta], sq[x.params[d] + 1]);
+            if (x.params[d] > 0) {
+                const long long o = (long long)d * E + x.idx - q.pst[d];
+                G_in[2 * d + 1] = cscalef(q.arr2[o], sq[x.params[d]]);
+                dG_in[2 * d + 1] = cscalef(tp.t2[o * nt + theta], sq[x.params[d]]);
+            }
+            for (int i = d + 1; i < Md; i++) {
+                if (x.params[i] > 0) {
+                    const long long o = (long long)(d * (Md - 1) + i - d - 1) * E + x.idx - q.pst[i];
+                    G_in[2 * i] = cscalef(q.arr1001[o], sq[x.params[i]]);
+                    G_in[2 * i + 1] = cscalef(q.arr1010[o], sq[x.params[i]]);
+                    dG_in[2 * i] = cscalef(tp.t1001[o * nt + theta], sq[x.params[i]]);
+                    dG_in[2 * i + 1] = cscalef(tp.t1010[o * nt + theta], sq[x.params[i]]);
+                }
+            }
+            const long long op = (long long)(2 * d) * E + x.idx;
+            const c128 piv = q.arr1[op], dpiv = tp.t1[op * nt + theta];
+            tp.t0[(x.idx + q.pst[d]) * nt + theta] =
+                tan_write_value(tp, 2 * d + 1, piv, dpiv, G_in, dG_in, 2 * d, theta, sq[x.params[d] + 1]);
+            if (x.params[d] + 2 < q.cut[d])
+                tp.t2[((long long)d * E + x.idx) * nt + theta] =
+                    tan_write_value(tp, 2 * d, piv, dpiv, G_in, dG_in, 2 * d, theta, sq[x.params[d] + 2]);
+            for (int i = d + 1; i < Md; i++) {
+                if (x.params[i] + 1 < q.cut[i]) {
+                    const long long o = ((long long)(d * (Md - 1) + i - d - 1) * E + x.idx) * nt + theta;
+                    tp.t1010[o] = tan_write_value(tp, 2 * i, piv, dpiv, G_in, dG_in, 2 * d, theta, sq[x.params[i] + 1]);
+                    tp.t1001[o] = tan_write_value(tp, 2 * i + 1, piv, dpiv, G_in, dG_in, 2 * d, theta, sq[x.params[i] + 1]);
+                }
+            }
+        }
+        if (x.params[d] != 0) break;
+    }
+}
+
+cudaError_t mmh_launch_diagonal_tangent(DiagTanParams tp, int nlevels, long long *launches, cudaStream_t st) {
+    const long long grid = (tp.q.E * tp.ntheta + 255) / 256;
+    *launches = 0;
+    for (int w = 0; w < nlevels; w++) {
+        tp.q.level = w;
+        k_diag_pivot_tan<<<(unsigned)grid, 256, 0, st>>>(tp);
+        k_diag_offdiag_tan<<<(unsigned)grid, 256, 0, st>>>(tp);
+        *launches += 2;
+    }
+    return cudaGetLastError();
+}

@@ -97,4 +97,10 @@ struct DiagParams {
     c128 *arr1010, *arr1001;   // [Md][Md-1] x that
     const double *sq;
 };
+struct DiagTanParams {
+    DiagParams q;        // value arrays (nb == 1, L0 == 0)
+    int ntheta;          // 4 M^2 + 2 M tangent directions: A[i,l] row-major, then B[i]
+    c128 *t0, *t1, *t2, *t1010, *t1001;   // tangents, same layout as the value arrays with theta innermost
+};
+cudaError_t mmh_launch_diagonal_tangent(DiagTanParams tp, int nlevels, long long *launches, cudaStream_t st);
 cudaError_t mmh_launch_diagonal(DiagParams q, const c128 *G0, int nlevels, long long *launches, cudaStream_t st);

@@ -20,6 +20,7 @@ __all__ = [
     "vanilla_numba", "stable_numba", "vanilla_batch_numba", "vanilla_vjp_numba",
     "vanilla_batch_vjp_numba", "binomial", "vanilla", "stable",
     "hermite_multidimensional_diagonal", "hermite_multidimensional_1leftoverMode", "fast_diagonal",
+    "grad_hermite_multidimensional_diagonal", "hermite_renormalized_diagonal_vjp",
 ]
 
 
@@ -240,3 +241,35 @@ def fast_diagonal(A, b, c, output_cutoff, pnr_cutoffs, stable=False):
     cut = (int(output_cutoff) + 1,) + tuple(p + 1 for p in pnr_cutoffs)
     out = hermite_multidimensional_1leftoverMode(np.ascontiguousarray(A), b, c, cut)
     return out.transpose(tuple(range(2, 2 + L - 1)) + (0, 1))
+
+
+def grad_hermite_multidimensional_diagonal(A, B, G0, arr0, arr2=None, arr1010=None, arr1001=None, arr1=None):
+    """Jacobians (arr0_dG0, arr0_dA, arr0_dB) of the diagonal amplitudes (compactFock/inputValidation.py:82-100,
+    diagonal_grad.py:261-354).  The reference takes the five forward arrays; only arr0.shape (= cutoffs) is used here,
+    the forward sweep is recomputed on the device.  Entries of A are treated as independent (no symmetrisation)."""
+    A = _c128(A)
+    B = _c128(B)
+    if A.shape[0] != B.shape[0]:
+        raise ValueError("The matrix A and vector B have incompatible dimensions")
+    if B.ndim != 1:
+        raise ValueError("B batched")          # the reference's jax bwd rule raises the same (jax_vjps/hermite.py:297-298)
+    cutoffs = tuple(int(s) for s in np.shape(arr0))
+    M = A.shape[0] // 2
+    if len(cutoffs) != M:
+        raise ValueError("The matrix A and cutoffs have incompatible dimensions")
+    G0 = _c128(G0, (1,))
+    dG0 = np.empty(cutoffs, np.complex128)
+    dA = np.empty(cutoffs + (2 * M, 2 * M), np.complex128)
+    dB = np.empty(cutoffs + (2 * M,), np.complex128)
+    check(lib.mmh_diagonal_grad_host(M, shape_array(cutoffs), _p(A), _p(B), _p(G0), _p(dG0), _p(dA), _p(dB)))
+    return dG0, dA, dB
+
+
+def hermite_renormalized_diagonal_vjp(A, B, G0, cutoffs, dLdpoly):
+    """The contraction the reference's jax bwd rule performs (jax_vjps/hermite.py:324-329): (dLdA, dLdB, dLdC) from the
+    cotangent of arr0.  A, B interleaved."""
+    cutoffs = tuple(int(c) for c in cutoffs)
+    dG0, dA, dB = grad_hermite_multidimensional_diagonal(A, B, G0, np.empty(cutoffs, np.complex128))
+    g = np.asarray(dLdpoly)
+    ax = tuple(range(g.ndim))
+    return np.sum(g[..., None, None] * dA, axis=ax), np.sum(g[..., None] * dB, axis=ax), np.sum(g * dG0, axis=ax)

@@ -49,6 +49,18 @@ def main():
         assert np.array_equal(G, G2)
         names.append(name)
     out["diag_cases"] = np.array(names)
+    # forward-mode Jacobians (compactFock/inputValidation.py:82-100 -> diagonal_grad.py)
+    from mrmustard.math.lattice.strategies.compactFock.inputValidation import grad_hermite_multidimensional_diagonal
+    gnames = []
+    for name in ("d1", "d2", "d3", "d3c", "d4"):
+        A, b, c = out[f"{name}_A"], out[f"{name}_b"], complex(out[f"{name}_c"])
+        cutoffs = tuple(int(x) for x in out[f"{name}_cut"])
+        A2, b2 = (np.asarray(x) for x in math.backend.reorder_AB_bargmann(A, b))
+        arrs = hermite_multidimensional_diagonal(A2, b2, c, cutoffs)
+        dG0, dA, dB = grad_hermite_multidimensional_diagonal(A2, b2, c, *arrs)
+        out.update({f"{name}_dG0": dG0, f"{name}_dA": dA, f"{name}_dB": dB})
+        gnames.append(name)
+    out["grad_cases"] = np.array(gnames)
     # b-batched diagonal (batch on the LAST axis of B and of the output, diagonal_amps.py:223-233)
     A, b, c = triple([0, 1, 2], 8)
     bb = np.stack([b, 0.5 * b, b + 0.05], axis=1)

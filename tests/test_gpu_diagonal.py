@@ -86,3 +86,34 @@ def test_validation_errors(mm):
         mm.strategies.hermite_multidimensional_diagonal(A, b, 1.0, (3, 3, 3))
     with pytest.raises(ValueError):
         mm.strategies.hermite_multidimensional_1leftoverMode(np.eye(2, dtype=complex), np.zeros(2, complex), 1.0, (3,))
+
+
+def test_diagonal_jacobians_golden(mm, gd):
+    """grad_hermite_multidimensional_diagonal vs the reference's forward-mode Jacobians (diagonal_grad.py)."""
+    for name in gd["grad_cases"]:
+        A, b, c = gd[f"{name}_A"], gd[f"{name}_b"], complex(gd[f"{name}_c"])
+        cut = tuple(int(x) for x in gd[f"{name}_cut"])
+        A2, b2 = mm.backend.reorder_AB_bargmann(A, b)
+        dG0, dA, dB = mm.strategies.grad_hermite_multidimensional_diagonal(np.ascontiguousarray(A2), b2, c, np.empty(cut, complex))
+        assert_parity(dG0, gd[f"{name}_dG0"], name + " dG0")
+        assert_parity(dA, gd[f"{name}_dA"], name + " dA")
+        assert_parity(dB, gd[f"{name}_dB"], name + " dB")
+
+
+def test_diagonal_vjp_finite_differences(mm, gd):
+    A, b, c = gd["d2_A"], gd["d2_b"], complex(gd["d2_c"])
+    cut = (6, 7)
+    A2, b2 = (np.ascontiguousarray(x) for x in mm.backend.reorder_AB_bargmann(A, b))
+    g = np.random.RandomState(0).standard_normal(cut) + 1j * np.random.RandomState(1).standard_normal(cut)
+    dLdA, dLdB, dLdC = mm.strategies.hermite_renormalized_diagonal_vjp(A2, b2, c, cut, g)
+    f = lambda A_, b_, c_: np.sum(g * mm.strategies.hermite_multidimensional_diagonal(A_, b_, c_, cut))
+    f0, eps = f(A2, b2, c), 1e-7
+    assert np.isclose((f(A2, b2, c + eps) - f0) / eps, dLdC, rtol=1e-5, atol=1e-7)
+    for i in range(4):
+        bp = b2.copy(); bp[i] += eps
+        assert np.isclose((f(A2, bp, c) - f0) / eps, dLdB[i], rtol=1e-4, atol=1e-6)
+        for l in range(i, 4):     # the forward validates symmetry: perturb (i,l) and (l,i) together
+            Ap = A2.copy(); Ap[i, l] += eps
+            if l != i: Ap[l, i] += eps
+            want = dLdA[i, l] + (dLdA[l, i] if l != i else 0)
+            assert np.isclose((f(Ap, b2, c) - f0) / eps, want, rtol=1e-4, atol=1e-6)

@@ -173,6 +173,7 @@ static int forward_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st, b
         StageParams sp;
         sp.d = d; sp.A = p.A; sp.b = p.b; sp.G = p.G; sp.sq = p.sq; sp.rsq = p.rsq;
         sp.batch = p.batch; sp.lat_stride = d.N; sp.stage = i; sp.L = L[i];
+        sp.c = p.c; sp.fuse_chain = 0; sp.pdl = 0;
         const long long grid = (p.batch + L[i] - 1) / L[i];
         g_launches++;
         CK(mmh_launch_march_stage(sp, R[i], (int)grid, T[i], sm[i], st));
@@ -264,9 +265,12 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
 static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st) {
     const LatticeDesc &d = p.d;
     const int D = d.D;
-    g_launches++;
-    CK(mmh_launch_chain(p, st));
+    // The launches of one lattice are chained with programmatic dependent launch: each kernel releases its
+    // successor at once and the successor's prologue (index decode, tables) overlaps it, blocking only where it first
+    // touches the lattice.  The chain (stage D-1) is fused into the first march launch when that is a single CTA.
     const size_t absmem = sizeof(c128) * (size_t)(D * D + D);
+    const bool use_pdl = !getenv("MMH_NO_PDL");
+    bool chain_done = false, first = true;
     int rc;
     for (int i = D - 2; i >= 0; i--) {
         if (d.shape[i] == 1) continue;
@@ -277,10 +281,22 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
             StageParams sp;
             sp.d = d; sp.A = p.A; sp.b = p.b; sp.G = p.G; sp.sq = p.sq; sp.rsq = p.rsq;
             sp.batch = 1; sp.lat_stride = d.N; sp.stage = i; sp.L = L;
+            sp.c = p.c; sp.fuse_chain = chain_done ? 0 : 1; sp.pdl = (use_pdl && !first) ? 1 : 0;
+            chain_done = true; first = false;
             g_launches++;
             CK(mmh_launch_march_stage(sp, R, 1, T, sm, st));
+            continue;
+        }
+        if (!chain_done) {
+            g_launches++;
+            CK(mmh_launch_chain(p, st));
+            chain_done = true; first = false;
+        }
+        if (0) {
         } else if (plan_march_tiled(d, i, ctx->sm_count, &tp, &R, &ntiles, &sm)) {
             tp.A = p.A; tp.b = p.b; tp.G = p.G; tp.sq = p.sq; tp.rsq = p.rsq;
+            tp.pdl = (use_pdl && !first && R != 4) ? 1 : 0;
+            first = false;
             {   // exchange buffer: grow-only scratch, (re)filled with the sentinel whenever it is (re)allocated
                 const size_t xbytes = sizeof(c128) * (size_t)ntiles * d.shape[i] * tp.hc_max;
                 if (ctx->xbuf.bytes < xbytes || !ctx->xbuf.ptr) {
@@ -324,7 +340,12 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
                 g_launches++;
                 CK(mmh_launch_panel_step(p, i, s, (int)grid, absmem, st));
             }
+            first = false;
         }
+    }
+    if (!chain_done) {   // D == 1 or every march stage has extent 1: the chain is the whole lattice
+        g_launches++;
+        CK(mmh_launch_chain(p, st));
     }
     return MMH_OK;
 }

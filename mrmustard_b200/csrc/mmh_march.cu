@@ -11,9 +11,16 @@
 // K2  k_fwd_batched_march : one CTA marches L small lattices in lock step (batched path, cfg3).
 // K1  k_fwd_tiled_march   : one lattice, every CTA owns a tile of the panel and exchanges one-cell halos
 //                           with its lower neighbours through L2 + release/acquire flags (cfg2, cfg5).
+#include <cstring>
+
 #include "mmh_params.cuh"
 #include "mmh_points.cuh"
 
+
+// Programmatic dependent launch (sm_90+): a kernel may let its successor in the stream start its prologue early
+// (launch_dependents) and the successor blocks at `wait` until the predecessor grid has completed and flushed.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // Divide all R numerators by sqrt(s) in place.  The IEEE slow path (inf/nan/subnormal-range numerators) is a
 // single warp-level branch for the whole step, so the common path stays branch-free and v's registers are reused.
@@ -58,9 +65,33 @@ __global__ void __launch_bounds__(R >= 4 ? 256 : 512, R >= 4 ? 2 : 1) k_march_st
     const int nlat = (int)((p.batch - lat0) < L ? (p.batch - lat0) : L);
     const int nslots = nlat * P;
 
+    pdl_launch_dependents();
     for (int t = tid; t < nlat; t += T) {
         sba[2 * t] = p.b[(lat0 + t) * D + i];
         sba[2 * t + 1] = p.A[(lat0 + t) * D * D + i * D + i];
+    }
+    if (p.fuse_chain) {
+        // single-lattice path: stage D-1 (the 1-D chain) is done here by one thread per lattice instead of a
+        // separate launch; its amplitudes are panel 0 of this stage (global memory, visible after the barrier)
+        if (tid < nlat) {
+            const long long l = lat0 + tid;
+            const int ic = D - 1;
+            const c128 Ac = p.A[l * D * D + ic * D + ic], bc = p.b[l * D + ic];
+            c128 *g = p.G + l * p.lat_stride;
+            const int Sc = d.shape[ic];
+            c128 p1 = p.c[l], p2 = c_make(0.0, 0.0);
+            g[0] = p1;
+            for (int s = 1; s < Sc; s++) {
+                c128 v = c_mul(bc, p1);
+                if (s >= 2) v = c_add(v, c_mul(c_scale(Ac, sq[s - 1]), p2));
+                v = c_div_table(v, sq[s], rsq[s]);
+                g[s] = v;
+                p2 = p1; p1 = v;
+            }
+        }
+        __syncthreads();
+    } else {
+        pdl_wait();   // panel 0 was written by the previous launch in the stream
     }
 
     // ---- per-slot constants (registers) -------------------------------------------------------------------
@@ -142,6 +173,7 @@ __global__ void __launch_bounds__(R >= 4 ? 256 : 512, R >= 4 ? 2 : 1) k_march_st
 // thread-per-lattice chain: stage D-1 (k_<D-1 = 0), G[n] = (b G[n-1] + A sqrt(n-1) G[n-2]) / sqrt(n).
 // For D == 1 this is the whole lattice (cfg1).
 __global__ void __launch_bounds__(128) k_fwd_chain(FwdParams p) {
+    pdl_launch_dependents();
     const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= p.batch) return;
     const int D = p.d.D, i = D - 1;
@@ -159,14 +191,26 @@ __global__ void __launch_bounds__(128) k_fwd_chain(FwdParams p) {
     }
 }
 
+// launch with (pdl = true) or without programmatic stream serialization
+template <typename P>
+static cudaError_t launch_pdl(void (*kern)(P), int grid, int block, size_t smem, cudaStream_t st, bool pdl, const P &p) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
 template <int R>
 static cudaError_t launch_stage_R(const StageParams &p, int grid, int block, size_t smem, cudaStream_t st) {
 #define MMH_CASE(N)                                                                                   \
     case N:                                                                                           \
         if (smem > 48 * 1024)                                                                         \
             cudaFuncSetAttribute(k_march_stage<R, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        k_march_stage<R, N><<<grid, block, smem, st>>>(p);                                            \
-        return cudaGetLastError();
+        return launch_pdl(k_march_stage<R, N>, grid, block, smem, st, p.pdl != 0, p);
     const int npd = p.d.D - 1 - p.stage;
     switch (npd) {
         MMH_CASE(1) MMH_CASE(2)
@@ -279,6 +323,7 @@ __global__ void __launch_bounds__((R >= 4 ? 256 : 512) + 32 * MMH_NHW, 1) k_marc
     const double *__restrict__ sq = p.sq;
     const double *__restrict__ rsq = p.rsq;
 
+    pdl_launch_dependents();
     // ---- tile geometry ----------------------------------------------------------------------------------
     int g[3], t[3], lo[3], e[3], h[3], gst[3], shp[3];
 #pragma unroll
@@ -332,6 +377,7 @@ __global__ void __launch_bounds__((R >= 4 ? 256 : 512) + 32 * MMH_NHW, 1) k_marc
     if (tid <= MMH_KRING) sync_words[tid] = 0;
     for (int s_ = tid; s_ < S; s_ += blockDim.x) sqtab[s_] = make_double2(sq[s_], rsq[s_]);
     __syncthreads();
+    pdl_wait();   // everything above overlapped the previous stage's kernel; panel 0 and X are touched from here on
     // panel 0 halo -> ring slot 0 (panel 0 is final: the previous stage's kernel has completed)
     for (int c = tid; c < HC; c += blockDim.x) ring[c] = __ldcg(p.G + hal_gofs[c]);
 
@@ -562,8 +608,7 @@ static cudaError_t launch_tiled_R(const TiledParams &p, int ntiles, size_t smem,
     case N:                                                                                           \
         if (smem > 48 * 1024)                                                                         \
             cudaFuncSetAttribute(k_march_tiled<R, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        k_march_tiled<R, N><<<ntiles, block, smem, st>>>(p);                                          \
-        return cudaGetLastError();
+        return launch_pdl(k_march_tiled<R, N>, ntiles, block, smem, st, p.pdl != 0, p);
     const int npd = p.d.D - 1 - p.stage;
     switch (npd) {
         MMH_CASE(1) MMH_CASE(2) MMH_CASE(3)

@@ -48,6 +48,9 @@ struct StageParams {
     long long lat_stride;        // elements between consecutive lattices in G (= N)
     int stage;                   // i: the index being marched (k_<i = 0)
     int L;                       // lattices marched in lock step by one CTA
+    const c128 *c;               // vacuum amplitudes (used when fuse_chain)
+    int fuse_chain;              // 1: this launch also computes stage D-1 (the chain) of its lattices first
+    int pdl;                     // 1: launched with programmatic stream serialization (waits for the previous launch)
 };
 
 struct TiledParams {
@@ -64,6 +67,7 @@ struct TiledParams {
     int tc;                      // compute threads (multiple of 32); the CTA adds its halo warps on top
     int ls_max;                  // shared-memory stride of one panel buffer (>= local box size of any tile)
     int hc_max;                  // shared-memory stride of one halo ring slot (>= halo cells of any tile)
+    int pdl;                     // 1: launched with programmatic stream serialization
     unsigned long long *trace;   // debug timeline [tile][step][4] of %globaltimer stamps (MMH_TRACE_FILE), else NULL
 };
 

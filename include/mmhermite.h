@@ -71,6 +71,15 @@ int mmh_forward_batched(int64_t batch, int ndim, const int64_t *shape, const voi
 int mmh_forward_batched_host(int64_t batch, int ndim, const int64_t *shape, const void *A,
                              const void *b, const void *c, void *G, int stable);
 
+/* One panel step of the vanilla fill restricted to a contiguous range of panel offsets: every amplitude
+ * G[k] with k_<stage = 0, k_stage = step and panel offset f in [f_lo, f_hi) (f = the flat index of
+ * (k_{stage+1}, ..., k_{ndim-1})), from panels step-1 and step-2 of the same lattice (vanilla/core.py:108-122 restricted
+ * to a slab).  This is the unit of work of the multi-GPU decomposition of ONE large lattice
+ * (mrmustard_b200/sharding.py:forward_single_sharded): ranks own ranges of f and exchange the last strides[stage+1]
+ * amplitudes of their range after every step.  G is the whole lattice (device pointer); no synchronisation.      */
+int mmh_forward_panel_range(int ndim, const int64_t *shape, const void *dA, const void *db, void *dG, int stage,
+                            int64_t step, int64_t f_lo, int64_t f_hi, void *stream);
+
 /* vector-Jacobian product ------------------------------------------------------------------------
  * replaces: strategies.vanilla_vjp_numba (vanilla/gradients.py:25-82), called from the jax backend's
  *           custom_vjp bwd (math/jax_vjps/hermite.py:86-102).

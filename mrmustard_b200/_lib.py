@@ -24,7 +24,7 @@ _EXC = {
 SYMBOLS = [
     "mmh_version", "mmh_error_string", "mmh_device_count", "mmh_set_device", "mmh_device_synchronize",
     "mmh_launch_count", "mmh_host_alloc", "mmh_host_free",
-    "mmh_forward", "mmh_forward_host", "mmh_forward_batched", "mmh_forward_batched_host",
+    "mmh_forward", "mmh_forward_host", "mmh_forward_batched", "mmh_forward_batched_host", "mmh_forward_panel_range",
     "mmh_vjp", "mmh_vjp_host", "mmh_vjp_batched", "mmh_vjp_batched_host",
     "mmh_binomial", "mmh_binomial_host",
     "mmh_diagonal", "mmh_diagonal_host", "mmh_1leftover", "mmh_1leftover_host",
@@ -58,6 +58,7 @@ def _load() -> ctypes.CDLL:
         "mmh_forward": ([ci, p64, vp, vp, vp, vp, ci, vp], ci),
         "mmh_forward_host": ([ci, p64, vp, vp, vp, vp, ci], ci),
         "mmh_forward_batched": ([i64, ci, p64, vp, vp, vp, vp, ci, vp], ci),
+        "mmh_forward_panel_range": ([ci, p64, vp, vp, vp, ci, i64, i64, i64, vp], ci),
         "mmh_forward_batched_host": ([i64, ci, p64, vp, vp, vp, vp, ci], ci),
         "mmh_vjp": ([ci, p64, vp, vp, vp, vp, vp, vp, vp], ci),
         "mmh_vjp_host": ([ci, p64, vp, vp, vp, vp, vp, vp], ci),

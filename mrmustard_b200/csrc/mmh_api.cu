@@ -338,7 +338,7 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
             if (grid > 8LL * ctx->sm_count) grid = 8LL * ctx->sm_count;
             for (int s = 1; s < d.shape[i]; s++) {
                 g_launches++;
-                CK(mmh_launch_panel_step(p, i, s, (int)grid, absmem, st));
+                CK(mmh_launch_panel_step(p, i, s, 0, P, (int)grid, absmem, st));
             }
             first = false;
         }
@@ -699,6 +699,33 @@ int mmh_forward(int ndim, const int64_t *shape, const void *dA, const void *db, 
                 int stable, void *stream) {
     std::lock_guard<std::mutex> lk(g_mutex);
     return forward_impl(1, ndim, shape, dA, db, dc, dG, stable, (cudaStream_t)stream);
+}
+
+int mmh_forward_panel_range(int ndim, const int64_t *shape, const void *dA, const void *db, void *dG, int stage,
+                            int64_t step, int64_t f_lo, int64_t f_hi, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    LatticeDesc d;
+    int mx;
+    int rc = make_desc(ndim, shape, &d, &mx);
+    if (rc) return rc;
+    if (!dA || !db || !dG) return MMH_ERR_NULL_POINTER;
+    if (stage < 0 || stage >= ndim || step < 1 || step >= d.shape[stage]) return MMH_ERR_BAD_SHAPE;
+    if (f_lo < 0 || f_hi > d.strides[stage] || f_lo > f_hi) return MMH_ERR_BAD_SHAPE;
+    if (f_lo == f_hi) return MMH_OK;
+    DeviceCtx *ctx;
+    if ((rc = get_ctx(&ctx))) return rc;
+    if ((rc = ensure_tables(*ctx, mx + 1))) return rc;
+    FwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.d = d;
+    p.A = (const c128 *)dA; p.b = (const c128 *)db; p.c = nullptr; p.G = (c128 *)dG;
+    p.sq = ctx->sq; p.rsq = ctx->rsq; p.batch = 1;
+    long long grid = (f_hi - f_lo + 255) / 256;
+    if (grid > 8LL * ctx->sm_count) grid = 8LL * ctx->sm_count;
+    g_launches++;
+    CK(mmh_launch_panel_step(p, stage, (int)step, f_lo, f_hi, (int)grid, sizeof(c128) * (size_t)(ndim * ndim + ndim),
+                             (cudaStream_t)stream));
+    return MMH_OK;
 }
 
 int mmh_forward_batched(int64_t batch, int ndim, const int64_t *shape, const void *dA, const void *db,

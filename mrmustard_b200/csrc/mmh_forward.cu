@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) k_stable_coop(FwdParams p) {
 
 // One (stage, step) panel as a plain grid-stride kernel: used when the panel is too large for the tiled
 // march (e.g. the 35.8 M-point panels of an (12,)*8 lattice), where a launch per step costs nothing.
-__global__ void __launch_bounds__(256) k_panel_step(FwdParams p, int stage, int s) {
+__global__ void __launch_bounds__(256) k_panel_step(FwdParams p, int stage, int s, long long f_lo, long long f_hi) {
     extern __shared__ c128 smem[];
     c128 *sA = smem;
     c128 *sb = smem + p.d.D * p.d.D;
@@ -190,7 +190,8 @@ __global__ void __launch_bounds__(256) k_panel_step(FwdParams p, int stage, int 
     const long long P = d.strides[stage];
     c128 *G = p.G;
     const long long base = (long long)s * P;
-    for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < P; f += (long long)gridDim.x * blockDim.x)
+    (void)P;
+    for (long long f = f_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; f < f_hi; f += (long long)gridDim.x * blockDim.x)
         G[base + f] = vanilla_point(d, sA, sb, G, p.sq, p.rsq, stage, s, f);
 }
 
@@ -278,8 +279,9 @@ cudaError_t mmh_launch_fwd_coop(const FwdParams &p, bool stable, int grid, int b
     return cudaLaunchCooperativeKernel((void *)k_fwd_coop, dim3(grid), dim3(block), args, smem, st);
 }
 
-cudaError_t mmh_launch_panel_step(const FwdParams &p, int stage, int s, int grid, size_t smem, cudaStream_t st) {
-    k_panel_step<<<grid, 256, smem, st>>>(p, stage, s);
+cudaError_t mmh_launch_panel_step(const FwdParams &p, int stage, int s, long long f_lo, long long f_hi, int grid,
+                                  size_t smem, cudaStream_t st) {
+    k_panel_step<<<grid, 256, smem, st>>>(p, stage, s, f_lo, f_hi);
     return cudaGetLastError();
 }
 

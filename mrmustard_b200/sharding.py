@@ -85,3 +85,104 @@ def vjp_batched_sharded(G_local, c, dLdG_local, rows, gather=True, compute=None)
     B = c.shape[0]
     return (_all_gather_rows(dA, B, dist, world), _all_gather_rows(db, B, dist, world),
             _all_gather_rows(dc.reshape(-1, 1), B, dist, world).reshape(-1))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ONE large lattice over several GPUs (second bullet)
+# ---------------------------------------------------------------------------------------------------------------
+# With the first-non-zero pivot every point with k_0 >= 1 reads only panels k_0 - 1 and k_0 - 2 (mmh_forward.cu), and
+# inside panel k_0 - 1 only offsets f - strides[j], j >= 1, i.e. at most strides[1] positions back.  So the stage-0
+# panels are cut into contiguous ranges of the panel offset f, rank r owns range r of EVERY panel, all ranks compute
+# panel s concurrently, and between steps rank r sends the last strides[1] amplitudes of its range to the rank(s)
+# above it (NCCL send/recv over NVLink; no reduction, no barrier beyond the p2p dependencies).  The sub-lattice
+# k_0 = 0 (1/shape[0] of the work) is computed redundantly by every rank.
+class CudaPanelOps:
+    """Device-side operations of forward_single_sharded through the C ABI (torch tensors are plumbing only)."""
+
+    def __init__(self):
+        import torch
+        from . import _lib
+        self.torch, self._lib = torch, _lib
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def alloc(self, n):
+        return self.torch.empty(n, dtype=self.torch.complex128, device=self.device)
+
+    def to_dev(self, x):
+        return self.torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.complex128))).to(self.device)
+
+    def _stream(self):
+        import ctypes
+        return ctypes.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    def sublattice(self, G, shape, A, b, c):
+        L = self._lib
+        D = len(shape)
+        dA, db, dc = self.to_dev(np.asarray(A)[1:, 1:]), self.to_dev(np.asarray(b)[1:]), self.to_dev(np.asarray(c).reshape(1))
+        L.check(L.lib.mmh_forward(D - 1, L.shape_array(shape[1:]), dA.data_ptr(), db.data_ptr(), dc.data_ptr(),
+                                  G.data_ptr(), 0, self._stream()))
+        self._keep = (dA, db, dc)
+
+    def prepare(self, shape, A, b):
+        self._A, self._b = self.to_dev(A), self.to_dev(b)
+
+    def panel_range(self, G, shape, step, f_lo, f_hi):
+        L = self._lib
+        L.check(L.lib.mmh_forward_panel_range(len(shape), L.shape_array(shape), self._A.data_ptr(), self._b.data_ptr(),
+                                              G.data_ptr(), 0, int(step), int(f_lo), int(f_hi), self._stream()))
+
+
+def forward_single_sharded(shape, A, b, c, gather=True, ops=None):
+    """hermite_renormalized (vanilla rule) of ONE lattice, stage 0 sharded over the ranks of the default process group.
+
+    Returns the full lattice on every rank (gather=True) or (G_local, (f_lo, f_hi)) where G_local is this rank's full-size
+    buffer holding the complete sub-lattice k_0 = 0 and, for k_0 >= 1, this rank's range of every panel (plus halos)."""
+    import torch
+    shape = tuple(int(s) for s in shape)
+    D = len(shape)
+    if D < 2:
+        raise ValueError("forward_single_sharded needs at least two modes")
+    dist, rank, world = _dist()
+    if ops is None:
+        ops = CudaPanelOps()
+    N = int(np.prod(shape, dtype=np.int64))
+    S0 = shape[0]
+    P = N // S0
+    H = int(np.prod(shape[2:], dtype=np.int64))          # strides[1]: the deepest look-back inside panel s - 1
+    G = ops.alloc(N)
+    ops.sublattice(G, shape, A, b, c)                     # panel 0, redundantly on every rank
+    ops.prepare(shape, A, b)
+    ranges = [shard_range(P, r, world) for r in range(world)]
+    f_lo, f_hi = ranges[rank]
+    Gr = torch.view_as_real(G)                            # NCCL/gloo p2p on the (re, im) view
+    for s in range(1, S0):
+        ops.panel_range(G, shape, s, f_lo, f_hi)
+        if world > 1 and s < S0 - 1:
+            reqs = []
+            for q in range(world):                        # rank q needs [f_lo_q - H, f_lo_q) of panel s from lower ranks
+                need_lo, need_hi = max(ranges[q][0] - H, 0), ranges[q][0]
+                for r in range(q):
+                    lo, hi = max(ranges[r][0], need_lo), min(ranges[r][1], need_hi)
+                    if hi <= lo:
+                        continue
+                    view = Gr[s * P + lo: s * P + hi]
+                    if rank == r:
+                        reqs.append(dist.P2POp(dist.isend, view, q))
+                    elif rank == q:
+                        reqs.append(dist.P2POp(dist.irecv, view, r))
+            if reqs:
+                for w in dist.batch_isend_irecv(reqs):
+                    w.wait()
+    if not gather or world == 1:
+        return (G, (f_lo, f_hi)) if not gather else G
+    # gather: rank r owns columns [f_lo_r, f_hi_r) of the (S0 - 1, P) matrix of panels 1..S0-1
+    maxw = max(hi - lo for lo, hi in ranges)
+    body = G[P:].view(S0 - 1, P)
+    send = torch.zeros((S0 - 1, maxw), dtype=torch.complex128, device=G.device)
+    send[:, : f_hi - f_lo] = body[:, f_lo:f_hi]
+    recv = [torch.empty_like(torch.view_as_real(send)) for _ in range(world)]
+    dist.all_gather(recv, torch.view_as_real(send).contiguous())
+    for r, (lo, hi) in enumerate(ranges):
+        if r != rank:
+            body[:, lo:hi] = torch.view_as_complex(recv[r])[:, : hi - lo]
+    return G

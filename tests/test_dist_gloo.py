@@ -63,3 +63,64 @@ def test_shard_range_is_a_partition():
             assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
             sizes = [hi - lo for lo, hi in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ---- one lattice sharded over two ranks (panel ranges + p2p halo exchange); CPU ops injected by the test ----------
+class _CpuPanelOps:
+    """numpy restatement of the two device operations, driven by the oracle's arithmetic (test-only)."""
+
+    def alloc(self, n):
+        return torch.zeros(n, dtype=torch.complex128)
+
+    def sublattice(self, G, shape, A, b, c):
+        import oracle
+        sub = oracle.vanilla(shape[1:], np.asarray(A)[1:, 1:], np.asarray(b)[1:], complex(np.asarray(c).reshape(-1)[0]))
+        G[: sub.size] = torch.from_numpy(sub.ravel().copy())
+
+    def prepare(self, shape, A, b):
+        self.A, self.b = np.asarray(A, complex), np.asarray(b, complex)
+
+    def panel_range(self, G, shape, step, f_lo, f_hi):
+        # vanilla update with pivot 0 (core.py:108-122), same operation order as the oracle
+        g = G.numpy()
+        D = len(shape)
+        strides = [int(np.prod(shape[i + 1:])) for i in range(D)]
+        P = strides[0]
+        for f in range(f_lo, f_hi):
+            flat = step * P + f
+            pivot = flat - P
+            k = np.unravel_index(f, shape[1:]) if D > 1 else ()
+            v = self.b[0] * g[pivot]
+            if step >= 2:
+                v = v + (self.A[0, 0] * np.sqrt(step - 1)) * g[pivot - P]
+            for j in range(1, D):
+                if k[j - 1] > 0:
+                    v = v + (self.A[0, j] * np.sqrt(k[j - 1])) * g[pivot - strides[j]]
+            g[flat] = v / np.sqrt(step)
+
+
+def _single_worker(rank, world, port, shape, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from mrmustard_b200 import sharding
+    A, b, c = random_triple(len(shape), (), seed=9)
+    G = sharding.forward_single_sharded(shape, A, b, complex(c), gather=True, ops=_CpuPanelOps())
+    want = oracle.vanilla(shape, A, b, complex(c))
+    q.put((rank, bool(np.allclose(G.numpy().reshape(shape), want, rtol=1e-12, atol=1e-15))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape", [(5, 4, 3), (4, 7), (3, 2, 3, 2)])
+def test_single_lattice_two_ranks(shape):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_single_worker, args=(r, world, port, shape, q)) for r in range(world)]
+    for p in procs: p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs: p.join(timeout=60)
+    assert all(ok for _, ok in res), res

@@ -191,8 +191,13 @@ __global__ void __launch_bounds__(256) k_panel_step(FwdParams p, int stage, int 
     c128 *G = p.G;
     const long long base = (long long)s * P;
     (void)P;
-    for (long long f = f_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; f < f_hi; f += (long long)gridDim.x * blockDim.x)
-        G[base + f] = vanilla_point(d, sA, sb, G, p.sq, p.rsq, stage, s, f);
+    if (d.N < 0x7fffffffLL) {   // 32-bit index arithmetic
+        for (long long f = f_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; f < f_hi; f += (long long)gridDim.x * blockDim.x)
+            G[base + f] = vanilla_point32(d, sA, sb, G, p.sq, p.rsq, stage, s, (unsigned)f);
+    } else {
+        for (long long f = f_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; f < f_hi; f += (long long)gridDim.x * blockDim.x)
+            G[base + f] = vanilla_point(d, sA, sb, G, p.sq, p.rsq, stage, s, f);
+    }
 }
 
 // ---- binomial: level wavefront in one CTA with deterministic per-level norm and early stop ---------
@@ -279,8 +284,75 @@ cudaError_t mmh_launch_fwd_coop(const FwdParams &p, bool stable, int grid, int b
     return cudaLaunchCooperativeKernel((void *)k_fwd_coop, dim3(grid), dim3(block), args, smem, st);
 }
 
+// Same panel step with a division-free index walk: each thread advances its multi-index by the mixed-radix digits of
+// the walking stride (as k_vjp_partial does).  NPD = number of panel dims = D - 1 - stage (<= 8), N < 2^31.
+struct PanelWalk { int dig[8]; };
+
+template <int NPD>
+__global__ void __launch_bounds__(256) k_panel_step_walk(FwdParams p, int stage, int s, unsigned f_lo, unsigned f_hi, PanelWalk w) {
+    extern __shared__ c128 smem[];
+    const LatticeDesc &d = p.d;
+    const int D = d.D;
+    c128 *sA = smem;
+    c128 *sb = smem + D * D;
+    load_Ab(p, 0, sA, sb);
+    __syncthreads();
+    const double *__restrict__ sq = p.sq;
+    const double *__restrict__ rsq = p.rsq;
+    unsigned st[NPD];
+    int sh[NPD], k[NPD];
+#pragma unroll
+    for (int jj = 0; jj < NPD; jj++) { st[jj] = (unsigned)d.strides[stage + 1 + jj]; sh[jj] = d.shape[stage + 1 + jj]; }
+    const unsigned P = (unsigned)d.strides[stage];
+    c128 *G = p.G;
+    const c128 *Gp = G + (size_t)(s - 1) * P;        // panel s-1
+    const c128 *Gpp = G + (size_t)(s >= 2 ? s - 2 : 0) * P;
+    c128 *Gc = G + (size_t)s * P;
+    const c128 bi = sb[stage], aii = c_scale(sA[stage * D + stage], sq[s - 1]);
+    const double sqs = sq[s], rsqs = rsq[s];
+    const unsigned stride = gridDim.x * blockDim.x;
+    unsigned f = f_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    {
+        unsigned rem = f < f_hi ? f : 0;
+#pragma unroll
+        for (int jj = 0; jj < NPD; jj++) { k[jj] = (int)(rem / st[jj]); rem -= (unsigned)k[jj] * st[jj]; }
+    }
+    for (; f < f_hi; f += stride) {
+        c128 val = c_mul(bi, Gp[f]);
+        if (s >= 2) val = c_add(val, c_mul(aii, Gpp[f]));
+#pragma unroll
+        for (int jj = 0; jj < NPD; jj++)
+            if (k[jj] > 0) val = c_add(val, c_mul(c_scale(sA[stage * D + stage + 1 + jj], sq[k[jj]]), Gp[f - st[jj]]));
+        Gc[f] = c_div_table(val, sqs, rsqs);
+        int carry = 0;
+#pragma unroll
+        for (int jj = NPD - 1; jj >= 0; jj--) {
+            int t = k[jj] + w.dig[jj] + carry;
+            carry = 0;
+            if (jj > 0) { while (t >= sh[jj]) { t -= sh[jj]; carry++; } }
+            k[jj] = t;
+        }
+    }
+}
+
 cudaError_t mmh_launch_panel_step(const FwdParams &p, int stage, int s, long long f_lo, long long f_hi, int grid,
                                   size_t smem, cudaStream_t st) {
+    const int npd = p.d.D - 1 - stage;
+    if (p.d.N < 0x7fffffffLL && npd >= 1 && npd <= 8) {
+        PanelWalk w;
+        long long sd = (long long)grid * 256;
+        for (int jj = npd - 1; jj >= 0; jj--) {
+            const int shj = p.d.shape[stage + 1 + jj];
+            if (jj > 0) { w.dig[jj] = (int)(sd % shj); sd /= shj; }
+            else w.dig[0] = (int)(sd < (1 << 30) ? sd : (1 << 30));
+        }
+        switch (npd) {
+#define MMH_CASE(N) case N: k_panel_step_walk<N><<<grid, 256, smem, st>>>(p, stage, s, (unsigned)f_lo, (unsigned)f_hi, w); break;
+            MMH_CASE(1) MMH_CASE(2) MMH_CASE(3) MMH_CASE(4) MMH_CASE(5) MMH_CASE(6) MMH_CASE(7) MMH_CASE(8)
+#undef MMH_CASE
+        }
+        return cudaGetLastError();
+    }
     k_panel_step<<<grid, 256, smem, st>>>(p, stage, s, f_lo, f_hi);
     return cudaGetLastError();
 }

@@ -165,6 +165,17 @@ def main():
     G, norm = S.binomial((4, 3, 5), A3d, b3d, complex(c3d), 1e9, 10)
     out.update(bin3_A=A3d, bin3_b=b3d, bin3_c=np.asarray(c3d), bin3_G=G, bin3_norm=np.asarray(norm))
 
+    # ---- reference test_vanilla_stable (tests/test_math/test_lattice/test_lattice_functions.py:137-149):
+    # Dgate(4+4j) and Sgate(r=4, phi=2) at cutoff 1000 through the stable strategy
+    from mrmustard.lab import Dgate  # noqa: PLC0415
+    for tag, gate in {"dg": Dgate(0, 4 + 4j), "sg": Sgate(0, r=4.0, phi=2.0)}.items():
+        At, bt, ct = (np.asarray(x, dtype=np.complex128) for x in gate.bargmann_triple())
+        Gt = S.stable_numba((1000, 1000), At, bt, complex(ct))
+        out.update({f"st_{tag}_A": At, f"st_{tag}_b": bt, f"st_{tag}_c": ct, f"st_{tag}_sha": np.array(sha(Gt)),
+                    f"st_{tag}_sample": Gt.ravel()[::7919].copy(), f"st_{tag}_absmax": np.asarray(np.abs(Gt).max())})
+    from mrmustard.math.lattice.strategies.displacement import displacement  # noqa: PLC0415
+    out["st_dg_closed_form_sample"] = displacement((1000, 1000), 4.0 + 4.0j).ravel()[::7919].copy()
+
     path = os.path.join(HERE, "vanilla_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) / 1e6, "MB;", len(out), "arrays")

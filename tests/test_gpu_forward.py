@@ -199,3 +199,17 @@ def test_reference_manager_semantics(O):
             mm.hermite_renormalized(A, b, c, shape, out=np.zeros((2, 1, 3, 5), complex))
         with pytest.raises(ValueError):
             mm.hermite_renormalized(A, b[:1], c, shape)
+
+
+@pytest.mark.parametrize("tag", ["dg", "sg"])
+def test_stable_cutoff_1000(S, golden, tag):
+    """Reference test_vanilla_stable (test_lattice_functions.py:137-149): Dgate(4+4j) / Sgate(r=4) at cutoff 1000 with the
+    stable rule, bit-identical to stable_numba, equal to the closed-form displacement, bounded for the squeezer."""
+    A, b, c = golden[f"st_{tag}_A"], golden[f"st_{tag}_b"], complex(golden[f"st_{tag}_c"])
+    G = S.stable_numba((1000, 1000), A, b, c)
+    assert sha(G) == str(golden[f"st_{tag}_sha"])
+    assert np.array_equal(G.ravel()[::7919], golden[f"st_{tag}_sample"])
+    if tag == "dg":
+        assert np.allclose(G.ravel()[::7919], golden["st_dg_closed_form_sample"])
+    else:
+        assert np.max(np.abs(G)) < 1

@@ -124,3 +124,15 @@ def test_binomial_3d(golden):
     G, norm = oracle.binomial((4, 3, 5), golden["bin3_A"], golden["bin3_b"], complex(golden["bin3_c"]), 1e9, 10)
     assert np.array_equal(G, golden["bin3_G"])
     assert norm == float(golden["bin3_norm"])
+
+
+@pytest.mark.parametrize("tag", ["dg", "sg"])
+def test_stable_cutoff_1000(golden, tag):
+    # reference test_vanilla_stable (tests/test_math/test_lattice/test_lattice_functions.py:137-149)
+    A, b, c = golden[f"st_{tag}_A"], golden[f"st_{tag}_b"], complex(golden[f"st_{tag}_c"])
+    G = oracle.stable((1000, 1000), A, b, c)
+    assert sha(G) == str(golden[f"st_{tag}_sha"])
+    if tag == "dg":
+        assert np.allclose(G.ravel()[::7919], golden["st_dg_closed_form_sample"])
+    else:
+        assert np.max(np.abs(G)) < 1

@@ -134,6 +134,14 @@ int mmh_diagonal_grad(int M, const int64_t *cutoffs, const void *dA, const void 
 int mmh_diagonal_grad_host(int M, const int64_t *cutoffs, const void *A, const void *B, const void *G0,
                            void *arr0_dG0_out, void *arr0_dA_out, void *arr0_dB_out);
 
+/* replaces: grad_hermite_multidimensional_1leftoverMode (inputValidation.py:125-142 -> singleLeftoverMode_grad.py:19-724;
+ *           jax bwd math/jax_vjps/hermite.py:397-439).  cutoffs = (c0, tail...), M >= 2 ->
+ *   arr0_dG0[c0,c0,tail...], arr0_dA[c0,c0,tail...,2M,2M], arr0_dB[c0,c0,tail...,2M].                              */
+int mmh_1leftover_grad(int M, const int64_t *cutoffs, const void *dA, const void *dB, const void *dG0,
+                       void *darr0_dG0_out, void *darr0_dA_out, void *darr0_dB_out, void *stream);
+int mmh_1leftover_grad_host(int M, const int64_t *cutoffs, const void *A, const void *B, const void *G0,
+                            void *arr0_dG0_out, void *arr0_dA_out, void *arr0_dB_out);
+
 /* compactFock "one leftover mode": density matrix of mode 0 conditioned on PNR outcomes of the others ----
  * replaces: hermite_multidimensional_1leftoverMode(A, B, G0, cutoffs)[0]
  *           (inputValidation.py:103-122 -> singleLeftoverMode_amps.py:290-475); the numpy backend computes

@@ -28,7 +28,7 @@ SYMBOLS = [
     "mmh_vjp", "mmh_vjp_host", "mmh_vjp_batched", "mmh_vjp_batched_host",
     "mmh_binomial", "mmh_binomial_host",
     "mmh_diagonal", "mmh_diagonal_host", "mmh_1leftover", "mmh_1leftover_host",
-    "mmh_diagonal_grad", "mmh_diagonal_grad_host",
+    "mmh_diagonal_grad", "mmh_diagonal_grad_host", "mmh_1leftover_grad", "mmh_1leftover_grad_host",
 ]
 
 
@@ -70,6 +70,8 @@ def _load() -> ctypes.CDLL:
         "mmh_diagonal_host": ([ci, p64, vp, vp, i64, vp, vp], ci),
         "mmh_diagonal_grad": ([ci, p64, vp, vp, vp, vp, vp, vp, vp], ci),
         "mmh_diagonal_grad_host": ([ci, p64, vp, vp, vp, vp, vp, vp], ci),
+        "mmh_1leftover_grad": ([ci, p64, vp, vp, vp, vp, vp, vp, vp], ci),
+        "mmh_1leftover_grad_host": ([ci, p64, vp, vp, vp, vp, vp, vp], ci),
         "mmh_1leftover": ([ci, p64, vp, vp, vp, vp, vp], ci),
         "mmh_1leftover_host": ([ci, p64, vp, vp, vp, vp], ci),
     }

@@ -564,20 +564,23 @@ __global__ void k_diag_split_jacobian(const c128 *t0, const c128 *arr0, const c1
     else dB_out[p * n2 + (th - n2 * n2)] = t0[p * nt + th];
 }
 
-static int diagonal_grad_impl(int M, const int64_t *cutoffs, const void *dA, const void *dB, const void *dG0,
+static int diagonal_grad_impl(int Mtot, const int64_t *cutoffs, int L0, const void *dA, const void *dB, const void *dG0,
                               void *o_dG0, void *o_dA, void *o_dB, cudaStream_t st) {
     if (!cutoffs) return MMH_ERR_NULL_POINTER;
+    const int M = Mtot - L0;   // detected modes
     if (M < 1 || M > 8) return MMH_ERR_BAD_NDIM;
     if (!dA || !dB || !dG0 || !o_dG0 || !o_dA || !o_dB) return MMH_ERR_NULL_POINTER;
     DiagTanParams tp;
     memset(&tp, 0, sizeof(tp));
     DiagParams &q = tp.q;
-    q.Md = M; q.L0 = 0; q.c0 = 1; q.nb = 1;
-    int mx = 1, nlevels = 1;
+    q.Md = M; q.L0 = L0; q.nb = 1;
+    q.c0 = L0 ? (int)cutoffs[0] : 1;
+    if (q.c0 < 1 || q.c0 > (1 << 20)) return MMH_ERR_BAD_SHAPE;
+    int mx = q.c0, nlevels = 1;
     long long P = 1;
     for (int j = 0; j < M; j++) {
-        if (cutoffs[j] < 1 || cutoffs[j] > (1 << 20)) return MMH_ERR_BAD_SHAPE;
-        q.cut[j] = (int)cutoffs[j];
+        if (cutoffs[j + L0] < 1 || cutoffs[j + L0] > (1 << 20)) return MMH_ERR_BAD_SHAPE;
+        q.cut[j] = (int)cutoffs[j + L0];
         if (q.cut[j] > mx) mx = q.cut[j];
         nlevels += q.cut[j] - 1;
         if (P > (1LL << 34) / q.cut[j]) return MMH_ERR_TOO_LARGE;
@@ -585,30 +588,31 @@ static int diagonal_grad_impl(int M, const int64_t *cutoffs, const void *dA, con
     }
     q.pst[M - 1] = 1;
     for (int j = M - 1; j > 0; j--) q.pst[j - 1] = q.pst[j] * q.cut[j];
-    q.P = P; q.E = P;
-    const int n2 = 2 * M;
+    q.P = P; q.E = (long long)q.c0 * q.c0 * P;
+    const int n2 = 2 * Mtot;
+    const long long Pv = q.E;   // amplitudes of arr0
     tp.ntheta = n2 * n2 + n2;
     DeviceCtx *ctx;
     int rc;
     if ((rc = get_ctx(&ctx))) return rc;
     if ((rc = ensure_tables(*ctx, mx + 3))) return rc;
     const long long naux = 2LL * M + M + 2LL * M * (M > 1 ? M - 1 : 1);   // arr1, arr2, arr1010, arr1001
-    const size_t nval = (size_t)(naux + 1) * (size_t)P;
+    const size_t nval = (size_t)(naux + 1) * (size_t)Pv;
     const size_t bytes = sizeof(c128) * nval * (size_t)(1 + tp.ntheta);
     if (bytes > (size_t)120 << 30) return MMH_ERR_TOO_LARGE;
     if ((rc = ensure_scratch(ctx->diag_ws, bytes))) return rc;
     CK(cudaMemsetAsync(ctx->diag_ws.ptr, 0, bytes, st));
     c128 *w = (c128 *)ctx->diag_ws.ptr;
-    q.arr0 = w;    w += P;
-    q.arr1 = w;    w += 2LL * M * P;
-    q.arr2 = w;    w += (long long)M * P;
-    q.arr1010 = w; w += (long long)M * (M > 1 ? M - 1 : 1) * P;
-    q.arr1001 = w; w += (long long)M * (M > 1 ? M - 1 : 1) * P;
+    q.arr0 = w;    w += Pv;
+    q.arr1 = w;    w += 2LL * M * Pv;
+    q.arr2 = w;    w += (long long)M * Pv;
+    q.arr1010 = w; w += (long long)M * (M > 1 ? M - 1 : 1) * Pv;
+    q.arr1001 = w; w += (long long)M * (M > 1 ? M - 1 : 1) * Pv;
     const long long nt = tp.ntheta;
-    tp.t0 = w;     w += P * nt;
-    tp.t1 = w;     w += 2LL * M * P * nt;
-    tp.t2 = w;     w += (long long)M * P * nt;
-    tp.t1010 = w;  w += (long long)M * (M > 1 ? M - 1 : 1) * P * nt;
+    tp.t0 = w;     w += Pv * nt;
+    tp.t1 = w;     w += 2LL * M * Pv * nt;
+    tp.t2 = w;     w += (long long)M * Pv * nt;
+    tp.t1010 = w;  w += (long long)M * (M > 1 ? M - 1 : 1) * Pv * nt;
     tp.t1001 = w;
     q.A = (const c128 *)dA; q.B = (const c128 *)dB; q.sq = ctx->sq;
     long long launches = 0;
@@ -616,8 +620,8 @@ static int diagonal_grad_impl(int M, const int64_t *cutoffs, const void *dA, con
     g_launches += launches;
     CK(mmh_launch_diagonal_tangent(tp, nlevels, &launches, st));
     g_launches += launches + 1;
-    const long long total = P * (nt + 1);
-    k_diag_split_jacobian<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tp.t0, q.arr0, (const c128 *)dG0, P, n2,
+    const long long total = Pv * (nt + 1);
+    k_diag_split_jacobian<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tp.t0, q.arr0, (const c128 *)dG0, Pv, n2,
                                                                          (c128 *)o_dG0, (c128 *)o_dA, (c128 *)o_dB);
     CK(cudaGetLastError());
     return MMH_OK;
@@ -819,16 +823,37 @@ int mmh_diagonal_host(int M, const int64_t *cutoffs, const void *A, const void *
 int mmh_diagonal_grad(int M, const int64_t *cutoffs, const void *dA, const void *dB, const void *dG0, void *o_dG0,
                       void *o_dA, void *o_dB, void *stream) {
     std::lock_guard<std::mutex> lk(g_mutex);
-    return diagonal_grad_impl(M, cutoffs, dA, dB, dG0, o_dG0, o_dA, o_dB, (cudaStream_t)stream);
+    return diagonal_grad_impl(M, cutoffs, 0, dA, dB, dG0, o_dG0, o_dA, o_dB, (cudaStream_t)stream);
 }
+int mmh_1leftover_grad(int M, const int64_t *cutoffs, const void *dA, const void *dB, const void *dG0, void *o_dG0,
+                       void *o_dA, void *o_dB, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (M < 2) return MMH_ERR_BAD_NDIM;
+    return diagonal_grad_impl(M, cutoffs, 1, dA, dB, dG0, o_dG0, o_dA, o_dB, (cudaStream_t)stream);
+}
+static int diagonal_grad_host_impl(int M, const int64_t *cutoffs, int L0, const void *A, const void *B, const void *G0,
+                                   void *o_dG0, void *o_dA, void *o_dB);
 int mmh_diagonal_grad_host(int M, const int64_t *cutoffs, const void *A, const void *B, const void *G0, void *o_dG0,
                            void *o_dA, void *o_dB) {
     std::lock_guard<std::mutex> lk(g_mutex);
+    return diagonal_grad_host_impl(M, cutoffs, 0, A, B, G0, o_dG0, o_dA, o_dB);
+}
+int mmh_1leftover_grad_host(int M, const int64_t *cutoffs, const void *A, const void *B, const void *G0, void *o_dG0,
+                            void *o_dA, void *o_dB) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (M < 2) return MMH_ERR_BAD_NDIM;
+    return diagonal_grad_host_impl(M, cutoffs, 1, A, B, G0, o_dG0, o_dA, o_dB);
+}
+static int diagonal_grad_host_impl(int M, const int64_t *cutoffs, int L0, const void *A, const void *B, const void *G0,
+                                   void *o_dG0, void *o_dA, void *o_dB) {
     if (!cutoffs) return MMH_ERR_NULL_POINTER;
-    if (M < 1 || M > 8) return MMH_ERR_BAD_NDIM;
+    if (M < 1 + L0 || M - L0 > 8) return MMH_ERR_BAD_NDIM;
     if (!A || !B || !G0 || !o_dG0 || !o_dA || !o_dB) return MMH_ERR_NULL_POINTER;
     size_t P = 1;
-    for (int j = 0; j < M; j++) { if (cutoffs[j] < 1) return MMH_ERR_BAD_SHAPE; P *= (size_t)cutoffs[j]; }
+    for (int j = 0; j < M; j++) {
+        if (cutoffs[j] < 1) return MMH_ERR_BAD_SHAPE;
+        P *= (size_t)cutoffs[j] * ((L0 && j == 0) ? (size_t)cutoffs[j] : 1);
+    }
     DeviceCtx *ctx;
     int rc;
     if ((rc = get_ctx(&ctx))) return rc;
@@ -840,7 +865,7 @@ int mmh_diagonal_grad_host(int M, const int64_t *cutoffs, const void *A, const v
     if ((rc = stage_in(*ctx, 4, nullptr, sizeof(c128) * P, &d0))) return rc;
     if ((rc = stage_in(*ctx, 5, nullptr, sizeof(c128) * P * n2 * n2, &d1))) return rc;
     if ((rc = stage_in(*ctx, 6, nullptr, sizeof(c128) * P * n2, &d2))) return rc;
-    if ((rc = diagonal_grad_impl(M, cutoffs, dA, dB, dG0, d0, d1, d2, 0))) return rc;
+    if ((rc = diagonal_grad_impl(M, cutoffs, L0, dA, dB, dG0, d0, d1, d2, 0))) return rc;
     CK(cudaMemcpyAsync(o_dG0, d0, sizeof(c128) * P, cudaMemcpyDeviceToHost, 0));
     CK(cudaMemcpyAsync(o_dA, d1, sizeof(c128) * P * n2 * n2, cudaMemcpyDeviceToHost, 0));
     CK(cudaMemcpyAsync(o_dB, d2, sizeof(c128) * P * n2, cudaMemcpyDeviceToHost, 0));

@@ -196,9 +196,13 @@ __device__ __forceinline__ bool tan_decode(const DiagTanParams &tp, long long gi
     const long long Et = q.E * tp.ntheta;
     if (gid >= Et) return false;
     theta = (int)(gid % tp.ntheta);
-    long long p = gid / tp.ntheta;     // value-array index (c0 = nb = 1 for the diagonal case)
-    x.idx = p;
-    x.m = x.n = x.t = 0;
+    const long long vi = gid / tp.ntheta;     // value-array index ((m*c0 + n) * P + p); nb == 1
+    x.idx = vi;
+    x.t = 0;
+    long long p = vi % q.P;
+    const int mn = (int)(vi / q.P);
+    x.m = mn / q.c0;
+    x.n = mn - x.m * q.c0;
     int sum = 0;
     for (int j = 0; j < q.Md; j++) {
         x.params[j] = (int)(p / q.pst[j]);
@@ -209,15 +213,27 @@ __device__ __forceinline__ bool tan_decode(const DiagTanParams &tp, long long gi
     return sum == q.level;
 }
 
-__device__ __forceinline__ c128 tan_write_value(const DiagTanParams &tp, int ii, c128 piv, c128 dpiv, const c128 *G_in,
-                                                const c128 *dG_in, int l_lo, int theta, double K) {
+// tangent of one written amplitude (calc_dA_dB: diagonal_grad.py:19-37, singleLeftoverMode_grad.py:19-47).
+// ii = row of the full A; (lm, ln) / (dlm, dln): sqrt(m) piv[m-1,n], sqrt(n) piv[m,n-1] of the pivot array and their
+// tangents (leftover case only).
+__device__ __forceinline__ c128 tan_write_value(const DiagTanParams &tp, int ii, c128 piv, c128 dpiv, c128 lm, c128 ln,
+                                                c128 dlm, c128 dln, const c128 *G_in, const c128 *dG_in, int l_lo, int theta,
+                                                double K) {
     const DiagParams &q = tp.q;
-    const int n2 = 2 * q.Md;
+    const int n2 = 2 * (q.Md + q.L0), o2 = 2 * q.L0;
     const c128 *Arow = q.A + (long long)ii * n2;
     c128 v = cmulf(dpiv, q.B[ii]);
     if (theta == n2 * n2 + ii) v = caddf(v, piv);                       // dB[i] += pivot_val
-    for (int l = l_lo; l < n2; l++) v = caddf(v, cmulf(Arow[l], dG_in[l]));
-    if (theta < n2 * n2 && theta / n2 == ii) v = caddf(v, G_in[theta % n2]);   // dA[i, l] += K_l G_in[l]
+    if (q.L0) {
+        v = caddf(v, cmulf(Arow[0], dlm));
+        v = caddf(v, cmulf(Arow[1], dln));
+    }
+    for (int l = l_lo; l < 2 * q.Md; l++) v = caddf(v, cmulf(Arow[o2 + l], dG_in[l]));
+    if (theta < n2 * n2 && theta / n2 == ii) {                          // dA[i, l] += (scaled) G_in[l]
+        const int col = theta % n2;
+        if (col >= o2) v = caddf(v, G_in[col - o2]);
+        else if (q.L0) v = caddf(v, col == 0 ? lm : ln);
+    }
     return make_double2(v.x / K, v.y / K);
 }
 
@@ -241,11 +257,17 @@ __global__ void __launch_bounds__(256) k_diag_pivot_tan(DiagTanParams tp) {
         }
     }
     const c128 piv = q.arr0[x.idx], dpiv = tp.t0[x.idx * nt + theta];
+    c128 lm = make_double2(0.0, 0.0), ln = lm, dlm = lm, dln = lm;
+    if (q.L0) {
+        const long long om = x.idx - (long long)q.c0 * q.P, on = x.idx - q.P;
+        if (x.m > 0) { lm = cscalef(q.arr0[om], sq[x.m]); dlm = cscalef(tp.t0[om * nt + theta], sq[x.m]); }
+        if (x.n > 0) { ln = cscalef(q.arr0[on], sq[x.n]); dln = cscalef(tp.t0[on * nt + theta], sq[x.n]); }
+    }
     for (int i = 0; i < 2 * Md; i++) {
         const int j = i >> 1;
         if (x.params[j] + 1 < q.cut[j] && (i != 1 || x.params[0] + 2 < q.cut[0]))
             tp.t1[((long long)i * E + x.idx) * nt + theta] =
-                tan_write_value(tp, i, piv, dpiv, G_in, dG_in, 0, theta, sq[x.params[j] + 1]);
+                tan_write_value(tp, i + 2 * q.L0, piv, dpiv, lm, ln, dlm, dln, G_in, dG_in, 0, theta, sq[x.params[j] + 1]);
     }
 }
 
@@ -255,7 +277,7 @@ __global__ void __launch_bounds__(256) k_diag_offdiag_tan(DiagTanParams tp) {
     int theta;
     if (!tan_decode(tp, (long long)blockIdx.x * blockDim.x + threadIdx.x, x, theta)) return;
     const double *__restrict__ sq = q.sq;
-    const int Md = q.Md, nt = tp.ntheta;
+    const int Md = q.Md, nt = tp.ntheta, o2 = 2 * q.L0;
     const long long E = q.E;
     c128 G_in[2 * MMH_DIAG_MAXMD], dG_in[2 * MMH_DIAG_MAXMD];
     for (int d = 0; d < Md; d++) {
@@ -279,16 +301,22 @@ __global__ void __launch_bounds__(256) k_diag_offdiag_tan(DiagTanParams tp) {
             }
             const long long op = (long long)(2 * d) * E + x.idx;
             const c128 piv = q.arr1[op], dpiv = tp.t1[op * nt + theta];
+            c128 lm = make_double2(0.0, 0.0), ln = lm, dlm = lm, dln = lm;
+            if (q.L0) {
+                const long long om = op - (long long)q.c0 * q.P, on = op - q.P;
+                if (x.m > 0) { lm = cscalef(q.arr1[om], sq[x.m]); dlm = cscalef(tp.t1[om * nt + theta], sq[x.m]); }
+                if (x.n > 0) { ln = cscalef(q.arr1[on], sq[x.n]); dln = cscalef(tp.t1[on * nt + theta], sq[x.n]); }
+            }
             tp.t0[(x.idx + q.pst[d]) * nt + theta] =
-                tan_write_value(tp, 2 * d + 1, piv, dpiv, G_in, dG_in, 2 * d, theta, sq[x.params[d] + 1]);
+                tan_write_value(tp, 2 * d + 1 + o2, piv, dpiv, lm, ln, dlm, dln, G_in, dG_in, 2 * d, theta, sq[x.params[d] + 1]);
             if (x.params[d] + 2 < q.cut[d])
                 tp.t2[((long long)d * E + x.idx) * nt + theta] =
-                    tan_write_value(tp, 2 * d, piv, dpiv, G_in, dG_in, 2 * d, theta, sq[x.params[d] + 2]);
+                    tan_write_value(tp, 2 * d + o2, piv, dpiv, lm, ln, dlm, dln, G_in, dG_in, 2 * d, theta, sq[x.params[d] + 2]);
             for (int i = d + 1; i < Md; i++) {
                 if (x.params[i] + 1 < q.cut[i]) {
                     const long long o = ((long long)(d * (Md - 1) + i - d - 1) * E + x.idx) * nt + theta;
-                    tp.t1010[o] = tan_write_value(tp, 2 * i, piv, dpiv, G_in, dG_in, 2 * d, theta, sq[x.params[i] + 1]);
-                    tp.t1001[o] = tan_write_value(tp, 2 * i + 1, piv, dpiv, G_in, dG_in, 2 * d, theta, sq[x.params[i] + 1]);
+                    tp.t1010[o] = tan_write_value(tp, 2 * i + o2, piv, dpiv, lm, ln, dlm, dln, G_in, dG_in, 2 * d, theta, sq[x.params[i] + 1]);
+                    tp.t1001[o] = tan_write_value(tp, 2 * i + 1 + o2, piv, dpiv, lm, ln, dlm, dln, G_in, dG_in, 2 * d, theta, sq[x.params[i] + 1]);
                 }
             }
         }
@@ -296,9 +324,57 @@ __global__ void __launch_bounds__(256) k_diag_offdiag_tan(DiagTanParams tp) {
     }
 }
 
+// tangents of the leftover seed block (singleLeftoverMode_grad.py:611-650): one thread per (theta, m); the first column
+// is a serial chain over m, then column n+1 follows from columns n, n-1 (parallel over m).
+__global__ void __launch_bounds__(1024) k_diag_seed_tan(DiagTanParams tp) {
+    const DiagParams &q = tp.q;
+    const int nt = tp.ntheta, c0 = q.c0;
+    const int n2 = 2 * (q.Md + 1);
+    const long long rowst = (long long)c0 * q.P, colst = q.P;
+    const c128 B0 = q.B[0], B1 = q.B[1], A00 = q.A[0], A10 = q.A[n2], A11 = q.A[n2 + 1];
+    const double *sq = q.sq;
+    const c128 *a = q.arr0;
+    c128 *t = tp.t0;
+    const int thB0 = n2 * n2, thB1 = n2 * n2 + 1, thA00 = 0, thA10 = n2, thA11 = n2 + 1;
+    for (int theta = threadIdx.x; theta < nt; theta += blockDim.x) {   // first column, serial in m
+        for (int m = 0; m + 1 < c0; m++) {
+            c128 v = cmulf(t[(m * rowst) * nt + theta], B0);
+            if (theta == thB0) v = caddf(v, a[m * rowst]);
+            if (m > 0) {
+                v = caddf(v, cmulf(cscalef(A00, sq[m]), t[((m - 1) * rowst) * nt + theta]));
+                if (theta == thA00) v = caddf(v, cscalef(a[(m - 1) * rowst], sq[m]));
+            }
+            t[((m + 1) * rowst) * nt + theta] = make_double2(v.x / sq[m + 1], v.y / sq[m + 1]);
+        }
+    }
+    __syncthreads();
+    for (int n = 0; n + 1 < c0; n++) {
+        for (int w = threadIdx.x; w < nt * c0; w += blockDim.x) {
+            const int theta = w % nt, m = w / nt;
+            const long long o = m * rowst + n * colst;
+            c128 v = cmulf(t[o * nt + theta], B1);
+            if (theta == thB1) v = caddf(v, a[o]);
+            if (m > 0) {
+                v = caddf(v, cmulf(cscalef(A10, sq[m]), t[(o - rowst) * nt + theta]));
+                if (theta == thA10) v = caddf(v, cscalef(a[o - rowst], sq[m]));
+            }
+            if (n > 0) {
+                v = caddf(v, cmulf(cscalef(A11, sq[n]), t[(o - colst) * nt + theta]));
+                if (theta == thA11) v = caddf(v, cscalef(a[o - colst], sq[n]));
+            }
+            t[(o + colst) * nt + theta] = make_double2(v.x / sq[n + 1], v.y / sq[n + 1]);
+        }
+        __syncthreads();
+    }
+}
+
 cudaError_t mmh_launch_diagonal_tangent(DiagTanParams tp, int nlevels, long long *launches, cudaStream_t st) {
     const long long grid = (tp.q.E * tp.ntheta + 255) / 256;
     *launches = 0;
+    if (tp.q.L0) {
+        k_diag_seed_tan<<<1, 1024, 0, st>>>(tp);
+        *launches += 1;
+    }
     for (int w = 0; w < nlevels; w++) {
         tp.q.level = w;
         k_diag_pivot_tan<<<(unsigned)grid, 256, 0, st>>>(tp);

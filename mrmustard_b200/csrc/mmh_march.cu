@@ -45,8 +45,12 @@ __device__ __forceinline__ void div_all_inplace(c128 (&v)[R], double sqs, double
 // The CTA marches L lattices in lock step; a thread owns R fixed panel positions ("slots").
 // ---------------------------------------------------------------------------------------------------
 // smem layout (c128 units): sba[L][2] = (b_i, A_ii) | buf[2][L*P]
+#ifndef MMH_K2_MAXT
+#define MMH_K2_MAXT(R) ((R) >= 4 ? 256 : 512)
+#define MMH_K2_MINB(R) ((R) >= 4 ? 2 : 1)
+#endif
 template <int R, int NPD>
-__global__ void __launch_bounds__(R >= 4 ? 256 : 512, R >= 4 ? 2 : 1) k_march_stage(StageParams p) {
+__global__ void __launch_bounds__(MMH_K2_MAXT(R), MMH_K2_MINB(R)) k_march_stage(StageParams p) {
     extern __shared__ c128 smem[];
     const LatticeDesc &d = p.d;
     const int D = d.D;

@@ -21,6 +21,7 @@ __all__ = [
     "vanilla_batch_vjp_numba", "binomial", "vanilla", "stable",
     "hermite_multidimensional_diagonal", "hermite_multidimensional_1leftoverMode", "fast_diagonal",
     "grad_hermite_multidimensional_diagonal", "hermite_renormalized_diagonal_vjp",
+    "grad_hermite_multidimensional_1leftoverMode",
 ]
 
 
@@ -273,3 +274,25 @@ def hermite_renormalized_diagonal_vjp(A, B, G0, cutoffs, dLdpoly):
     g = np.asarray(dLdpoly)
     ax = tuple(range(g.ndim))
     return np.sum(g[..., None, None] * dA, axis=ax), np.sum(g[..., None] * dB, axis=ax), np.sum(g * dG0, axis=ax)
+
+
+def grad_hermite_multidimensional_1leftoverMode(A, B, G0, arr0, arr2=None, arr1010=None, arr1001=None, arr1=None):
+    """Jacobians (arr0_dG0, arr0_dA, arr0_dB) of the one-leftover-mode amplitudes (compactFock/inputValidation.py:125-142,
+    singleLeftoverMode_grad.py:560-724).  Only arr0.shape = (c0, c0, *cutoffs_tail) is used; the forward sweep is recomputed."""
+    A = _c128(A)
+    B = _c128(B)
+    if A.shape[0] != B.shape[0]:
+        raise ValueError("The matrix A and vector B have incompatible dimensions")
+    M = A.shape[0] // 2
+    if M <= 1:
+        raise ValueError("The number of modes should be greater than 1.")
+    shp = tuple(int(s) for s in np.shape(arr0))
+    if len(shp) != M + 1 or shp[0] != shp[1]:
+        raise ValueError("arr0 must have shape (c0, c0, *cutoffs_tail)")
+    cutoffs = shp[1:]
+    G0 = _c128(G0, (1,))
+    dG0 = np.empty(shp, np.complex128)
+    dA = np.empty(shp + (2 * M, 2 * M), np.complex128)
+    dB = np.empty(shp + (2 * M,), np.complex128)
+    check(lib.mmh_1leftover_grad_host(M, shape_array(cutoffs), _p(A), _p(B), _p(G0), _p(dG0), _p(dA), _p(dB)))
+    return dG0, dA, dB

@@ -117,3 +117,26 @@ def test_diagonal_vjp_finite_differences(mm, gd):
             if l != i: Ap[l, i] += eps
             want = dLdA[i, l] + (dLdA[l, i] if l != i else 0)
             assert np.isclose((f(Ap, b2, c) - f0) / eps, want, rtol=1e-4, atol=1e-6)
+
+
+def test_leftover_jacobians_finite_differences(mm, gd):
+    """grad_hermite_multidimensional_1leftoverMode: the reference implementation does not compile under this image's numba
+    (see tests/golden/gen_golden_diagonal.py), so the Jacobians are pinned by finite differences of the (golden-pinned)
+    forward path and by d(arr0)/dG0 = arr0 / G0."""
+    A, b, c = gd["l3_A"], gd["l3_b"], complex(gd["l3_c"])
+    A2, b2 = (np.ascontiguousarray(x) for x in mm.backend.reorder_AB_bargmann(A, b))
+    cut = (4, 2, 3)
+    fwd = lambda A_, b_, c_: np.ascontiguousarray(mm.strategies.hermite_multidimensional_1leftoverMode(A_, b_, c_, cut))
+    G = fwd(A2, b2, c)
+    dG0, dA, dB = mm.strategies.grad_hermite_multidimensional_1leftoverMode(A2, b2, c, G)
+    assert dA.shape == G.shape + (6, 6) and dB.shape == G.shape + (6,)
+    assert np.allclose(dG0, G / c, rtol=1e-12, atol=1e-15)
+    eps = 1e-7
+    for i in range(6):
+        bp = b2.copy(); bp[i] += eps
+        assert np.allclose((fwd(A2, bp, c) - G) / eps, dB[..., i], rtol=1e-4, atol=1e-6), f"dB[{i}]"
+        for l in range(i, 6):
+            Ap = A2.copy(); Ap[i, l] += eps
+            if l != i: Ap[l, i] += eps
+            want = dA[..., i, l] + (dA[..., l, i] if l != i else 0)
+            assert np.allclose((fwd(Ap, b2, c) - G) / eps, want, rtol=1e-4, atol=1e-6), f"dA[{i},{l}]"

@@ -184,8 +184,11 @@ static int forward_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st, b
 }
 
 // K1 plan: tile grid over the first nt panel dims of `stage` (mmh_march.cu k_march_tiled)
+static bool tiled_v1() { return getenv("MMH_TILED_V1") != nullptr; }   // A/B hook: first-generation tiled kernel
+
 static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, TiledParams *tp, int *R_out,
                              int *ntiles_out, size_t *smem_out) {
+    const bool v1 = tiled_v1();
     const int npd = d.D - 1 - stage;
     if (npd < 1 || npd > 7) return false;
     const long long P = d.strides[stage];
@@ -232,7 +235,7 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
                     const int tcmax = two_per_sm ? 256 : (Rs[r] == 4 ? 256 : 512);
                     if (eR && atoi(eR) != Rs[r]) continue;
                     if (two_per_sm && Rs[r] == 4) continue;
-                    if ((long long)Rs[r] * tcmax >= TS && (Rs[r] == 1 || Rs[r] * npd <= 12)) { R = Rs[r]; break; }
+                    if ((long long)Rs[r] * tcmax >= TS && (Rs[r] == 1 || Rs[r] * npd <= (v1 ? 12 : 10))) { R = Rs[r]; break; }
                 }
                 if (!R) continue;
                 const int TC = round_up32((TS + R - 1) / R);
@@ -240,6 +243,12 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
                 smem = (smem + 15) / 16 * 16;
                 const size_t sqtab_off = smem / 16;
                 smem += sizeof(c128) * (size_t)(S + 2);     // (sqrt, 1/sqrt) table + (b_i, A_ii)
+                if (!v1) {
+                    if (R == 4) continue;
+                    LS = TS + HC + 2;                       // compact box + halo faces + zero cell + trash cell
+                    smem = mmh_tiled2_smem((int)LS, (int)HCs, S, R * TC);
+                    if ((double)g0 * g1 * g2 * (double)S * (double)HCs >= 2147483648.0) continue;   // 32-bit export offsets
+                }
                 if (smem > (two_per_sm ? 100 : 200) * 1024) continue;
                 double step_us = (double)TS * 0.55e-3;          // issue time of one panel step of the tile
                 if (step_us < 0.15) step_us = 0.15;             // dependent-chain floor of one panel step
@@ -311,13 +320,15 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
                 CK(mmh_stage_constants(p.A, p.b, D, i, tp.cslot, st));
             }
             const char *trace_file = getenv("MMH_TRACE_FILE");   // debug timeline of the tile pipeline
-            const size_t trace_words = (size_t)ntiles * d.shape[i] * 4;
+            const size_t trace_words = (size_t)ntiles * d.shape[i] * 8;
+            if (trace_file && tiled_v1()) trace_file = nullptr;
             if (trace_file) {
                 CK(cudaMalloc(&tp.trace, trace_words * 8));
                 CK(cudaMemset(tp.trace, 0, trace_words * 8));
             }
             g_launches++;
-            CK(mmh_launch_march_tiled(tp, R, ntiles, sm, st));
+            if (tiled_v1()) CK(mmh_launch_march_tiled(tp, R, ntiles, sm, st));
+            else CK(mmh_launch_march_tiled2(tp, R, ntiles, sm, st));
             if (trace_file) {
                 std::vector<unsigned long long> h(trace_words);
                 CK(cudaStreamSynchronize(st));

@@ -73,6 +73,8 @@ struct TiledParams {
 
 cudaError_t mmh_stage_constants(const c128 *A, const c128 *b, int D, int stage, int slot, cudaStream_t st);
 cudaError_t mmh_launch_march_tiled(const TiledParams &p, int R, int ntiles, size_t smem, cudaStream_t st);
+cudaError_t mmh_launch_march_tiled2(const TiledParams &p, int R, int ntiles, size_t smem, cudaStream_t st);
+size_t mmh_tiled2_smem(int ls_max, int hc_max, int S, int slots);
 cudaError_t mmh_launch_march_stage(const StageParams &p, int R, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t mmh_launch_chain(const FwdParams &p, cudaStream_t st);
 cudaError_t mmh_launch_fwd_cta(const FwdParams &p, bool stable, int grid, int block, size_t smem, cudaStream_t st);

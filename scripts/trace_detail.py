@@ -11,7 +11,7 @@ A, b, c = gold["cfg2_A"], gold["cfg2_b"], complex(gold["cfg2_c"])
 strategies.vanilla_numba((50,) * 4, A, b, c); strategies.vanilla_numba((50,) * 4, A, b, c)
 raw = open("gpurun_out/trace.stage0.bin", "rb").read()
 ntiles, S, g0, g1, g2, R, tc, _ = struct.unpack("8i", raw[:32])
-t = np.frombuffer(raw[32:], dtype=np.uint64).reshape(ntiles, S, 4).astype(np.int64)
+t = np.frombuffer(raw[32:], dtype=np.uint64).reshape(ntiles, S, 8).astype(np.int64)
 t0 = t[t > 0].min(); rel = np.where(t > 0, (t - t0) / 1e3, np.nan)
 for tile in [int(x) for x in sys.argv[1:]] or [0, 31, 62]:
     lower = [tile - g1 * g2, tile - g2, tile - 1]

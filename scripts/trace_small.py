@@ -17,7 +17,7 @@ for grid in sys.argv[2:]:
     strategies.vanilla_numba(shape, A, b, c); strategies.vanilla_numba(shape, A, b, c)
     raw = open("gpurun_out/trace_s.stage0.bin", "rb").read()
     ntiles, S, g0, g1, g2, R, tc, _ = struct.unpack("8i", raw[:32])
-    t = np.frombuffer(raw[32:], dtype=np.uint64).reshape(ntiles, S, 4).astype(np.int64)
+    t = np.frombuffer(raw[32:], dtype=np.uint64).reshape(ntiles, S, 8).astype(np.int64)
     t0 = t[t > 0].min(); rel = np.where(t > 0, t - t0, -1)
     print(f"shape {shape} grid {g0}x{g1}x{g2} tiles {ntiles} R={R} tc={tc} total {rel.max()/1e3:.1f} us")
     for tile in sorted(set([0, ntiles - 1])):

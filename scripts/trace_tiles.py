@@ -14,7 +14,7 @@ for stage in (1, 0):
     raw = open(f"gpurun_out/trace.stage{stage}.bin", "rb").read()
     hdr = struct.unpack("8i", raw[:32])
     ntiles, S, g0, g1, g2, R, tc, _ = hdr
-    t = np.frombuffer(raw[32:], dtype=np.uint64).reshape(ntiles, S, 4).astype(np.int64)
+    t = np.frombuffer(raw[32:], dtype=np.uint64).reshape(ntiles, S, 8).astype(np.int64)
     t0 = t[t > 0].min()
     rel = np.where(t > 0, t - t0, -1)
     print(f"stage {stage}: tiles {ntiles} grid {g0}x{g1}x{g2} S={S} R={R} tc={tc}; total {rel.max()/1e3:.1f} us")

@@ -71,6 +71,19 @@ int mmh_forward_batched(int64_t batch, int ndim, const int64_t *shape, const voi
 int mmh_forward_batched_host(int64_t batch, int ndim, const int64_t *shape, const void *A,
                              const void *b, const void *c, void *G, int stable);
 
+/* lattice followed by the contraction over its trailing "derived" axes ----------
+ * replaces: the pair  G = math.hermite_renormalized(A, b, ones, shape + shape_derived_vars);
+ *                     ret = einsum("...abc..k,...k->...abc..", G.reshape(.., -1), c.reshape(.., -1))
+ *           of CircuitComponent.fock_array (lab/circuit_components.py:516-530) and of
+ *           PolyExpAnsatz.decompose_ansatz (physics/ansatz/polyexp_ansatz.py:447-462).
+ * shape has ndim entries; its first ncore_dims entries are the core (Fock) axes, the rest the derived axes.
+ * A[batch,ndim,ndim], b[batch,ndim], cpoly[batch, prod(derived)] -> out[batch, prod(core)].
+ * The lattice is computed with vacuum amplitude 1 and never leaves the device.                                   */
+int mmh_forward_contract(int64_t batch, int ndim, const int64_t *shape, int ncore_dims, const void *dA, const void *db,
+                         const void *dcpoly, void *dout, int stable, void *stream);
+int mmh_forward_contract_host(int64_t batch, int ndim, const int64_t *shape, int ncore_dims, const void *A, const void *b,
+                              const void *cpoly, void *out, int stable);
+
 /* One panel step of the vanilla fill restricted to a contiguous range of panel offsets: every amplitude
  * G[k] with k_<stage = 0, k_stage = step and panel offset f in [f_lo, f_hi) (f = the flat index of
  * (k_{stage+1}, ..., k_{ndim-1})), from panels step-1 and step-2 of the same lattice (vanilla/core.py:108-122 restricted
@@ -152,6 +165,10 @@ int mmh_1leftover(int M, const int64_t *cutoffs, const void *dA, const void *dB,
                   void *darr0_out, void *stream);
 int mmh_1leftover_host(int M, const int64_t *cutoffs, const void *A, const void *B, const void *G0,
                        void *arr0_out);
+
+/* debug aid, not part of the reference interface: 16 x 4 %globaltimer stamps (entry, dependency wait passed, first step,
+ * exit of CTA 0) of the last single-lattice forward's kernels; synchronises the device.                          */
+int mmh_debug_timeline(unsigned long long *out64);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,7 @@ from .backend import (  # noqa: F401
     hermite_renormalized_batched,
     hermite_renormalized_1leftoverMode,
     hermite_renormalized_binomial,
+    hermite_renormalized_contracted,
     hermite_renormalized_diagonal,
 )
 

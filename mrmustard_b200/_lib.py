@@ -29,6 +29,7 @@ SYMBOLS = [
     "mmh_binomial", "mmh_binomial_host",
     "mmh_diagonal", "mmh_diagonal_host", "mmh_1leftover", "mmh_1leftover_host",
     "mmh_diagonal_grad", "mmh_diagonal_grad_host", "mmh_1leftover_grad", "mmh_1leftover_grad_host",
+    "mmh_forward_contract", "mmh_forward_contract_host", "mmh_debug_timeline",
 ]
 
 
@@ -58,6 +59,9 @@ def _load() -> ctypes.CDLL:
         "mmh_forward": ([ci, p64, vp, vp, vp, vp, ci, vp], ci),
         "mmh_forward_host": ([ci, p64, vp, vp, vp, vp, ci], ci),
         "mmh_forward_batched": ([i64, ci, p64, vp, vp, vp, vp, ci, vp], ci),
+        "mmh_forward_contract": ([i64, ci, p64, ci, vp, vp, vp, vp, ci, vp], ci),
+        "mmh_forward_contract_host": ([i64, ci, p64, ci, vp, vp, vp, vp, ci], ci),
+        "mmh_debug_timeline": ([vp], ci),
         "mmh_forward_panel_range": ([ci, p64, vp, vp, vp, ci, i64, i64, i64, vp], ci),
         "mmh_forward_batched_host": ([i64, ci, p64, vp, vp, vp, vp, ci], ci),
         "mmh_vjp": ([ci, p64, vp, vp, vp, vp, vp, vp, vp], ci),

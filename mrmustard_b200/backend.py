@@ -112,3 +112,32 @@ def hermite_renormalized(A, b, c, shape, stable=False, out=None):
         return result.reshape(batch_shape + shape)
     check_out_shape(())
     return hermite_renormalized_unbatched(A, b, c, shape, stable, out)
+
+
+def hermite_renormalized_contracted(A, b, c, shape, stable=False):
+    """Fock array of a PolyExpAnsatz with derived variables: `c` carries the polynomial coefficients,
+    c.shape = batch_shape + shape_derived_vars, and the result is what CircuitComponent.fock_array computes in its
+    `num_derived_vars > 0` branch (lab/circuit_components.py:516-530) -- hermite_renormalized over
+    `shape + shape_derived_vars` with unit vacuum amplitude followed by the einsum over the derived axes -- without
+    ever materialising the big lattice on the host.  Same batching as hermite_renormalized (A[..., D, D], b[..., D])."""
+    A = np.asarray(A)
+    b = np.asarray(b)
+    c = np.asarray(c)
+    shape = tuple(shape)
+    stable = stable or _reference_settings().STABLE_FOCK_CONVERSION
+    batch_shape = b.shape[:-1]
+    D = b.shape[-1]
+    n_derived = D - len(shape)
+    if n_derived < 0:
+        raise ValueError(f"len(shape)={len(shape)} exceeds the number of variables {D}")
+    if c.shape[: len(batch_shape)] != batch_shape or c.ndim != len(batch_shape) + n_derived:
+        raise ValueError(f"c.shape={c.shape} must be batch_shape={batch_shape} + {n_derived} derived axes")
+    shape_derived = c.shape[len(batch_shape):]
+    if A.shape[:-2] not in ((), batch_shape):
+        raise ValueError(f"A.shape={A.shape} must match batch_shape={batch_shape}")
+    if not batch_shape:
+        return strategies.vanilla_contract_numba(shape, shape_derived, A, b, c, stable)
+    B = int(np.prod(batch_shape))
+    Ab = np.broadcast_to(A, (*batch_shape, D, D)).reshape(B, D, D)
+    out = strategies.vanilla_contract_numba(shape, shape_derived, Ab, b.reshape(B, D), c.reshape(B, -1), stable)
+    return out.reshape(batch_shape + shape)

@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "mmh_params.cuh"
@@ -41,6 +43,9 @@ struct DeviceCtx {
     Scratch xbuf;                 // halo exchange buffer of the tiled march; all-ones sentinel between launches
     Scratch partial;              // VJP partial sums
     Scratch norm;                 // binomial norm scalar
+    Scratch timeline;             // 16 x 4 debug stamps of the last forward launches
+    Scratch lattice_ws;           // lattice kept on the device by mmh_forward_contract
+    Scratch ones;                 // vacuum amplitudes c = 1 of mmh_forward_contract
     Scratch host_slots[8];        // staging for the *_host entry points
 };
 static DeviceCtx g_ctx[64];
@@ -173,7 +178,7 @@ static int forward_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st, b
         StageParams sp;
         sp.d = d; sp.A = p.A; sp.b = p.b; sp.G = p.G; sp.sq = p.sq; sp.rsq = p.rsq;
         sp.batch = p.batch; sp.lat_stride = d.N; sp.stage = i; sp.L = L[i];
-        sp.c = p.c; sp.fuse_chain = 0; sp.pdl = 0;
+        sp.c = p.c; sp.fuse_chain = 0; sp.pdl = 0; sp.timeline = nullptr;
         const long long grid = (p.batch + L[i] - 1) / L[i];
         g_launches++;
         CK(mmh_launch_march_stage(sp, R[i], (int)grid, T[i], sm[i], st));
@@ -269,6 +274,34 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
     return true;
 }
 
+// The brute-force search above costs tens of microseconds of host time -- more than the GPU needs for a small stage, so an
+// uncached plan leaves the device idle between the launches of one lattice (measured: 12 us gaps on cfg2).  Plans are cached per
+// (shape, stage, SM count, tuning environment); callers hold g_mutex.
+struct TiledPlan { bool ok; TiledParams tp; int R, ntiles; size_t smem; };
+static bool plan_march_tiled_cached(const LatticeDesc &d, int stage, int sm_count, TiledParams *tp, int *R_out,
+                                    int *ntiles_out, size_t *smem_out) {
+    static std::map<std::string, TiledPlan> cache;
+    std::string key((const char *)d.shape, sizeof(int) * (size_t)d.D);
+    key.push_back((char)stage); key.push_back((char)d.D); key.append(std::to_string(sm_count));
+    for (const char *name : { "MMH_TILE_G", "MMH_TILE_STAGE", "MMH_TILE_MAXT", "MMH_TILE_R", "MMH_TILED_V1" }) {
+        const char *v = getenv(name);
+        key.push_back('|');
+        if (v) key.append(v);
+    }
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        TiledPlan pl;
+        memset(&pl, 0, sizeof(pl));
+        pl.ok = plan_march_tiled(d, stage, sm_count, &pl.tp, &pl.R, &pl.ntiles, &pl.smem);
+        if (cache.size() > 4096) cache.clear();
+        it = cache.emplace(key, pl).first;
+    }
+    const TiledPlan &pl = it->second;
+    if (!pl.ok) return false;
+    *tp = pl.tp; *R_out = pl.R; *ntiles_out = pl.ntiles; *smem_out = pl.smem;
+    return true;
+}
+
 // one large lattice: chain, then per stage the smallest machinery that fits
 // (single-CTA march / tiled multi-CTA march / plain per-step launches for giant panels)
 static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st) {
@@ -279,6 +312,11 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
     // touches the lattice.  The chain (stage D-1) is fused into the first march launch when that is a single CTA.
     const size_t absmem = sizeof(c128) * (size_t)(D * D + D);
     const bool use_pdl = !getenv("MMH_NO_PDL");
+    if (!ctx->timeline.ptr) {
+        int rc0;
+        if ((rc0 = ensure_scratch(ctx->timeline, 64 * sizeof(unsigned long long)))) return rc0;
+        CK(cudaMemset(ctx->timeline.ptr, 0, 64 * sizeof(unsigned long long)));
+    }
     bool chain_done = false, first = true;
     int rc;
     for (int i = D - 2; i >= 0; i--) {
@@ -286,11 +324,22 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
         int L, R, T, ntiles;
         size_t sm;
         TiledParams tp;
+        if (i == D - 2 && !chain_done && d.shape[D - 1] <= 64 && !getenv("MMH_NO_WARP_TAIL") && !getenv("MMH_FORCE_TILED")) {
+            // the two trailing stages by one warp (shuffles instead of shared memory + barriers)
+            StageParams sp;
+            sp.d = d; sp.A = p.A; sp.b = p.b; sp.G = p.G; sp.sq = p.sq; sp.rsq = p.rsq;
+            sp.batch = 1; sp.lat_stride = d.N; sp.stage = i; sp.L = 1;
+            sp.c = p.c; sp.fuse_chain = 1; sp.pdl = 0; sp.timeline = (unsigned long long *)ctx->timeline.ptr;
+            chain_done = true; first = false;
+            g_launches++;
+            CK(mmh_launch_warp_tail(sp, st));
+            continue;
+        }
         if (!getenv("MMH_FORCE_TILED") && plan_march_stage(d, i, 1, &L, &R, &T, &sm)) {
             StageParams sp;
             sp.d = d; sp.A = p.A; sp.b = p.b; sp.G = p.G; sp.sq = p.sq; sp.rsq = p.rsq;
             sp.batch = 1; sp.lat_stride = d.N; sp.stage = i; sp.L = L;
-            sp.c = p.c; sp.fuse_chain = chain_done ? 0 : 1; sp.pdl = (use_pdl && !first) ? 1 : 0;
+            sp.c = p.c; sp.fuse_chain = chain_done ? 0 : 1; sp.pdl = (use_pdl && !first) ? 1 : 0; sp.timeline = nullptr;
             chain_done = true; first = false;
             g_launches++;
             CK(mmh_launch_march_stage(sp, R, 1, T, sm, st));
@@ -302,8 +351,8 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
             chain_done = true; first = false;
         }
         if (0) {
-        } else if (plan_march_tiled(d, i, ctx->sm_count, &tp, &R, &ntiles, &sm)) {
-            tp.A = p.A; tp.b = p.b; tp.G = p.G; tp.sq = p.sq; tp.rsq = p.rsq;
+        } else if (plan_march_tiled_cached(d, i, ctx->sm_count, &tp, &R, &ntiles, &sm)) {
+            tp.A = p.A; tp.b = p.b; tp.G = p.G; tp.sq = p.sq; tp.rsq = p.rsq; tp.timeline = (unsigned long long *)ctx->timeline.ptr;
             tp.pdl = (use_pdl && !first && R != 4) ? 1 : 0;
             first = false;
             {   // exchange buffer: grow-only scratch, (re)filled with the sentinel whenever it is (re)allocated
@@ -923,3 +972,76 @@ int mmh_binomial_host(int ndim, const int64_t *shape, const void *A, const void 
 }
 
 }  // extern "C"
+
+// debug aid (not part of the reference interface): copies the 16 x 4 %globaltimer stamps of the last launches (mmh_common.cuh)
+extern "C" int mmh_debug_timeline(unsigned long long *out64) {
+    if (!out64) return MMH_ERR_NULL_POINTER;
+    CK(cudaDeviceSynchronize());
+    DeviceCtx *ctx;
+    int rc;
+    if ((rc = get_ctx(&ctx))) return rc;
+    if (!ctx->timeline.ptr) return MMH_ERR_UNSUPPORTED;
+    CK(cudaMemcpy(out64, ctx->timeline.ptr, sizeof(unsigned long long) * 64, cudaMemcpyDeviceToHost));
+    return MMH_OK;
+}
+
+// ---- lattice + derived-variable contraction ---------------------------------------------------------
+static int forward_contract_impl(long long batch, int ndim, const int64_t *shape, int ncore_dims, const void *dA, const void *db,
+                                 const void *dcp, void *dout, int stable, cudaStream_t st) {
+    if (batch < 0) return MMH_ERR_BAD_BATCH;
+    LatticeDesc d;
+    int mx;
+    int rc = make_desc(ndim, shape, &d, &mx);
+    if (rc) return rc;
+    if (ncore_dims < 0 || ncore_dims > ndim) return MMH_ERR_BAD_NDIM;
+    if (batch == 0) return MMH_OK;
+    if (!dA || !db || !dcp || !dout) return MMH_ERR_NULL_POINTER;
+    long long ncore = 1, nd = 1;
+    for (int i = 0; i < ndim; i++) (i < ncore_dims ? ncore : nd) *= shape[i];
+    if (nd > (1LL << 30)) return MMH_ERR_TOO_LARGE;
+    DeviceCtx *ctx;
+    if ((rc = get_ctx(&ctx))) return rc;
+    if ((size_t)batch * (size_t)d.N > ((size_t)150 << 30) / sizeof(c128)) return MMH_ERR_TOO_LARGE;
+    if ((rc = ensure_scratch(ctx->lattice_ws, sizeof(c128) * (size_t)batch * (size_t)d.N))) return rc;
+    if (ctx->ones.bytes < sizeof(c128) * (size_t)batch) {
+        if ((rc = ensure_scratch(ctx->ones, sizeof(c128) * (size_t)batch))) return rc;
+        g_launches++;
+        CK(mmh_launch_fill_ones((c128 *)ctx->ones.ptr, (long long)(ctx->ones.bytes / sizeof(c128)), st));
+    }
+    if ((rc = forward_impl(batch, ndim, shape, dA, db, ctx->ones.ptr, ctx->lattice_ws.ptr, stable, st))) return rc;
+    g_launches++;
+    CK(mmh_launch_contract_last((const c128 *)ctx->lattice_ws.ptr, (const c128 *)dcp, (c128 *)dout, batch * ncore, ncore, (int)nd, st));
+    return MMH_OK;
+}
+
+extern "C" int mmh_forward_contract(int64_t batch, int ndim, const int64_t *shape, int ncore_dims, const void *dA, const void *db,
+                                    const void *dcpoly, void *dout, int stable, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return forward_contract_impl(batch, ndim, shape, ncore_dims, dA, db, dcpoly, dout, stable, (cudaStream_t)stream);
+}
+
+extern "C" int mmh_forward_contract_host(int64_t batch, int ndim, const int64_t *shape, int ncore_dims, const void *A, const void *b,
+                                         const void *cpoly, void *out, int stable) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (batch < 0) return MMH_ERR_BAD_BATCH;
+    LatticeDesc d; int mx;
+    int rc = make_desc(ndim, shape, &d, &mx);
+    if (rc) return rc;
+    if (ncore_dims < 0 || ncore_dims > ndim) return MMH_ERR_BAD_NDIM;
+    if (batch == 0) return MMH_OK;
+    if (!A || !b || !cpoly || !out) return MMH_ERR_NULL_POINTER;
+    size_t ncore = 1, nd = 1;
+    for (int i = 0; i < ndim; i++) (i < ncore_dims ? ncore : nd) *= (size_t)shape[i];
+    DeviceCtx *ctx;
+    if ((rc = get_ctx(&ctx))) return rc;
+    void *dA, *db, *dcp, *dout;
+    const size_t D = ndim;
+    if ((rc = stage_in(*ctx, 0, A, sizeof(c128) * batch * D * D, &dA))) return rc;
+    if ((rc = stage_in(*ctx, 1, b, sizeof(c128) * batch * D, &db))) return rc;
+    if ((rc = stage_in(*ctx, 2, cpoly, sizeof(c128) * batch * nd, &dcp))) return rc;
+    if ((rc = stage_in(*ctx, 3, nullptr, sizeof(c128) * batch * ncore, &dout))) return rc;
+    if ((rc = forward_contract_impl(batch, ndim, shape, ncore_dims, dA, db, dcp, dout, stable, 0))) return rc;
+    CK(cudaMemcpyAsync(out, dout, sizeof(c128) * batch * ncore, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    return MMH_OK;
+}

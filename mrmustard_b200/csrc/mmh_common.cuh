@@ -22,6 +22,15 @@ struct LatticeDesc {
     long long strides[MMH_MAX_DIM];     // row-major element strides, strides[D-1] = 1
 };
 
+// Debug timeline (always on, four stamps per launch by one thread): tl[slot * 4 + what] = %globaltimer at kernel entry, after the
+// programmatic-dependency wait, at the first march step and at exit of CTA 0.  slot = stage index (0..7), 8 = trailing-stage kernel.
+// The buffer belongs to the device context; read back with mmh_debug_timeline() (mmh_api.cu), used by scripts/timeline_cfg2.py.
+__device__ __forceinline__ void timeline_stamp(unsigned long long *tl, int slot, int what) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (tl) tl[slot * 4 + what] = t;
+}
+
 __device__ __forceinline__ c128 c_make(double re, double im) { return make_double2(re, im); }
 
 // complex * complex, exactly as numba lowers it: (ac - bd, ad + bc), four products and two sums, no FMA.
@@ -60,7 +69,10 @@ __device__ __forceinline__ double div_by_table(double x, double s, double r) {
     if (!div_needs_slow(x)) return div_fast(x, s, r);
     return __ddiv_rn(x, s);
 }
+// one range test for both components, so that the two 5-level quotient chains interleave instead of running one after
+// the other behind two data-dependent branches (the 1-D chain is a pure latency loop: 170 -> ~105 cycles per step)
 __device__ __forceinline__ c128 c_div_table(c128 v, double s, double r) {
+    if (!(div_needs_slow(v.x) | div_needs_slow(v.y))) return make_double2(div_fast(v.x, s, r), div_fast(v.y, s, r));
     return make_double2(div_by_table(v.x, s, r), div_by_table(v.y, s, r));
 }
 __device__ __forceinline__ c128 c_div_real(c128 v, double s) {

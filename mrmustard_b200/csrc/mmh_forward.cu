@@ -361,3 +361,55 @@ cudaError_t mmh_launch_binomial(const BinomParams &p, int block, size_t smem, cu
     k_binomial_cta<<<1, block, smem, st>>>(p);
     return cudaGetLastError();
 }
+
+
+// ---------------------------------------------------------------------------------------------------
+// Derived-variable contraction after the lattice (CircuitComponent.fock_array, lab/circuit_components.py:516-530;
+// PolyExpAnsatz.decompose_ansatz, physics/ansatz/polyexp_ansatz.py:447-462):
+//     out[l, i] = sum_d G[l, i, d] * cpoly[l, d]          i < ncore, d < nd (the trailing "derived" axes of the lattice)
+// The lattice stays in device memory; only `out` (nd times smaller) travels to the host.
+// nd <= 32: one thread per output, terms added in index order; nd > 32: one warp per output, lanes stride over d and a
+// fixed-order shuffle tree adds the partial sums (deterministic).  Separate roundings (no FMA): the sum is what
+// np.einsum's scalar loop computes up to its (unspecified) order.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_contract_last(const c128 *__restrict__ G, const c128 *__restrict__ cp, c128 *__restrict__ out,
+                                                       long long nout, long long ncore, int nd) {
+    if (nd <= 32) {
+        const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (o >= nout) return;
+        const c128 *g = G + o * nd, *c = cp + (o / ncore) * nd;
+        c128 acc = c_mul(g[0], c[0]);
+        for (int d = 1; d < nd; d++) acc = c_add(acc, c_mul(g[d], c[d]));
+        out[o] = acc;
+    } else {
+        const long long o = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        const int lane = threadIdx.x & 31;
+        if (o >= nout) return;
+        const c128 *g = G + o * nd, *c = cp + (o / ncore) * nd;
+        c128 acc = c_make(0.0, 0.0);
+        for (int d = lane; d < nd; d += 32) acc = c_add(acc, c_mul(g[d], c[d]));
+        for (int w = 16; w > 0; w >>= 1) {
+            acc.x = __dadd_rn(acc.x, __shfl_down_sync(0xffffffffu, acc.x, w));
+            acc.y = __dadd_rn(acc.y, __shfl_down_sync(0xffffffffu, acc.y, w));
+        }
+        if (lane == 0) out[o] = acc;
+    }
+}
+
+cudaError_t mmh_launch_contract_last(const c128 *G, const c128 *cp, c128 *out, long long nout, long long ncore, int nd,
+                                     cudaStream_t st) {
+    const long long threads = nd <= 32 ? nout : nout * 32;
+    const long long grid = (threads + 255) / 256;
+    if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
+    k_contract_last<<<(unsigned)grid, 256, 0, st>>>(G, cp, out, nout, ncore, nd);
+    return cudaGetLastError();
+}
+
+__global__ void k_fill_ones(c128 *p, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = c_make(1.0, 0.0);
+}
+cudaError_t mmh_launch_fill_ones(c128 *p, long long n, cudaStream_t st) {
+    k_fill_ones<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n);
+    return cudaGetLastError();
+}

@@ -176,23 +176,148 @@ __global__ void __launch_bounds__(MMH_K2_MAXT(R), MMH_K2_MINB(R)) k_march_stage(
 
 // thread-per-lattice chain: stage D-1 (k_<D-1 = 0), G[n] = (b G[n-1] + A sqrt(n-1) G[n-2]) / sqrt(n).
 // For D == 1 this is the whole lattice (cfg1).
-__global__ void __launch_bounds__(128) k_fwd_chain(FwdParams p) {
+// dynamic shared memory: (sqrt, 1/sqrt) table of the chain when it fits (tab != 0), see k_warp_tail
+__global__ void __launch_bounds__(128) k_fwd_chain(FwdParams p, int tab) {
+    extern __shared__ double2 sqt_chain[];
     pdl_launch_dependents();
+    const int D = p.d.D, i = D - 1;
+    const int S = p.d.shape[i];
+    if (tab) {
+        for (int n = threadIdx.x; n < S; n += blockDim.x) sqt_chain[n] = make_double2(p.sq[n], p.rsq[n]);
+        __syncthreads();
+    }
     const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= p.batch) return;
-    const int D = p.d.D, i = D - 1;
     const c128 A = p.A[l * D * D + i * D + i], b = p.b[l * D + i];
     c128 *g = p.G + l * p.d.N;
-    const int S = p.d.shape[i];
     c128 p1 = p.c[l], p2 = c_make(0.0, 0.0);
     g[0] = p1;
+    double sqm = 0.0;
     for (int s = 1; s < S; s++) {
+        const double2 t = tab ? sqt_chain[s] : make_double2(p.sq[s], p.rsq[s]);
         c128 v = c_mul(b, p1);
-        if (s >= 2) v = c_add(v, c_mul(c_scale(A, p.sq[s - 1]), p2));
-        v = c_div_table(v, p.sq[s], p.rsq[s]);
+        if (s >= 2) v = c_add(v, c_mul(c_scale(A, sqm), p2));
+        v = c_div_table(v, t.x, t.y);
         g[s] = v;
-        p2 = p1; p1 = v;
+        p2 = p1; p1 = v; sqm = t.x;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// One warp, no shared-memory hand-off, no barrier: the two trailing stages of ONE lattice.
+//   stage D-1 (the 1-D chain, lane 0) and stage D-2 (panels of shape[D-1] <= 64 points, two per lane).
+// The only neighbour of stage D-2 is k - e_{D-2} - e_{D-1}: the previous panel's value one lane below, i.e. a
+// warp shuffle.  A step is then one dependent chain (shuffle, 2 + 1 + 5 FP64 levels, store): ~0.06 us instead of
+// the ~0.22 us of the shared-memory + barrier step, and both stages are latency bound (98 dependent steps of cfg2).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ c128 shfl_up_c128(c128 v, int delta) {
+    return make_double2(__shfl_up_sync(0xffffffffu, v.x, delta), __shfl_up_sync(0xffffffffu, v.y, delta));
+}
+__device__ __forceinline__ c128 shfl_c128(c128 v, int src) {
+    return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+
+__global__ void __launch_bounds__(32) k_warp_tail(StageParams p) {
+    __shared__ double2 sqt[64];
+    __shared__ c128 chain[64];
+    const LatticeDesc &d = p.d;
+    const int D = d.D, ic = D - 1, i2 = D - 2;
+    const int Sc = d.shape[ic], S2 = d.shape[i2];
+    const int lane = threadIdx.x;
+    const double *__restrict__ sq = p.sq;
+    const double *__restrict__ rsq = p.rsq;
+    pdl_launch_dependents();
+    if (lane == 0) { timeline_stamp(p.timeline, 8, 0); timeline_stamp(p.timeline, 8, 1); }
+    for (int n = lane; n < Sc; n += 32) sqt[n] = make_double2(sq[n], rsq[n]);
+    __syncwarp();
+    if (lane == 0) {   // stage D-1: G[n] = (b G[n-1] + A sqrt(n-1) G[n-2]) / sqrt(n)   (core.py:97-104 with i = D-1)
+        const c128 Ac = p.A[ic * D + ic], bc = p.b[ic];
+        c128 p1 = p.c[0], p2 = c_make(0.0, 0.0);
+        chain[0] = p1;
+        for (int s = 1; s < Sc; s++) {
+            c128 v = c_mul(bc, p1);
+            if (s >= 2) v = c_add(v, c_mul(c_scale(Ac, sqt[s - 1].x), p2));
+            v = c_div_table(v, sqt[s].x, sqt[s].y);
+            chain[s] = v;
+            p2 = p1; p1 = v;
+        }
+    }
+    __syncwarp();
+    // stage D-2: lane l owns k_{D-1} = l and l + 32
+    bool act[2];
+    c128 h0[2], h1[2], coef[2];
+    c128 *g[2];
+    const c128 Arow = p.A[i2 * D + ic];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int k = lane + 32 * r;
+        act[r] = k < Sc;
+        h1[r] = act[r] ? chain[k] : c_make(0.0, 0.0);
+        h0[r] = c_make(0.0, 0.0);
+        coef[r] = (act[r] && k > 0) ? c_scale(Arow, sqt[k].x) : c_make(0.0, 0.0);
+        g[r] = p.G + k;
+        if (act[r]) *g[r] = h1[r];
+    }
+    if (lane == 0) timeline_stamp(p.timeline, 8, 2);   // chain done
+    if (S2 < 2) return;
+    // (sqrt(s), 1/sqrt(s)) of the marched index in shared memory: a cold global load per step (an L2 round trip of
+    // ~300 cycles every few steps) would sit on the dependent chain of a ~100-cycle step
+    extern __shared__ double2 sqt2[];
+    const bool tab = p.L != 0;   // the host sets L = 1 when the table fits in shared memory
+    if (tab) {
+        for (int n = lane; n < S2; n += 32) sqt2[n] = make_double2(sq[n], rsq[n]);
+        __syncwarp();
+    }
+#define MMH_TAIL_SQ(n) (tab ? sqt2[(n)] : make_double2(sq[(n)], rsq[(n)]))
+    const c128 b0 = p.b[i2], a00 = p.A[i2 * D + i2];
+    const long long P = d.strides[i2];   // = Sc
+#define MMH_TAIL_STEP(P1, P2, SCUR)                                                                   \
+    {                                                                                                 \
+        const c128 up0 = shfl_up_c128(P1[0], 1), up1 = shfl_up_c128(P1[1], 1), wrap = shfl_c128(P1[0], 31); \
+        c128 nb[2];                                                                                   \
+        nb[0] = lane == 0 ? c_make(0.0, 0.0) : up0;                                                   \
+        nb[1] = lane == 0 ? wrap : up1;                                                               \
+        c128 v[2];                                                                                    \
+        _Pragma("unroll") for (int r = 0; r < 2; r++) {                                               \
+            v[r] = c_mul(b0, P1[r]);                                                                  \
+            if ((SCUR) >= 2) v[r] = c_add(v[r], c_mul(a00s, P2[r]));                                  \
+            v[r] = c_add(v[r], c_mul(coef[r], nb[r]));                                                \
+        }                                                                                             \
+        div_all_inplace<2>(v, sqs, rsqs);                                                             \
+        _Pragma("unroll") for (int r = 0; r < 2; r++) {                                               \
+            P2[r] = v[r];                                                                             \
+            g[r] += P;                                                                                \
+            if (act[r]) *g[r] = v[r];                                                                 \
+        }                                                                                             \
+    }
+    double2 t1_ = MMH_TAIL_SQ(1);
+    double sqs = t1_.x, rsqs = t1_.y;
+    c128 a00s = c_make(0.0, 0.0);
+    int s = 1;
+#pragma unroll 1
+    for (; s + 1 < S2; s += 2) {
+        const double2 ta = MMH_TAIL_SQ(s + 1);
+        const double2 tb = MMH_TAIL_SQ(s + 2 < S2 ? s + 2 : s + 1);
+        MMH_TAIL_STEP(h1, h0, s)
+        a00s = c_scale(a00, sqs); sqs = ta.x; rsqs = ta.y;
+        MMH_TAIL_STEP(h0, h1, s + 1)
+        a00s = c_scale(a00, sqs); sqs = tb.x; rsqs = tb.y;
+    }
+    if (s < S2) MMH_TAIL_STEP(h1, h0, s)
+#undef MMH_TAIL_STEP
+#undef MMH_TAIL_SQ
+    if (lane == 0) timeline_stamp(p.timeline, 8, 3);
+}
+
+cudaError_t mmh_launch_warp_tail(const StageParams &p0, cudaStream_t st) {
+    StageParams p = p0;
+    const int S2 = p.d.shape[p.d.D - 2];
+    size_t smem = sizeof(double2) * (size_t)S2;
+    p.L = smem <= 160 * 1024 ? 1 : 0;
+    if (!p.L) smem = 0;
+    if (smem > 40 * 1024) cudaFuncSetAttribute(k_warp_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_warp_tail<<<1, 32, smem, st>>>(p);
+    return cudaGetLastError();
 }
 
 // launch with (pdl = true) or without programmatic stream serialization
@@ -242,7 +367,11 @@ cudaError_t mmh_launch_march_stage(const StageParams &p, int R, int grid, int bl
 cudaError_t mmh_launch_chain(const FwdParams &p, cudaStream_t st) {
     const int block = 128;
     const long long grid = (p.batch + block - 1) / block;
-    k_fwd_chain<<<(unsigned)grid, block, 0, st>>>(p);
+    size_t smem = sizeof(double2) * (size_t)p.d.shape[p.d.D - 1];
+    const int tab = smem <= 160 * 1024 ? 1 : 0;
+    if (!tab) smem = 0;
+    if (smem > 40 * 1024) cudaFuncSetAttribute(k_fwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fwd_chain<<<(unsigned)grid, block, smem, st>>>(p, tab);
     return cudaGetLastError();
 }
 

@@ -51,6 +51,7 @@ struct StageParams {
     const c128 *c;               // vacuum amplitudes (used when fuse_chain)
     int fuse_chain;              // 1: this launch also computes stage D-1 (the chain) of its lattices first
     int pdl;                     // 1: launched with programmatic stream serialization (waits for the previous launch)
+    unsigned long long *timeline;   // debug stamps (mmh_common.cuh timeline_stamp), may be NULL
 };
 
 struct TiledParams {
@@ -68,7 +69,8 @@ struct TiledParams {
     int ls_max;                  // shared-memory stride of one panel buffer (>= local box size of any tile)
     int hc_max;                  // shared-memory stride of one halo ring slot (>= halo cells of any tile)
     int pdl;                     // 1: launched with programmatic stream serialization
-    unsigned long long *trace;   // debug timeline [tile][step][4] of %globaltimer stamps (MMH_TRACE_FILE), else NULL
+    unsigned long long *trace;   // debug timeline [tile][step][8] of %globaltimer stamps (MMH_TRACE_FILE), else NULL
+    unsigned long long *timeline;   // per-launch debug stamps (mmh_common.cuh timeline_stamp), may be NULL
 };
 
 cudaError_t mmh_stage_constants(const c128 *A, const c128 *b, int D, int stage, int slot, cudaStream_t st);
@@ -76,6 +78,9 @@ cudaError_t mmh_launch_march_tiled(const TiledParams &p, int R, int ntiles, size
 cudaError_t mmh_launch_march_tiled2(const TiledParams &p, int R, int ntiles, size_t smem, cudaStream_t st);
 size_t mmh_tiled2_smem(int ls_max, int hc_max, int S, int slots);
 cudaError_t mmh_launch_march_stage(const StageParams &p, int R, int grid, int block, size_t smem, cudaStream_t st);
+cudaError_t mmh_launch_warp_tail(const StageParams &p, cudaStream_t st);
+cudaError_t mmh_launch_contract_last(const c128 *G, const c128 *cp, c128 *out, long long nout, long long ncore, int nd, cudaStream_t st);
+cudaError_t mmh_launch_fill_ones(c128 *p, long long n, cudaStream_t st);
 cudaError_t mmh_launch_chain(const FwdParams &p, cudaStream_t st);
 cudaError_t mmh_launch_fwd_cta(const FwdParams &p, bool stable, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t mmh_coop_max_blocks(bool stable, int block, size_t smem, int *per_sm);

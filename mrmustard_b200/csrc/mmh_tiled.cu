@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
     constexpr int NB = MMH_T2_NB;
 
     pdl_launch_dependents2();
+    const bool tl = blockIdx.x == 0 && tid == 32 * MMH_T2_NHW;   // the timeline thread: compute thread 0 of tile 0
+    if (tl) timeline_stamp(p.timeline, i & 7, 0);
     // ---- tile geometry ----------------------------------------------------------------------------------
     int g[3], t[3], lo[3], e[3], h[3], gst[3], shp[3];
 #pragma unroll
@@ -210,6 +212,7 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
     }
     __syncthreads();
     pdl_wait2();   // panel 0 (written by the previous stage's kernel) and X are touched from here on
+    if (tl) timeline_stamp(p.timeline, i & 7, 1);
     // panel 0: halo faces and own cells -> buffer 0
     for (int c = tid; c < HC; c += blockDim.x) {
         int m = 0;
@@ -355,6 +358,7 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
 
     int s = 1;
     double sqm = 0.0;   // sqrt(s - 1)
+    if (tl) timeline_stamp(p.timeline, i & 7, 2);
 #pragma unroll 1
     for (; s + 1 < S; s += 2) {
         MMH_T2_STEP(h1, h0, s)
@@ -362,6 +366,7 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
     }
     if (s < S) MMH_T2_STEP(h1, h0, s)
 #undef MMH_T2_STEP
+    if (tl) timeline_stamp(p.timeline, i & 7, 3);
 }
 
 static cudaError_t launch_pdl2(void (*kern)(TiledParams), int grid, int block, size_t smem, cudaStream_t st, bool pdl,
@@ -379,10 +384,13 @@ static cudaError_t launch_pdl2(void (*kern)(TiledParams), int grid, int block, s
 template <int R>
 static cudaError_t launch_tiled2_R(const TiledParams &p, int ntiles, size_t smem, cudaStream_t st) {
     const int block = p.tc + 32 * MMH_T2_NHW;
+    static size_t smem_set[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };   // opt-in dynamic shared memory already granted (per instantiation)
 #define MMH_CASE(N)                                                                                   \
     case N:                                                                                           \
-        if (smem > 48 * 1024)                                                                         \
+        if (smem > 48 * 1024 && smem > smem_set[N]) {                                                 \
             cudaFuncSetAttribute(k_march_tiled2<R, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            smem_set[N] = smem;                                                                       \
+        }                                                                                             \
         return launch_pdl2(k_march_tiled2<R, N>, ntiles, block, smem, st, p.pdl != 0, p);
     const int npd = p.d.D - 1 - p.stage;
     switch (npd) {

@@ -21,7 +21,7 @@ __all__ = [
     "vanilla_batch_vjp_numba", "binomial", "vanilla", "stable",
     "hermite_multidimensional_diagonal", "hermite_multidimensional_1leftoverMode", "fast_diagonal",
     "grad_hermite_multidimensional_diagonal", "hermite_renormalized_diagonal_vjp",
-    "grad_hermite_multidimensional_1leftoverMode",
+    "grad_hermite_multidimensional_1leftoverMode", "vanilla_contract_numba",
 ]
 
 
@@ -296,3 +296,33 @@ def grad_hermite_multidimensional_1leftoverMode(A, B, G0, arr0, arr2=None, arr10
     dB = np.empty(shp + (2 * M,), np.complex128)
     check(lib.mmh_1leftover_grad_host(M, shape_array(cutoffs), _p(A), _p(B), _p(G0), _p(dG0), _p(dA), _p(dB)))
     return dG0, dA, dB
+
+
+def vanilla_contract_numba(shape, shape_derived, A, b, c_poly, stable=False) -> np.ndarray:
+    """Lattice with vacuum amplitude 1 over `shape + shape_derived`, contracted over the derived axes with the polynomial
+    coefficients `c_poly`: the fused form of
+        G = hermite_renormalized(A, b, ones, shape + shape_derived); einsum("...k,...k->...", G.reshape(.., -1), c.reshape(.., -1))
+    in CircuitComponent.fock_array (lab/circuit_components.py:516-530) and PolyExpAnsatz.decompose_ansatz
+    (physics/ansatz/polyexp_ansatz.py:447-462).  Unbatched (A[D,D], b[D], c_poly[*shape_derived]) or batched on the first
+    axis (A[B,D,D], b[B,D], c_poly[B,*shape_derived]).  The lattice never leaves the device."""
+    shape = _check_shape(shape)
+    shape_derived = _check_shape(shape_derived)
+    full = shape + shape_derived
+    D = len(full)
+    A = _c128(A)
+    b = _c128(b)
+    if b.shape[-1] != D:
+        raise ValueError(f"len(shape + shape_derived)={D} must equal b.shape[-1]={b.shape[-1]}")
+    batched = b.ndim == 2
+    B = b.shape[0] if batched else 1
+    nd = int(np.prod(shape_derived, dtype=np.int64))
+    A = A.reshape(B, D, D)
+    b = b.reshape(B, D)
+    c_poly = _c128(c_poly)
+    if c_poly.size != B * nd:
+        raise ValueError(f"c_poly has {c_poly.size} entries, expected batch x prod(shape_derived) = {B * nd}")
+    c_poly = c_poly.reshape(B, nd)
+    out = _lib.pinned_empty((B, *shape))
+    check(lib.mmh_forward_contract_host(B, D, shape_array(full), len(shape), _p(A), _p(b), _p(c_poly), _p(out),
+                                        int(bool(stable))))
+    return out if batched else out.reshape(shape)

@@ -121,3 +121,14 @@ def binomial(local_cutoffs, A, b, c, max_l2, global_cutoff):
     lib().mmo_binomial(ctypes.c_int(D), _p(sh), _p(A), _p(b), _p(c), ctypes.c_double(float(max_l2)),
                        ctypes.c_int64(int(global_cutoff)), _p(G), ctypes.byref(norm))
     return G, norm.value
+
+
+def vanilla_contract(shape, shape_derived, A, b, c_poly, stable=False):
+    """CircuitComponent.fock_array's derived-variable branch (lab/circuit_components.py:516-530), restated: the lattice over
+    shape + shape_derived with vacuum amplitude 1 (C oracle), then the reference's einsum over the flattened derived axes."""
+    shape = tuple(int(s) for s in shape); shape_derived = tuple(int(s) for s in shape_derived)
+    G = vanilla(shape + shape_derived, A, b, 1.0 + 0.0j, stable=stable)
+    G = G.reshape(shape + (-1,))
+    cs = np.asarray(c_poly, dtype=np.complex128).reshape(-1)
+    core = "".join(chr(97 + i) for i in range(G.ndim))
+    return np.einsum(f"{core},{core[-1]}->{core[:-1]}", G, cs)

@@ -77,6 +77,38 @@ __global__ void k_mix(double *out, long long *cyc, double a, double b, int n, in
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// the 1-D chain recurrence itself (complex, table division), one lane: cycles and wall ns per dependent step
+__device__ __forceinline__ double divf(double x, double s, double r) {
+    double q = __dmul_rn(x, r);
+    double e = __fma_rn(-s, q, x);
+    q = __fma_rn(e, r, q);
+    e = __fma_rn(-s, q, x);
+    return __fma_rn(e, r, q);
+}
+__global__ void k_chainrec(double *out, long long *cyc, double bx, double by, double ax, double ay, int n) {
+    __shared__ double2 tab[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) { double s = sqrt((double)(i + 1)); tab[i] = make_double2(s, 1.0 / s); }
+    __syncthreads();
+    double p1x = 1.0, p1y = 0.5, p2x = 0.0, p2y = 0.0;
+    unsigned long long g0, g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+    long long t0 = clk();
+    for (int s = 1; s < n; s++) {
+        const double2 t = tab[s & 1023];
+        double vx = __dsub_rn(__dmul_rn(bx, p1x), __dmul_rn(by, p1y)), vy = __dadd_rn(__dmul_rn(bx, p1y), __dmul_rn(by, p1x));
+        const double cx = __dmul_rn(ax, t.x), cy = __dmul_rn(ay, t.x);
+        vx = __dadd_rn(vx, __dsub_rn(__dmul_rn(cx, p2x), __dmul_rn(cy, p2y)));
+        vy = __dadd_rn(vy, __dadd_rn(__dmul_rn(cx, p2y), __dmul_rn(cy, p2x)));
+        vx = divf(vx, t.x, t.y); vy = divf(vy, t.x, t.y);
+        p2x = p1x; p2y = p1y; p1x = vx; p1y = vy;
+        if (fabs(p1x) > 1e100) { p1x *= 1e-100; p1y *= 1e-100; }
+    }
+    long long t1 = clk();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    if (threadIdx.x == 0) { cyc[0] = t1 - t0; cyc[1] = (long long)(g1 - g0); }
+    out[threadIdx.x] = p1x + p1y;
+}
+
 __global__ void k_lds(int *out, long long *cyc, int n) {
     __shared__ int tab[1024];
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) tab[i] = (i * 33 + 7) & 1023;
@@ -163,6 +195,11 @@ int main() {
         k_tput<2><<<148, warps * 32>>>(out, cyc, 1.0, 0.5, 2048); CK(cudaDeviceSynchronize());
         CK(cudaMemcpy(h, cyc, 8, cudaMemcpyDeviceToHost));
         printf("DFMA throughput, %2d warps/SM x ILP2: %.2f lane-ops/clk/SM\n", warps, 2048.0 * 2 * warps * 32 / h[0]);
+    }
+    for (int rep = 0; rep < 3; rep++) {
+        k_chainrec<<<1, 32>>>(out, cyc, 0.3, 0.2, -0.4, 0.1, 20000); CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(h, cyc, 16, cudaMemcpyDeviceToHost));
+        printf("chain recurrence, one warp: %.1f cycles/step, %.1f ns/step (=> %.0f MHz effective)\n", (double)h[0] / 20000, (double)h[1] / 20000, 1e3 * h[0] / (double)h[1]);
     }
 #define MIX(OP, NI) { k_mix<OP, NI><<<148, 512>>>(out, cyc, 1.0, 0.999, 2048, 3); CK(cudaDeviceSynchronize()); \
         CK(cudaMemcpy(h, cyc, 8, cudaMemcpyDeviceToHost)); \

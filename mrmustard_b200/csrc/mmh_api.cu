@@ -319,6 +319,38 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
     }
     bool chain_done = false, first = true;
     int rc;
+    // Stage overlap: when the last two marched stages are both tiled, the last one does not wait for its predecessor's
+    // kernel but for the amplitudes themselves (TiledParams::poll0).  Its panel 0 -- the first strides[i0] amplitudes of
+    // G -- is pre-filled with the sentinel before anything runs, and the two kernels get disjoint exchange buffers.
+    int i0 = -1, i1 = -1;            // last marched stage and its predecessor
+    for (int i = 0; i < D - 1 && i1 < 0; i++) {
+        if (d.shape[i] == 1) continue;
+        if (i0 < 0) i0 = i; else i1 = i;
+    }
+    bool overlap = false, overlap1 = false;   // overlap1: stage i1 in turn overlaps the one-warp kernel of the trailing stages
+    size_t xoff1 = 0;                // exchange-buffer offset (bytes) of stage i0 when it overlaps stage i1
+    if (use_pdl && i1 >= 0 && !tiled_v1() && !getenv("MMH_TRACE_FILE") && !getenv("MMH_NO_OVERLAP")) {
+        int L_, R_, T_, n0 = 0, n1 = 0;
+        size_t sm_;
+        TiledParams t0, t1;
+        const bool k2_0 = !getenv("MMH_FORCE_TILED") && plan_march_stage(d, i0, 1, &L_, &R_, &T_, &sm_);
+        const bool k2_1 = !getenv("MMH_FORCE_TILED") && plan_march_stage(d, i1, 1, &L_, &R_, &T_, &sm_);
+        const bool tail1 = i1 == D - 2 && d.shape[D - 1] <= 64 && !getenv("MMH_NO_WARP_TAIL") && !getenv("MMH_FORCE_TILED");
+        if (!k2_0 && !k2_1 && !tail1 && plan_march_tiled_cached(d, i0, ctx->sm_count, &t0, &R_, &n0, &sm_) &&
+            plan_march_tiled_cached(d, i1, ctx->sm_count, &t1, &R_, &n1, &sm_) && n0 + n1 <= ctx->sm_count &&
+            d.strides[i0] * (long long)sizeof(c128) <= (64LL << 20)) {
+            overlap = true;
+            overlap1 = i1 == D - 3 && d.shape[D - 2] > 1 && d.shape[D - 1] <= 64 && !getenv("MMH_NO_WARP_TAIL") &&
+                       !getenv("MMH_FORCE_TILED") && !getenv("MMH_NO_OVERLAP1");
+            xoff1 = (sizeof(c128) * (size_t)n1 * d.shape[i1] * t1.hc_max + 255) / 256 * 256;
+            const size_t xtotal = xoff1 + sizeof(c128) * (size_t)n0 * d.shape[i0] * t0.hc_max;
+            if (ctx->xbuf.bytes < xtotal || !ctx->xbuf.ptr) {   // both kernels' exchange buffers, before either is launched
+                if ((rc = ensure_scratch(ctx->xbuf, xtotal))) return rc;
+                CK(cudaMemset(ctx->xbuf.ptr, 0xFF, ctx->xbuf.bytes));
+            }
+            CK(cudaMemsetAsync(p.G, 0xFF, sizeof(c128) * (size_t)d.strides[i0], st));
+        }
+    }
     for (int i = D - 2; i >= 0; i--) {
         if (d.shape[i] == 1) continue;
         int L, R, T, ntiles;
@@ -355,13 +387,15 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
             tp.A = p.A; tp.b = p.b; tp.G = p.G; tp.sq = p.sq; tp.rsq = p.rsq; tp.timeline = (unsigned long long *)ctx->timeline.ptr;
             tp.pdl = (use_pdl && !first && R != 4) ? 1 : 0;
             first = false;
+            tp.poll0 = ((overlap && i == i0) || (overlap1 && i == i1)) ? 1 : 0;
             {   // exchange buffer: grow-only scratch, (re)filled with the sentinel whenever it is (re)allocated
-                const size_t xbytes = sizeof(c128) * (size_t)ntiles * d.shape[i] * tp.hc_max;
+                const size_t xoff = (overlap && i == i0) ? xoff1 : 0;
+                const size_t xbytes = xoff + sizeof(c128) * (size_t)ntiles * d.shape[i] * tp.hc_max;
                 if (ctx->xbuf.bytes < xbytes || !ctx->xbuf.ptr) {
                     if ((rc = ensure_scratch(ctx->xbuf, xbytes))) return rc;
                     CK(cudaMemset(ctx->xbuf.ptr, 0xFF, ctx->xbuf.bytes));
                 }
-                tp.X = (c128 *)ctx->xbuf.ptr;
+                tp.X = (c128 *)((char *)ctx->xbuf.ptr + xoff);
             }
             tp.cslot = 0;
             if (R == 4) {   // only the R == 4 variant reads A_i. and b_i from constant memory

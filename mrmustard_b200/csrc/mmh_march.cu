@@ -228,83 +228,82 @@ __global__ void __launch_bounds__(32) k_warp_tail(StageParams p) {
     const double *__restrict__ rsq = p.rsq;
     pdl_launch_dependents();
     if (lane == 0) { timeline_stamp(p.timeline, 8, 0); timeline_stamp(p.timeline, 8, 1); }
+    // every cold global load of the kernel is issued here, before the first use of any of them (one DRAM round trip
+    // instead of three dependent ones in front of the chain)
+    const c128 Ac = p.A[ic * D + ic], bc = p.b[ic], c0 = p.c[0];
+    const c128 Arow = p.A[i2 * D + ic], b0 = p.b[i2], a00 = p.A[i2 * D + i2];
     for (int n = lane; n < Sc; n += 32) sqt[n] = make_double2(sq[n], rsq[n]);
+    extern __shared__ double2 sqt2[];
+    const bool tab = p.L != 0;   // the host sets L = 1 when the table of the marched index fits in shared memory
+    if (tab) for (int n = lane; n < S2; n += 32) sqt2[n] = make_double2(sq[n], rsq[n]);
     __syncwarp();
     if (lane == 0) {   // stage D-1: G[n] = (b G[n-1] + A sqrt(n-1) G[n-2]) / sqrt(n)   (core.py:97-104 with i = D-1)
-        const c128 Ac = p.A[ic * D + ic], bc = p.b[ic];
-        c128 p1 = p.c[0], p2 = c_make(0.0, 0.0);
+        // software pipelined: the A-term of step s+1, (A sqrt(s)) G[s-1], and the table entry of step s+1 are issued
+        // beside the quotient of step s, so the dependent chain of a step is b*G (2 levels), one add, the range test and
+        // the 5-level quotient
+        c128 p1 = c0, aterm = c_make(0.0, 0.0);
         chain[0] = p1;
+        double2 t = sqt[Sc > 1 ? 1 : 0];
         for (int s = 1; s < Sc; s++) {
+            const double2 tn = sqt[s + 1 < Sc ? s + 1 : s];
             c128 v = c_mul(bc, p1);
-            if (s >= 2) v = c_add(v, c_mul(c_scale(Ac, sqt[s - 1].x), p2));
-            v = c_div_table(v, sqt[s].x, sqt[s].y);
+            if (s >= 2) v = c_add(v, aterm);
+            aterm = c_mul(c_scale(Ac, t.x), p1);
+            v = c_div_table(v, t.x, t.y);
             chain[s] = v;
-            p2 = p1; p1 = v;
+            p1 = v; t = tn;
         }
     }
     __syncwarp();
     // stage D-2: lane l owns k_{D-1} = l and l + 32
     bool act[2];
-    c128 h0[2], h1[2], coef[2];
+    c128 P1[2], aterm[2], coef[2];
     c128 *g[2];
-    const c128 Arow = p.A[i2 * D + ic];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
         const int k = lane + 32 * r;
         act[r] = k < Sc;
-        h1[r] = act[r] ? chain[k] : c_make(0.0, 0.0);
-        h0[r] = c_make(0.0, 0.0);
+        P1[r] = act[r] ? chain[k] : c_make(0.0, 0.0);
+        aterm[r] = c_make(0.0, 0.0);
         coef[r] = (act[r] && k > 0) ? c_scale(Arow, sqt[k].x) : c_make(0.0, 0.0);
         g[r] = p.G + k;
-        if (act[r]) *g[r] = h1[r];
+        if (act[r]) *g[r] = P1[r];
     }
     if (lane == 0) timeline_stamp(p.timeline, 8, 2);   // chain done
     if (S2 < 2) return;
     // (sqrt(s), 1/sqrt(s)) of the marched index in shared memory: a cold global load per step (an L2 round trip of
     // ~300 cycles every few steps) would sit on the dependent chain of a ~100-cycle step
-    extern __shared__ double2 sqt2[];
-    const bool tab = p.L != 0;   // the host sets L = 1 when the table fits in shared memory
-    if (tab) {
-        for (int n = lane; n < S2; n += 32) sqt2[n] = make_double2(sq[n], rsq[n]);
-        __syncwarp();
-    }
 #define MMH_TAIL_SQ(n) (tab ? sqt2[(n)] : make_double2(sq[(n)], rsq[(n)]))
-    const c128 b0 = p.b[i2], a00 = p.A[i2 * D + i2];
     const long long P = d.strides[i2];   // = Sc
-#define MMH_TAIL_STEP(P1, P2, SCUR)                                                                   \
-    {                                                                                                 \
-        const c128 up0 = shfl_up_c128(P1[0], 1), up1 = shfl_up_c128(P1[1], 1), wrap = shfl_c128(P1[0], 31); \
-        c128 nb[2];                                                                                   \
-        nb[0] = lane == 0 ? c_make(0.0, 0.0) : up0;                                                   \
-        nb[1] = lane == 0 ? wrap : up1;                                                               \
-        c128 v[2];                                                                                    \
-        _Pragma("unroll") for (int r = 0; r < 2; r++) {                                               \
-            v[r] = c_mul(b0, P1[r]);                                                                  \
-            if ((SCUR) >= 2) v[r] = c_add(v[r], c_mul(a00s, P2[r]));                                  \
-            v[r] = c_add(v[r], c_mul(coef[r], nb[r]));                                                \
-        }                                                                                             \
-        div_all_inplace<2>(v, sqs, rsqs);                                                             \
-        _Pragma("unroll") for (int r = 0; r < 2; r++) {                                               \
-            P2[r] = v[r];                                                                             \
-            g[r] += P;                                                                                \
-            if (act[r]) *g[r] = v[r];                                                                 \
-        }                                                                                             \
-    }
-    double2 t1_ = MMH_TAIL_SQ(1);
-    double sqs = t1_.x, rsqs = t1_.y;
-    c128 a00s = c_make(0.0, 0.0);
-    int s = 1;
+    const int rot_src = (lane + 31) & 31;
+    double2 t = MMH_TAIL_SQ(1);
 #pragma unroll 1
-    for (; s + 1 < S2; s += 2) {
-        const double2 ta = MMH_TAIL_SQ(s + 1);
-        const double2 tb = MMH_TAIL_SQ(s + 2 < S2 ? s + 2 : s + 1);
-        MMH_TAIL_STEP(h1, h0, s)
-        a00s = c_scale(a00, sqs); sqs = ta.x; rsqs = ta.y;
-        MMH_TAIL_STEP(h0, h1, s + 1)
-        a00s = c_scale(a00, sqs); sqs = tb.x; rsqs = tb.y;
+    for (int s = 1; s < S2; s++) {
+        const double2 tn = MMH_TAIL_SQ(s + 1 < S2 ? s + 1 : s);
+        // neighbours k_{D-1} - 1 of the previous panel: slot 0 from the lane below; slot 1 from the lane below, lane 0 from
+        // lane 31's slot 0 (one rotate of a per-lane selected value: two complex shuffles per step)
+        const c128 up0 = shfl_up_c128(P1[0], 1);
+        const c128 rot = shfl_c128(lane == 31 ? P1[0] : P1[1], rot_src);
+        c128 nb[2], v[2];
+        nb[0] = lane == 0 ? c_make(0.0, 0.0) : up0;
+        nb[1] = rot;
+        const c128 a00s = c_scale(a00, t.x);   // A_ii sqrt(s): coefficient of this panel in step s+1
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            v[r] = c_mul(b0, P1[r]);
+            if (s >= 2) v[r] = c_add(v[r], aterm[r]);
+            v[r] = c_add(v[r], c_mul(coef[r], nb[r]));
+            aterm[r] = c_mul(a00s, P1[r]);
+        }
+        div_all_inplace<2>(v, t.x, t.y);
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            P1[r] = v[r];
+            g[r] += P;
+            if (act[r]) *g[r] = v[r];
+        }
+        t = tn;
     }
-    if (s < S2) MMH_TAIL_STEP(h1, h0, s)
-#undef MMH_TAIL_STEP
 #undef MMH_TAIL_SQ
     if (lane == 0) timeline_stamp(p.timeline, 8, 3);
 }

@@ -69,6 +69,8 @@ struct TiledParams {
     int ls_max;                  // shared-memory stride of one panel buffer (>= local box size of any tile)
     int hc_max;                  // shared-memory stride of one halo ring slot (>= halo cells of any tile)
     int pdl;                     // 1: launched with programmatic stream serialization
+    int poll0;                   // 1: the previous stage's kernel is still running: do not wait for its completion, validate
+                                 //    every panel-0 amplitude by the sentinel the host pre-filled it with (stage overlap)
     unsigned long long *trace;   // debug timeline [tile][step][8] of %globaltimer stamps (MMH_TRACE_FILE), else NULL
     unsigned long long *timeline;   // per-launch debug stamps (mmh_common.cuh timeline_stamp), may be NULL
 };

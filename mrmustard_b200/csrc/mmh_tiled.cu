@@ -45,6 +45,17 @@ __device__ __forceinline__ void ldg_relaxed_v2(const void *p, unsigned long long
 __device__ __forceinline__ void stg_relaxed_v2(void *p, unsigned long long a, unsigned long long b) {
     asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
+// panel-0 amplitude that may not have been written yet (stage overlap): poll until both words differ from the sentinel
+__device__ __forceinline__ c128 poll_c128(const c128 *p, unsigned long long t_giveup) {
+    unsigned long long a, b;
+    unsigned spins = 0;
+    ldg_relaxed_v2(p, a, b);
+    while ((a == MMH_SENTINEL || b == MMH_SENTINEL) && ((++spins & 255u) != 0u || gtimer_ns() < t_giveup)) {
+        __nanosleep(100);
+        ldg_relaxed_v2(p, a, b);
+    }
+    return make_double2(__longlong_as_double((long long)a), __longlong_as_double((long long)b));
+}
 // shared memory through 32-bit addresses (byte offsets in the shared window)
 __device__ __forceinline__ c128 lds_c128(unsigned addr) {
     c128 v;
@@ -211,7 +222,21 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
         }
     }
     __syncthreads();
-    pdl_wait2();   // panel 0 (written by the previous stage's kernel) and X are touched from here on
+    // panel 0 (written by the previous stages' kernels) and X are touched from here on.  Normally that waits for the previous
+    // kernel to complete.  With poll0 the previous stage is still marching: every tile starts as soon as ITS part of panel 0
+    // exists (the host pre-filled panel 0 with the sentinel), so the tile pipeline of this stage fills while the previous
+    // stage finishes.  One thread first watches the last amplitude of the box (the previous stage writes panel 0 in
+    // ascending order of this box's first dim), so that 600 threads do not poll for tens of microseconds.
+    const unsigned long long t_giveup0 = gtimer_ns() + 4000000000ull;
+    if (!p.poll0) pdl_wait2();
+    else {
+        if (tid == 0) {
+            const long long last = (long long)(lo[0] + e[0] - 1) * gst[0] + (long long)(lo[1] + e[1] - 1) * gst[1] +
+                                   (long long)(lo[2] + e[2] - 1) * gst[2] + inner - 1;
+            (void)poll_c128(p.G + last, t_giveup0);
+        }
+        __syncthreads();
+    }
     if (tl) timeline_stamp(p.timeline, i & 7, 1);
     // panel 0: halo faces and own cells -> buffer 0
     for (int c = tid; c < HC; c += blockDim.x) {
@@ -228,12 +253,12 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
         const int loa = a == 0 ? lo[0] : lo[1], ga = a == 0 ? gst[0] : gst[1];
         const int lob = b == 1 ? lo[1] : lo[2], gb = b == 1 ? gst[1] : gst[2];
         const int go = (lom - 1) * gm + (loa + xa) * ga + (lob + xb) * gb + rr;
-        sts_c128(sbase + halo_off + 16u * (unsigned)c, __ldcg(p.G + go));
+        sts_c128(sbase + halo_off + 16u * (unsigned)c, p.poll0 ? poll_c128(p.G + go, t_giveup0) : __ldcg(p.G + go));
     }
 #pragma unroll
     for (int r = 0; r < R; r++) {
         h0[r] = c_make(0.0, 0.0);
-        h1[r] = (flags[r] & 1u) ? __ldcg(p.G + gofs[r]) : c_make(0.0, 0.0);
+        h1[r] = (flags[r] & 1u) ? (p.poll0 ? poll_c128(p.G + gofs[r], t_giveup0) : __ldcg(p.G + gofs[r])) : c_make(0.0, 0.0);
         if (tidc >= 0) sts_c128(sbase + loco[r], h1[r]);
     }
     __syncthreads();

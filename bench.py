@@ -333,7 +333,8 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     # one step = one mmh_forward[_batched] call = the launches listed here; the roofline figure is the whole step's
     # algorithmic bytes over the whole step's device time (a lower bound of the dominant kernel's own figure)
-    kernel_name = ("mmh_forward: k_fwd_chain + k_march_stage<2,1> + k_march_tiled<1,2> + k_march_tiled<2,3> (dominant, ~62% of the step)"
+    kernel_name = ("mmh_forward: memset(panel 0) + k_warp_tail + k_march_tiled2<1,2> + k_march_tiled2<2,3> (dominant, 66% of the serialised "
+                   "kernel time; the three kernels overlap)"
                    if w["batch"] is None else "mmh_forward_batched: k_fwd_chain + k_march_stage<2,1> (dominant, >95% of the step)")
     traffic_note = None
     if os.path.exists(tpath):

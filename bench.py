@@ -420,6 +420,15 @@ def extras(torch, dev, lib, check, _lib, stream, sptr, flush):
         oc = torch.empty((1,), dtype=torch.complex128, device=dev)
         ms = timeit(lambda: check(lib.mmh_vjp(4, sh, dG.data_ptr(), dc.data_ptr(), g.data_ptr(), oA.data_ptr(), ob.data_ptr(), oc.data_ptr(), sptr)), 10, True)
         out["cfg5_vjp"] = {"amps_per_s": n / (ms * 1e-3), "ms": ms, "hbm_frac": 32.0 * n / (ms * 1e-3) / 1e9 / peak}
+        # cfg2 as a batch: 8 x (50,)^4 through hermite_renormalized_batched (consecutive lattices pipelined on the device)
+        A, b, c = gold["cfg2_A"], gold["cfg2_b"], gold["cfg2_c"].reshape(1)
+        Bq = 8
+        dA, db, dc = (torch.from_numpy(np.ascontiguousarray(np.repeat(x[None], Bq, 0))).to(dev) for x in (A, b, c))
+        shape = (50,) * 4; sh = _lib.shape_array(shape); n = 50 ** 4
+        dG = torch.empty((Bq, n), dtype=torch.complex128, device=dev)
+        ms = timeit(lambda: check(lib.mmh_forward_batched(Bq, 4, sh, dA.data_ptr(), db.data_ptr(), dc.data_ptr(), dG.data_ptr(), 0, sptr)), 5, True)
+        out["cfg2_batch8_forward"] = {"amps_per_s": Bq * n / (ms * 1e-3), "ms": ms, "hbm_frac": 16.0 * Bq * n / (ms * 1e-3) / 1e9 / peak}
+        del dG
         # cfg1: latency config
         A, b, c = gold["cfg1_A"], gold["cfg1_b"], gold["cfg1_c"].reshape(1)
         dA, db, dc = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (A, b, c))

@@ -166,7 +166,7 @@ int mmh_1leftover(int M, const int64_t *cutoffs, const void *dA, const void *dB,
 int mmh_1leftover_host(int M, const int64_t *cutoffs, const void *A, const void *B, const void *G0,
                        void *arr0_out);
 
-/* debug aid, not part of the reference interface: 16 x 4 %globaltimer stamps (entry, dependency wait passed, first step,
+/* debug aid, not part of the reference interface: 4 (lattice index mod 4) x 16 x 4 %globaltimer stamps (entry, dependency wait passed, first step,
  * exit of CTA 0) of the last single-lattice forward's kernels; synchronises the device.                          */
 int mmh_debug_timeline(unsigned long long *out64);
 

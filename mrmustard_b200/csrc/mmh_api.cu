@@ -178,7 +178,7 @@ static int forward_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st, b
         StageParams sp;
         sp.d = d; sp.A = p.A; sp.b = p.b; sp.G = p.G; sp.sq = p.sq; sp.rsq = p.rsq;
         sp.batch = p.batch; sp.lat_stride = d.N; sp.stage = i; sp.L = L[i];
-        sp.c = p.c; sp.fuse_chain = 0; sp.pdl = 0; sp.timeline = nullptr;
+        sp.c = p.c; sp.fuse_chain = 0; sp.pdl = 0; sp.timeline = nullptr; sp.fill_n = 0;
         const long long grid = (p.batch + L[i] - 1) / L[i];
         g_launches++;
         CK(mmh_launch_march_stage(sp, R[i], (int)grid, T[i], sm[i], st));
@@ -304,7 +304,12 @@ static bool plan_march_tiled_cached(const LatticeDesc &d, int stage, int sm_coun
 
 // one large lattice: chain, then per stage the smallest machinery that fits
 // (single-CTA march / tiled multi-CTA march / plain per-step launches for giant panels)
-static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st) {
+// `seq` = index of the lattice inside one API call.  Consecutive lattices of a batch are pipelined: lattice seq+1's kernels are
+// launched with programmatic stream serialization behind lattice seq's last kernel, so its latency-bound small stages and the
+// fill of its tile pipeline run on the SMs that lattice seq's tile pipeline has already vacated.  Every kMaxInFlight-th lattice
+// is launched in plain stream order (full wait), which makes the reuse of an exchange-buffer slot (seq % kMaxInFlight) safe.
+static const int kMaxInFlight = 4;
+static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st, long long seq) {
     const LatticeDesc &d = p.d;
     const int D = d.D;
     // The launches of one lattice are chained with programmatic dependent launch: each kernel releases its
@@ -314,8 +319,8 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
     const bool use_pdl = !getenv("MMH_NO_PDL");
     if (!ctx->timeline.ptr) {
         int rc0;
-        if ((rc0 = ensure_scratch(ctx->timeline, 64 * sizeof(unsigned long long)))) return rc0;
-        CK(cudaMemset(ctx->timeline.ptr, 0, 64 * sizeof(unsigned long long)));
+        if ((rc0 = ensure_scratch(ctx->timeline, 256 * sizeof(unsigned long long)))) return rc0;
+        CK(cudaMemset(ctx->timeline.ptr, 0, 256 * sizeof(unsigned long long)));
     }
     bool chain_done = false, first = true;
     int rc;
@@ -328,6 +333,8 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
         if (i0 < 0) i0 = i; else i1 = i;
     }
     bool overlap = false, overlap1 = false;   // overlap1: stage i1 in turn overlaps the one-warp kernel of the trailing stages
+    bool pipelined = false;          // this lattice's first kernels are chained behind the previous lattice's (see kMaxInFlight)
+    size_t xbase = 0;                // exchange-buffer slot of this lattice
     size_t xoff1 = 0;                // exchange-buffer offset (bytes) of stage i0 when it overlaps stage i1
     if (use_pdl && i1 >= 0 && !tiled_v1() && !getenv("MMH_TRACE_FILE") && !getenv("MMH_NO_OVERLAP")) {
         int L_, R_, T_, n0 = 0, n1 = 0;
@@ -343,12 +350,18 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
             overlap1 = i1 == D - 3 && d.shape[D - 2] > 1 && d.shape[D - 1] <= 64 && !getenv("MMH_NO_WARP_TAIL") &&
                        !getenv("MMH_FORCE_TILED") && !getenv("MMH_NO_OVERLAP1");
             xoff1 = (sizeof(c128) * (size_t)n1 * d.shape[i1] * t1.hc_max + 255) / 256 * 256;
-            const size_t xtotal = xoff1 + sizeof(c128) * (size_t)n0 * d.shape[i0] * t0.hc_max;
-            if (ctx->xbuf.bytes < xtotal || !ctx->xbuf.ptr) {   // both kernels' exchange buffers, before either is launched
+            const size_t xslot = (xoff1 + sizeof(c128) * (size_t)n0 * d.shape[i0] * t0.hc_max + 255) / 256 * 256;
+            const size_t xtotal = xslot * (size_t)kMaxInFlight;
+            if (ctx->xbuf.bytes < xtotal || !ctx->xbuf.ptr) {   // every kernel's exchange buffer, before any is launched
                 if ((rc = ensure_scratch(ctx->xbuf, xtotal))) return rc;
                 CK(cudaMemset(ctx->xbuf.ptr, 0xFF, ctx->xbuf.bytes));
             }
-            CK(cudaMemsetAsync(p.G, 0xFF, sizeof(c128) * (size_t)d.strides[i0], st));
+            xbase = xslot * (size_t)(seq % kMaxInFlight);
+            pipelined = overlap1;   // the first kernel is then the one-warp tail, which fills panel 0 with the sentinel itself
+            if (!pipelined) {       // else: a separate fill kernel in plain stream order
+                g_launches++;
+                CK(mmh_launch_fill_sentinel((c128 *)p.G, d.strides[i0], false, st));
+            }
         }
     }
     for (int i = D - 2; i >= 0; i--) {
@@ -361,7 +374,8 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
             StageParams sp;
             sp.d = d; sp.A = p.A; sp.b = p.b; sp.G = p.G; sp.sq = p.sq; sp.rsq = p.rsq;
             sp.batch = 1; sp.lat_stride = d.N; sp.stage = i; sp.L = 1;
-            sp.c = p.c; sp.fuse_chain = 1; sp.pdl = 0; sp.timeline = (unsigned long long *)ctx->timeline.ptr;
+            sp.c = p.c; sp.fuse_chain = 1; sp.fill_n = pipelined ? d.strides[i0] : 0;
+            sp.pdl = (pipelined && (seq % kMaxInFlight) != 0) ? 1 : 0; sp.timeline = (unsigned long long *)ctx->timeline.ptr + 64 * (seq % kMaxInFlight);
             chain_done = true; first = false;
             g_launches++;
             CK(mmh_launch_warp_tail(sp, st));
@@ -371,7 +385,7 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
             StageParams sp;
             sp.d = d; sp.A = p.A; sp.b = p.b; sp.G = p.G; sp.sq = p.sq; sp.rsq = p.rsq;
             sp.batch = 1; sp.lat_stride = d.N; sp.stage = i; sp.L = L;
-            sp.c = p.c; sp.fuse_chain = chain_done ? 0 : 1; sp.pdl = (use_pdl && !first) ? 1 : 0; sp.timeline = nullptr;
+            sp.c = p.c; sp.fuse_chain = chain_done ? 0 : 1; sp.pdl = (use_pdl && !first) ? 1 : 0; sp.timeline = nullptr; sp.fill_n = 0;
             chain_done = true; first = false;
             g_launches++;
             CK(mmh_launch_march_stage(sp, R, 1, T, sm, st));
@@ -384,12 +398,12 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
         }
         if (0) {
         } else if (plan_march_tiled_cached(d, i, ctx->sm_count, &tp, &R, &ntiles, &sm)) {
-            tp.A = p.A; tp.b = p.b; tp.G = p.G; tp.sq = p.sq; tp.rsq = p.rsq; tp.timeline = (unsigned long long *)ctx->timeline.ptr;
+            tp.A = p.A; tp.b = p.b; tp.G = p.G; tp.sq = p.sq; tp.rsq = p.rsq; tp.timeline = (unsigned long long *)ctx->timeline.ptr + 64 * (seq % kMaxInFlight);
             tp.pdl = (use_pdl && !first && R != 4) ? 1 : 0;
             first = false;
             tp.poll0 = ((overlap && i == i0) || (overlap1 && i == i1)) ? 1 : 0;
             {   // exchange buffer: grow-only scratch, (re)filled with the sentinel whenever it is (re)allocated
-                const size_t xoff = (overlap && i == i0) ? xoff1 : 0;
+                const size_t xoff = xbase + ((overlap && i == i0) ? xoff1 : 0);
                 const size_t xbytes = xoff + sizeof(c128) * (size_t)ntiles * d.shape[i] * tp.hc_max;
                 if (ctx->xbuf.bytes < xbytes || !ctx->xbuf.ptr) {
                     if ((rc = ensure_scratch(ctx->xbuf, xbytes))) return rc;
@@ -487,7 +501,7 @@ static int forward_impl(long long batch, int ndim, const int64_t *shape, const v
             FwdParams q = p;
             q.A = p.A + l * ndim * ndim; q.b = p.b + l * ndim; q.c = p.c + l; q.G = p.G + l * d.N;
             q.batch = 1;
-            if ((rc = forward_single_staged(q, ctx, st))) return rc;
+            if ((rc = forward_single_staged(q, ctx, st, l))) return rc;
         }
         return MMH_OK;
     }
@@ -1015,7 +1029,7 @@ extern "C" int mmh_debug_timeline(unsigned long long *out64) {
     int rc;
     if ((rc = get_ctx(&ctx))) return rc;
     if (!ctx->timeline.ptr) return MMH_ERR_UNSUPPORTED;
-    CK(cudaMemcpy(out64, ctx->timeline.ptr, sizeof(unsigned long long) * 64, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out64, ctx->timeline.ptr, sizeof(unsigned long long) * 256, cudaMemcpyDeviceToHost));
     return MMH_OK;
 }
 

@@ -203,6 +203,19 @@ __global__ void __launch_bounds__(128) k_fwd_chain(FwdParams p, int tab) {
     }
 }
 
+// launch with (pdl = true) or without programmatic stream serialization
+template <typename P>
+static cudaError_t launch_pdl(void (*kern)(P), int grid, int block, size_t smem, cudaStream_t st, bool pdl, const P &p) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // One warp, no shared-memory hand-off, no barrier: the two trailing stages of ONE lattice.
 //   stage D-1 (the 1-D chain, lane 0) and stage D-2 (panels of shape[D-1] <= 64 points, two per lane).
@@ -226,7 +239,24 @@ __global__ void __launch_bounds__(32) k_warp_tail(StageParams p) {
     const int lane = threadIdx.x;
     const double *__restrict__ sq = p.sq;
     const double *__restrict__ rsq = p.rsq;
+    // Stage overlap (p.fill_n > 0): the dependents validate amplitudes by the all-ones sentinel, so G[0, fill_n) is filled with
+    // it before they are released -- by this kernel itself (CTAs >= 1, and CTA 0 for the cells it is about to compute), never
+    // by a griddepcontrol.wait: a kernel that waits also waits for everything its predecessor was chained to, which would
+    // serialise consecutive lattices of a batch.  __threadfence makes the fill visible before the release.
+    if (p.fill_n > 0) {
+        ulonglong2 *gs = (ulonglong2 *)p.G;
+        const ulonglong2 sent = make_ulonglong2(0xFFFFFFFFFFFFFFFFull, 0xFFFFFFFFFFFFFFFFull);
+        const long long own = (long long)Sc * S2 < p.fill_n ? (long long)Sc * S2 : p.fill_n;   // what CTA 0 computes itself
+        if (blockIdx.x == 0) {
+            for (long long n = lane; n < own; n += 32) gs[n] = sent;
+        } else {
+            const long long nf = gridDim.x - 1;
+            for (long long n = own + (long long)(blockIdx.x - 1) * 32 + lane; n < p.fill_n; n += nf * 32) gs[n] = sent;
+        }
+        __threadfence();
+    }
     pdl_launch_dependents();
+    if (blockIdx.x != 0) return;
     if (lane == 0) { timeline_stamp(p.timeline, 8, 0); timeline_stamp(p.timeline, 8, 1); }
     // every cold global load of the kernel is issued here, before the first use of any of them (one DRAM round trip
     // instead of three dependent ones in front of the chain)
@@ -308,6 +338,21 @@ __global__ void __launch_bounds__(32) k_warp_tail(StageParams p) {
     if (lane == 0) timeline_stamp(p.timeline, 8, 3);
 }
 
+// all-ones sentinel over n amplitudes (stage overlap: panel 0 of the last tiled stage)
+struct FillArgs { ulonglong2 *p; long long n; };
+__global__ void __launch_bounds__(256) k_fill_sentinel_s(FillArgs a) {
+    pdl_launch_dependents();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride)
+        a.p[i] = make_ulonglong2(0xFFFFFFFFFFFFFFFFull, 0xFFFFFFFFFFFFFFFFull);
+}
+cudaError_t mmh_launch_fill_sentinel(c128 *p, long long n, bool pdl, cudaStream_t st) {
+    long long grid = (n + 255) / 256;
+    if (grid > 592) grid = 592;
+    FillArgs a = { (ulonglong2 *)p, n };
+    return launch_pdl(k_fill_sentinel_s, (int)grid, 256, 0, st, pdl, a);
+}
+
 cudaError_t mmh_launch_warp_tail(const StageParams &p0, cudaStream_t st) {
     StageParams p = p0;
     const int S2 = p.d.shape[p.d.D - 2];
@@ -315,21 +360,12 @@ cudaError_t mmh_launch_warp_tail(const StageParams &p0, cudaStream_t st) {
     p.L = smem <= 160 * 1024 ? 1 : 0;
     if (!p.L) smem = 0;
     if (smem > 40 * 1024) cudaFuncSetAttribute(k_warp_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_warp_tail<<<1, 32, smem, st>>>(p);
-    return cudaGetLastError();
-}
-
-// launch with (pdl = true) or without programmatic stream serialization
-template <typename P>
-static cudaError_t launch_pdl(void (*kern)(P), int grid, int block, size_t smem, cudaStream_t st, bool pdl, const P &p) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kern, p);
+    int grid = 1;
+    if (p.fill_n > (long long)p.d.shape[p.d.D - 1] * S2) {
+        const long long cells = p.fill_n - (long long)p.d.shape[p.d.D - 1] * S2;
+        grid += (int)((cells + 32 * 32 - 1) / (32 * 32) < 512 ? (cells + 32 * 32 - 1) / (32 * 32) : 512);
+    }
+    return launch_pdl(k_warp_tail, grid, 32, smem, st, p.pdl != 0, p);
 }
 
 template <int R>

@@ -52,6 +52,7 @@ struct StageParams {
     int fuse_chain;              // 1: this launch also computes stage D-1 (the chain) of its lattices first
     int pdl;                     // 1: launched with programmatic stream serialization (waits for the previous launch)
     unsigned long long *timeline;   // debug stamps (mmh_common.cuh timeline_stamp), may be NULL
+    long long fill_n;            // k_warp_tail: pre-fill G[0, fill_n) with the all-ones sentinel first (stage overlap), 0 = no
 };
 
 struct TiledParams {
@@ -82,6 +83,7 @@ size_t mmh_tiled2_smem(int ls_max, int hc_max, int S, int slots);
 cudaError_t mmh_launch_march_stage(const StageParams &p, int R, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t mmh_launch_warp_tail(const StageParams &p, cudaStream_t st);
 cudaError_t mmh_launch_contract_last(const c128 *G, const c128 *cp, c128 *out, long long nout, long long ncore, int nd, cudaStream_t st);
+cudaError_t mmh_launch_fill_sentinel(c128 *p, long long n, bool pdl, cudaStream_t st);
 cudaError_t mmh_launch_fill_ones(c128 *p, long long n, cudaStream_t st);
 cudaError_t mmh_launch_chain(const FwdParams &p, cudaStream_t st);
 cudaError_t mmh_launch_fwd_cta(const FwdParams &p, bool stable, int grid, int block, size_t smem, cudaStream_t st);

@@ -16,13 +16,13 @@ dG = torch.empty(shape, dtype=torch.complex128, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 def run(): _lib.check(_lib.lib.mmh_forward(4, sh, dA.data_ptr(), db.data_ptr(), dc.data_ptr(), dG.data_ptr(), 0, None))
 for _ in range(3): run()
-out = (ctypes.c_ulonglong * 64)()
+out = (ctypes.c_ulonglong * 256)()
 for rep in range(3):
     flush.fill_(1); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); run(); b.record(); torch.cuda.synchronize()
     assert lib.mmh_debug_timeline(out) == 0
-    t = np.array(list(out), dtype=np.int64).reshape(16, 4)
+    t = np.array(list(out), dtype=np.int64).reshape(4, 16, 4)[0]
     t0 = t[8, 0]
     print(f"rep {rep}: event time {a.elapsed_time(b)*1e3:.1f} us")
     for slot, name in ((8, "tail (chain + stage 2)"), (1, "stage 1 tiled"), (0, "stage 0 tiled")):

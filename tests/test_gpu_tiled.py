@@ -61,3 +61,15 @@ def test_giant_panel_fallback(S, O):
     shape = (3, 11, 11, 11, 11, 11, 11)
     A, b, c = random_triple(len(shape), (), seed=9)
     assert np.array_equal(S.vanilla_numba(shape, A, b, complex(c)), O.vanilla(shape, A, b, complex(c)))
+
+
+def test_batch_of_large_lattices_pipelined(S, O):
+    """A batch of lattices that each take the multi-kernel single-lattice path: consecutive lattices are pipelined behind each other
+    (programmatic launch chain, rotating exchange-buffer slots, full stream order every 4th lattice) -- 6 lattices cross that boundary."""
+    shape = (24, 25, 26, 27)
+    A, b, c = random_triple(4, (6,), seed=31)
+    G = S.vanilla_batch_numba(shape, A, b, c)
+    for l in range(6):
+        assert np.array_equal(G[l], O.vanilla(shape, A[l], b[l], complex(c[l]))), l
+    G2 = S.vanilla_batch_numba(shape, A, b, c)   # second call reuses the slots
+    assert np.array_equal(G, G2)

@@ -13,7 +13,6 @@
 
 #include "mmh_params.cuh"
 
-#define MMH_KRING_HOST 4  // must equal MMH_KRING in mmh_march.cu
 
 
 #define CK(call)                                   \
@@ -38,7 +37,6 @@ struct DeviceCtx {
     int table_len = 0;
     unsigned *barrier = nullptr;  // 64 counters; one is consumed per cooperative launch (round robin)
     int barrier_next = 0;
-    int cslot_next = 0;           // ring of constant-memory slots for the tiled march (MMH_CSLOTS)
     Scratch diag_ws;              // auxiliary arrays of the compactFock sweeps
     Scratch xbuf;                 // halo exchange buffer of the tiled march; all-ones sentinel between launches
     Scratch partial;              // VJP partial sums
@@ -189,11 +187,8 @@ static int forward_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st, b
 }
 
 // K1 plan: tile grid over the first nt panel dims of `stage` (mmh_march.cu k_march_tiled)
-static bool tiled_v1() { return getenv("MMH_TILED_V1") != nullptr; }   // A/B hook: first-generation tiled kernel
-
 static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, TiledParams *tp, int *R_out,
                              int *ntiles_out, size_t *smem_out) {
-    const bool v1 = tiled_v1();
     const int npd = d.D - 1 - stage;
     if (npd < 1 || npd > 7) return false;
     const long long P = d.strides[stage];
@@ -208,11 +203,9 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
         if (!getenv("MMH_TILE_STAGE") || atoi(getenv("MMH_TILE_STAGE")) == stage)
             sscanf(eg, "%d,%d,%d", &forced[0], &forced[1], &forced[2]);
     double best = 1e300;
-    int bg[3] = { 0, 0, 0 }, bR = 0, bTC = 0, bLS = 0, bHC = 0, bSq = 0;
-    // up to two tile-owner CTAs per SM (R <= 2 CTAs of <= 320 threads fit twice in the register file and overlap one
-    // tile's dependent FP64 chain with the other's issue); all tiles must be co-resident
-    // (measured on cfg2: two CTAs per SM give no gain over one, 177 vs 176 us, so the default stays one per SM)
-    const int maxt = getenv("MMH_TILE_MAXT") ? atoi(getenv("MMH_TILE_MAXT")) : sm_count;
+    int bg[3] = { 0, 0, 0 }, bR = 0, bTC = 0, bLS = 0, bHC = 0;
+    // one tile-owner CTA per SM (640 threads x 96 registers fill the register file); all tiles must be co-resident
+    const int maxt = sm_count;
     for (int g0 = 1; g0 <= shp[0] && g0 <= maxt; g0++)
         for (int g1 = 1; g1 <= shp[1] && g0 * g1 <= maxt; g1++)
             for (int g2 = 1; g2 <= shp[2] && g0 * g1 * g2 <= maxt; g2++) {
@@ -228,39 +221,29 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
                 if (TS > 1024) continue;
                 long long HC = 0;
                 for (int m = 0; m < 3; m++) if (g[m] > 1) HC += TS / e[m];
-                const long long HCs = HC > 0 ? HC : 1;   // the kernel lays the ring out with stride hc_max >= 1
-                size_t smem = sizeof(c128) * (size_t)(2 * LS + MMH_KRING_HOST * HCs) + sizeof(int) * (size_t)(HCs + 16);
+                const long long HCs = HC > 0 ? HC : 1;   // X rows are laid out with stride hc_max >= 1
                 int R = 0;
-                const int Rs[3] = { 1, 2, 4 };
+                const int Rs[2] = { 1, 2 };
                 const char *eR = getenv("MMH_TILE_R");
-                const int ntl = g0 * g1 * g2;
-                const bool two_per_sm = ntl > sm_count;
-                for (int r = 0; r < 3; r++) {
-                    // two CTAs per SM: 2 x (256 + 64) threads x 96 registers
-                    const int tcmax = two_per_sm ? 256 : (Rs[r] == 4 ? 256 : 512);
+                for (int r = 0; r < 2; r++) {
+                    const int tcmax = 512;
                     if (eR && atoi(eR) != Rs[r]) continue;
-                    if (two_per_sm && Rs[r] == 4) continue;
-                    if ((long long)Rs[r] * tcmax >= TS && (Rs[r] == 1 || Rs[r] * npd <= (v1 ? 12 : 10))) { R = Rs[r]; break; }
+                    if ((long long)Rs[r] * tcmax >= TS && (Rs[r] == 1 || Rs[r] * npd <= 10)) { R = Rs[r]; break; }
                 }
                 if (!R) continue;
                 const int TC = round_up32((TS + R - 1) / R);
-                smem += sizeof(int) * 3 * (size_t)R * TC;   // export offsets
-                smem = (smem + 15) / 16 * 16;
-                const size_t sqtab_off = smem / 16;
-                smem += sizeof(c128) * (size_t)(S + 2);     // (sqrt, 1/sqrt) table + (b_i, A_ii)
-                if (!v1) {
-                    if (R == 4) continue;
-                    LS = TS + HC + 2;                       // compact box + halo faces + zero cell + trash cell
-                    smem = mmh_tiled2_smem((int)LS, (int)HCs, S, R * TC);
-                    if ((double)g0 * g1 * g2 * (double)S * (double)HCs >= 2147483648.0) continue;   // 32-bit export offsets
-                }
-                if (smem > (two_per_sm ? 100 : 200) * 1024) continue;
-                double step_us = (double)TS * 0.55e-3;          // issue time of one panel step of the tile
-                if (step_us < 0.15) step_us = 0.15;             // dependent-chain floor of one panel step
+                LS = TS + HC + 2;                           // compact box + halo faces + zero cell + trash cell
+                const size_t smem = mmh_tiled2_smem((int)LS, (int)HCs, S, R * TC);
+                if ((double)g0 * g1 * g2 * (double)S * (double)HCs >= 2147483648.0) continue;   // 32-bit export offsets
+                if (smem > 200 * 1024) continue;
+                // cost model (us): issue time of a step ~ points of the tile, floor = dependent chain of a step, plus the hops of
+                // the longest tile-pipeline path.  The constants are the ones the measured optimum of cfg2 follows from
+                // (stage 0: 5x5x5, stage 1: 3x3; a re-fit to the absolute step times picked 5x5 for stage 1 and lost 14 us).
+                double step_us = (double)TS * 0.55e-3;
+                if (step_us < 0.15) step_us = 0.15;
                 const double cost = (S - 1) * step_us + (g0 + g1 + g2 - 3) * 0.7;
                 if (cost < best) {
                     best = cost; bg[0] = g0; bg[1] = g1; bg[2] = g2; bR = R; bTC = TC; bLS = (int)LS; bHC = (int)HC;
-                    bSq = (int)sqtab_off;
                     *smem_out = smem;
                 }
             }
@@ -268,7 +251,7 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
     memset(tp, 0, sizeof(*tp));
     tp->d = d; tp->stage = stage; tp->nt = nt;
     for (int m = 0; m < 3; m++) tp->g[m] = bg[m];
-    tp->tc = bTC; tp->ls_max = bLS; tp->hc_max = bHC > 0 ? bHC : 1; tp->sqtab_off = bSq;
+    tp->tc = bTC; tp->ls_max = bLS; tp->hc_max = bHC > 0 ? bHC : 1;
     *R_out = bR;
     *ntiles_out = bg[0] * bg[1] * bg[2];
     return true;
@@ -283,7 +266,7 @@ static bool plan_march_tiled_cached(const LatticeDesc &d, int stage, int sm_coun
     static std::map<std::string, TiledPlan> cache;
     std::string key((const char *)d.shape, sizeof(int) * (size_t)d.D);
     key.push_back((char)stage); key.push_back((char)d.D); key.append(std::to_string(sm_count));
-    for (const char *name : { "MMH_TILE_G", "MMH_TILE_STAGE", "MMH_TILE_MAXT", "MMH_TILE_R", "MMH_TILED_V1" }) {
+    for (const char *name : { "MMH_TILE_G", "MMH_TILE_STAGE", "MMH_TILE_R" }) {
         const char *v = getenv(name);
         key.push_back('|');
         if (v) key.append(v);
@@ -336,7 +319,7 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
     bool pipelined = false;          // this lattice's first kernels are chained behind the previous lattice's (see kMaxInFlight)
     size_t xbase = 0;                // exchange-buffer slot of this lattice
     size_t xoff1 = 0;                // exchange-buffer offset (bytes) of stage i0 when it overlaps stage i1
-    if (use_pdl && i1 >= 0 && !tiled_v1() && !getenv("MMH_TRACE_FILE") && !getenv("MMH_NO_OVERLAP")) {
+    if (use_pdl && i1 >= 0 && !getenv("MMH_TRACE_FILE") && !getenv("MMH_NO_OVERLAP")) {
         int L_, R_, T_, n0 = 0, n1 = 0;
         size_t sm_;
         TiledParams t0, t1;
@@ -399,7 +382,7 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
         if (0) {
         } else if (plan_march_tiled_cached(d, i, ctx->sm_count, &tp, &R, &ntiles, &sm)) {
             tp.A = p.A; tp.b = p.b; tp.G = p.G; tp.sq = p.sq; tp.rsq = p.rsq; tp.timeline = (unsigned long long *)ctx->timeline.ptr + 64 * (seq % kMaxInFlight);
-            tp.pdl = (use_pdl && !first && R != 4) ? 1 : 0;
+            tp.pdl = (use_pdl && !first) ? 1 : 0;
             first = false;
             tp.poll0 = ((overlap && i == i0) || (overlap1 && i == i1)) ? 1 : 0;
             {   // exchange buffer: grow-only scratch, (re)filled with the sentinel whenever it is (re)allocated
@@ -411,21 +394,14 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
                 }
                 tp.X = (c128 *)((char *)ctx->xbuf.ptr + xoff);
             }
-            tp.cslot = 0;
-            if (R == 4) {   // only the R == 4 variant reads A_i. and b_i from constant memory
-                g_launches++;
-                CK(mmh_stage_constants(p.A, p.b, D, i, tp.cslot, st));
-            }
             const char *trace_file = getenv("MMH_TRACE_FILE");   // debug timeline of the tile pipeline
             const size_t trace_words = (size_t)ntiles * d.shape[i] * 8;
-            if (trace_file && tiled_v1()) trace_file = nullptr;
             if (trace_file) {
                 CK(cudaMalloc(&tp.trace, trace_words * 8));
                 CK(cudaMemset(tp.trace, 0, trace_words * 8));
             }
             g_launches++;
-            if (tiled_v1()) CK(mmh_launch_march_tiled(tp, R, ntiles, sm, st));
-            else CK(mmh_launch_march_tiled2(tp, R, ntiles, sm, st));
+            CK(mmh_launch_march_tiled2(tp, R, ntiles, sm, st));
             if (trace_file) {
                 std::vector<unsigned long long> h(trace_words);
                 CK(cudaStreamSynchronize(st));

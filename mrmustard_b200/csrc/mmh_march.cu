@@ -8,9 +8,10 @@
 //   * A_0j sqrt(k_j) comes from a per-lattice shared-memory table,
 //   * every amplitude is written to HBM exactly once (coalesced along the last mode) and never re-read.
 //
-// K2  k_fwd_batched_march : one CTA marches L small lattices in lock step (batched path, cfg3).
-// K1  k_fwd_tiled_march   : one lattice, every CTA owns a tile of the panel and exchanges one-cell halos
-//                           with its lower neighbours through L2 + release/acquire flags (cfg2, cfg5).
+// K2  k_march_stage : one CTA marches L small lattices in lock step (batched path, cfg3).
+//     k_fwd_chain   : stage D-1 (a 1-D chain), one thread per lattice.
+//     k_warp_tail   : the two trailing stages of ONE lattice by one warp.
+// K1  (one lattice over many tile-owner CTAs) lives in mmh_tiled.cu.
 #include <cstring>
 
 #include "mmh_params.cuh"
@@ -408,395 +409,4 @@ cudaError_t mmh_launch_chain(const FwdParams &p, cudaStream_t st) {
     if (smem > 40 * 1024) cudaFuncSetAttribute(k_fwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_fwd_chain<<<(unsigned)grid, block, smem, st>>>(p, tab);
     return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------------------------------
-// K1: tiled march of ONE lattice over many CTAs.
-//
-// The panel of stage i is cut into a grid of boxes over its first nt (<= 3) dims; CTA t owns box t for
-// the whole march.  A point k reads G[k - e_i - e_j] (j > i), i.e. the cell one lower in panel dim j of
-// panel s-1: either inside the box (shared memory, written by the CTA one step earlier) or in the one-
-// cell "low" halo that belongs to the lower neighbour box.  Dependencies only point to LOWER tiles, so
-// the exchange is a one-directional pipeline with no global barrier.
-//
-// Halo exchange without fences or flags: besides its lattice entry, a producer stores every amplitude
-// on a high face of its box into an exchange buffer X[consumer tile][panel][cell].  X is kept filled
-// with a sentinel (all-ones bit pattern, a NaN no FP64 instruction can produce); the consumer's halo
-// warps poll their cells with L1-bypassing loads until both 64-bit words of a cell differ from the
-// sentinel (64-bit stores are single-copy atomic, so every word validates itself), move the cell into a
-// 4-deep shared-memory ring, and write the sentinel back (self-cleaning).  One hop of the tile pipeline
-// therefore costs one L2 write + one L2 read instead of fence + flag + poll + fetch.
-// ---------------------------------------------------------------------------------------------------
-#define MMH_KRING 4
-#define MMH_NHW 2   // halo warps per CTA (panel u is served by warp u % MMH_NHW)
-
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-__device__ __forceinline__ void ld_relaxed_v2_u64(const void *p, unsigned long long &a, unsigned long long &b) {
-    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
-}
-__device__ __forceinline__ void st_relaxed_v2_u64(void *p, unsigned long long a, unsigned long long b) {
-    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
-}
-#define MMH_SENTINEL 0xFFFFFFFFFFFFFFFFull
-#ifndef MMH_XSTORE_MODE
-#define MMH_XSTORE_MODE 1
-#endif
-#if MMH_XSTORE_MODE == 0      // experiment: no export at all (results invalid)
-#define MMH_XSTORE(ptr, val) do { } while (0)
-#elif MMH_XSTORE_MODE == 1    // weak L2-only store; every 64-bit word is single-copy atomic and self-validating
-#define MMH_XSTORE(ptr, val) __stcg((ptr), (val))
-#else                         // strong relaxed store at gpu scope
-#define MMH_XSTORE(ptr, val) st_relaxed_v2_u64((ptr), (unsigned long long)__double_as_longlong((val).x), (unsigned long long)__double_as_longlong((val).y))
-#endif
-
-// A_i,i.. row and b_i of the lattice being marched, staged in constant memory (stream-ordered device->constant
-// copy before each tiled launch) so that they are immediate constant-bank operands of the DMULs, not registers.
-// One slot: launches of the tiled march on one device are serialised on a single stream.
-__constant__ c128 c_triple[9];      // [0] = A_ii, [1 + jj] = A_i,i+1+jj, [8] = b_i
-__device__ c128 g_triple_stage[9];  // global staging area
-
-__global__ void k_stage_constants(const c128 *A, const c128 *b, int D, int stage) {
-    const int t = threadIdx.x;
-    if (t < 8) g_triple_stage[t] = (stage + t < D) ? A[stage * D + stage + t] : make_double2(0.0, 0.0);
-    if (t == 8) g_triple_stage[8] = b[stage];
-}
-
-cudaError_t mmh_stage_constants(const c128 *A, const c128 *b, int D, int stage, int slot, cudaStream_t st) {
-    (void)slot;
-    k_stage_constants<<<1, 32, 0, st>>>(A, b, D, stage);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    void *src = nullptr;
-    e = cudaGetSymbolAddress(&src, g_triple_stage);
-    if (e != cudaSuccess) return e;
-    return cudaMemcpyToSymbolAsync(c_triple, src, sizeof(c128) * 9, 0, cudaMemcpyDeviceToDevice, st);
-}
-
-template <int R, int NPD>
-__global__ void __launch_bounds__((R >= 4 ? 256 : 512) + 32 * MMH_NHW, 1) k_march_tiled(TiledParams p) {
-    extern __shared__ c128 smem[];
-    const LatticeDesc &d = p.d;
-    const int D = d.D;
-    const int i = p.stage;
-    const long long P = d.strides[i];
-    const int S = d.shape[i];
-    const int TC = p.tc;
-    const int tid = threadIdx.x;
-    const int tidc = tid - 32 * MMH_NHW;
-    const int nt = p.nt;
-    const double *__restrict__ sq = p.sq;
-    const double *__restrict__ rsq = p.rsq;
-
-    pdl_launch_dependents();
-    // ---- tile geometry ----------------------------------------------------------------------------------
-    int g[3], t[3], lo[3], e[3], h[3], gst[3], shp[3];
-#pragma unroll
-    for (int m = 0; m < 3; m++) g[m] = m < nt ? p.g[m] : 1;
-    const int tile = blockIdx.x;
-    t[2] = tile % g[2];
-    t[1] = (tile / g[2]) % g[1];
-    t[0] = tile / (g[1] * g[2]);
-#pragma unroll
-    for (int m = 0; m < 3; m++) {
-        if (m < nt) {
-            shp[m] = d.shape[i + 1 + m];
-            lo[m] = (int)(((long long)t[m] * shp[m]) / g[m]);
-            e[m] = (int)(((long long)(t[m] + 1) * shp[m]) / g[m]) - lo[m];
-            h[m] = lo[m] > 0 ? 1 : 0;
-            gst[m] = (int)d.strides[i + 1 + m];
-        } else { shp[m] = 1; lo[m] = 0; e[m] = 1; h[m] = 0; gst[m] = 0; }
-    }
-    const int inner = (int)d.strides[i + nt];
-    int lst[3];
-    lst[2] = inner;
-    lst[1] = lst[2] * (e[2] + h[2]);
-    lst[0] = lst[1] * (e[1] + h[1]);
-    const int TS = e[0] * e[1] * e[2] * inner;
-    int faceoff[3];
-    faceoff[0] = 0;
-    faceoff[1] = faceoff[0] + h[0] * (TS / e[0]);
-    faceoff[2] = faceoff[1] + h[1] * (TS / e[1]);
-    const int HC = faceoff[2] + h[2] * (TS / e[2]);
-
-    c128 *buf = smem;                         // [2][ls_max]
-    c128 *ring = smem + 2 * (size_t)p.ls_max; // [KRING][hc_max]
-    int *hal_gofs = (int *)(ring + MMH_KRING * (size_t)p.hc_max);
-    int *sync_words = hal_gofs + p.hc_max;    // [0..KRING) = panel held by ring slot k ; [KRING] = cdone
-    int *xo_s = sync_words + 8;               // [3][R * TC] export offsets (consumer tile block + cell)
-    double2 *sqtab = (double2 *)(smem + p.sqtab_off);   // [S] (sqrt(s), 1/sqrt(s))
-    const int ringstride = p.hc_max;
-    const size_t xtile = (size_t)S * p.hc_max;   // X elements per consumer tile
-
-    // ---- halo cell table: global panel offset of every halo cell (panel 0 is read from G itself) ---------------
-    for (int c = tid; c < HC; c += blockDim.x) {
-        int m = 0;
-        if (c >= faceoff[2] && h[2]) m = 2;
-        else if (c >= faceoff[1] && h[1]) m = 1;
-        int cc = c - faceoff[m];
-        const int a = m == 0 ? 1 : 0, b = m == 2 ? 1 : 2;  // the two other tiled dims, in order
-        const int rr = cc % inner; cc /= inner;
-        const int xb = cc % e[b], xa = cc / e[b];
-        hal_gofs[c] = (lo[m] - 1) * gst[m] + (lo[a] + xa) * gst[a] + (lo[b] + xb) * gst[b] + rr;
-    }
-    if (tid <= MMH_KRING) sync_words[tid] = 0;
-    for (int s_ = tid; s_ < S; s_ += blockDim.x) sqtab[s_] = make_double2(sq[s_], rsq[s_]);
-    __syncthreads();
-    pdl_wait();   // everything above overlapped the previous stage's kernel; panel 0 and X are touched from here on
-    // panel 0 halo -> ring slot 0 (panel 0 is final: the previous stage's kernel has completed)
-    for (int c = tid; c < HC; c += blockDim.x) ring[c] = __ldcg(p.G + hal_gofs[c]);
-
-    // uniform operands straight from the constant bank: crow[0] = A_ii, crow[1 + jj] = A_i,i+1+jj, crow[8] = b_i
-    // (b_i, A_ii): R == 4 takes them (and A_ij) from the constant bank staged by mmh_stage_constants; R <= 2 keeps the
-    // coefficients in registers and re-reads (b_i, A_ii) from shared memory, so no constant staging launch is needed.
-    c128 *sba2 = (c128 *)(sqtab + S);
-    if (tid == 0) { sba2[0] = p.b[i]; sba2[1] = p.A[i * D + i]; }
-#define crow (p.A + i * D + i)
-#define b0 (COEF_REG ? sba2[0] : c_triple[8])
-#define a00 (COEF_REG ? sba2[1] : c_triple[0])
-
-    // ---- per-slot constants (compute warps) -----------------------------------------------------------------
-    bool act[R];
-    unsigned hm[R];             // bit jj: neighbour jj lives in the halo ring
-    int loc[R];
-    int nbi[R][NPD];
-    unsigned xm[R];             // bit m: the slot is on the high face of tiled dim m (its amplitude is exported);
-                                // the offset inside the upper neighbour's exchange block is kept in shared memory
-    // coefficient A_ij sqrt(k_j) of every neighbour: R <= 2 keeps the complex product in registers; R == 4 keeps only
-    // sqrt(k_j) (0 when the neighbour does not exist) and multiplies by A_ij from the constant bank each step
-    constexpr bool COEF_REG = R <= 2;
-    c128 coef[COEF_REG ? R : 1][NPD];
-    double sqk[COEF_REG ? 1 : R][NPD];
-    int gofs[R];                // panel offset f of the slot: G index = s * P + f
-    c128 h0[R], h1[R];
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        const int q = r * TC + tidc;
-        act[r] = tidc >= 0 && q < TS;
-        hm[r] = 0u;
-        const int qq = act[r] ? q : 0;
-        const int rr = qq % inner;
-        int q1 = qq / inner;
-        int x[3];
-        x[2] = q1 % e[2]; q1 /= e[2];
-        x[1] = q1 % e[1];
-        x[0] = q1 / e[1];
-        loc[r] = (x[0] + h[0]) * lst[0] + (x[1] + h[1]) * lst[1] + (x[2] + h[2]) * lst[2] + rr;
-        const int f = (lo[0] + x[0]) * gst[0] + (lo[1] + x[1]) * gst[1] + (lo[2] + x[2]) * gst[2] + rr;
-        gofs[r] = f;
-        int rem = rr;
-#pragma unroll
-        for (int jj = 0; jj < NPD; jj++) {
-            const int j = i + 1 + jj;
-            int k, nb;
-            bool halo = false;
-            if (jj < nt) {
-                k = lo[jj] + x[jj];
-                if (x[jj] > 0) nb = loc[r] - lst[jj];
-                else {  // lower neighbour is a halo cell (or does not exist when k == 0)
-                    halo = true;
-                    const int a = jj == 0 ? 1 : 0, b = jj == 2 ? 1 : 2;
-                    nb = faceoff[jj] + (x[a] * e[b] + x[b]) * inner + rr;
-                }
-            } else {
-                const int sj = (int)d.strides[j];
-                k = rem / sj;
-                rem -= k * sj;
-                nb = loc[r] - sj;
-            }
-            const bool has = act[r] && k > 0;
-            if (!has) { nb = loc[r]; halo = false; }
-            nbi[r][jj] = nb;
-            if (halo) hm[r] |= 1u << jj;
-            if constexpr (COEF_REG) coef[r][jj] = has ? c_scale(crow[1 + jj], sq[k]) : c_make(0.0, 0.0);
-            else sqk[r][jj] = has ? sq[k] : 0.0;
-        }
-        // high faces: where does the upper neighbour in dim m expect this amplitude?
-        xm[r] = 0u;
-#pragma unroll
-        for (int m = 0; m < 3; m++) {
-            if (act[r] && m < nt && t[m] + 1 < g[m] && x[m] == e[m] - 1) {
-                // the consumer box: same extents except in dim m
-                const int lo_up = (int)(((long long)(t[m] + 1) * shp[m]) / g[m]);
-                const int e_up = (int)(((long long)(t[m] + 2) * shp[m]) / g[m]) - lo_up;
-                int ec[3] = { e[0], e[1], e[2] }, hc[3] = { h[0], h[1], h[2] };
-                ec[m] = e_up; hc[m] = 1;
-                const int TSc = ec[0] * ec[1] * ec[2] * inner;
-                int fo = 0;
-                for (int mm = 0; mm < m; mm++) fo += hc[mm] * (TSc / ec[mm]);
-                const int a = m == 0 ? 1 : 0, b = m == 2 ? 1 : 2;
-                xm[r] |= 1u << m;
-                const int up = tile + (m == 0 ? g[1] * g[2] : (m == 1 ? g[2] : 1));   // the consumer tile
-                xo_s[m * (R * TC) + q] = (int)(up * xtile) + fo + (x[a] * ec[b] + x[b]) * inner + rr;
-            }
-        }
-        h0[r] = c_make(0.0, 0.0);
-        h1[r] = act[r] ? __ldcg(p.G + gofs[r]) : c_make(0.0, 0.0);
-        if (act[r]) buf[loc[r]] = h1[r];
-    }
-    __syncthreads();
-
-    if (tid < 32 * MMH_NHW) {
-        // ================= halo warps: panel u is served by warp u % NHW =================
-        if (HC == 0) return;
-        const int lane = tid & 31, hw = tid >> 5;
-        c128 *xin = p.X + (size_t)tile * xtile;
-#pragma unroll 1
-        for (int u = 1 + hw; u <= S - 2; u += MMH_NHW) {
-            if (u - MMH_KRING + 1 >= 1) {   // ring slot of panel u-KRING must have been consumed
-                if (lane == 0) while (ld_acquire_cta_shared(&sync_words[MMH_KRING]) < u - MMH_KRING + 1) { }
-                __syncwarp();
-            }
-            c128 *dst = ring + (size_t)(u % MMH_KRING) * ringstride;
-            c128 *src = xin + (size_t)u * p.hc_max;
-            // canary: the exports of one producer step land within one L2 write latency of each other, so first
-            // watch a single cell per face with back-off instead of hammering L2 with the whole face
-            if (lane < 3 && h[lane]) {
-                const int cc = faceoff[lane];
-                unsigned long long a_, b_;
-                unsigned spins = 0;
-                ld_relaxed_v2_u64(src + cc, a_, b_);
-#pragma unroll 1
-                while ((a_ == MMH_SENTINEL || b_ == MMH_SENTINEL) && ++spins < (1u << 24)) {
-                    __nanosleep(64);
-                    ld_relaxed_v2_u64(src + cc, a_, b_);
-                }
-            }
-            __syncwarp();
-#pragma unroll 1
-            for (int c0 = lane; c0 < HC; c0 += 32 * 4) {
-                unsigned long long a[4], b[4];
-                bool need[4];
-#pragma unroll
-                for (int w = 0; w < 4; w++) {
-                    const int c = c0 + 32 * w;
-                    need[w] = c < HC;
-                    if (need[w]) ld_relaxed_v2_u64(src + c, a[w], b[w]);
-                }
-#pragma unroll
-                for (int w = 0; w < 4; w++) {
-                    const int c = c0 + 32 * w;
-                    if (!need[w]) continue;
-                    unsigned spins = 0;
-#pragma unroll 1
-                    while ((a[w] == MMH_SENTINEL || b[w] == MMH_SENTINEL) && ++spins < (1u << 24)) {
-                        __nanosleep(32);
-                        ld_relaxed_v2_u64(src + c, a[w], b[w]);
-                    }
-                    dst[c] = make_double2(__longlong_as_double((long long)a[w]), __longlong_as_double((long long)b[w]));
-                    st_relaxed_v2_u64(src + c, MMH_SENTINEL, MMH_SENTINEL);   // self-cleaning
-                }
-            }
-            __syncwarp();
-            if (lane == 0) st_release_cta_shared(&sync_words[u % MMH_KRING], u);
-            if (p.trace && lane == 0) p.trace[((size_t)tile * S + u) * 4 + 3] = globaltimer_ns();
-        }
-        return;
-    }
-
-    // ================= compute warps =================
-#define MMH_TILED_STEP(P1, P2, OFFP, OFFC, OFFH, SCUR)                                                \
-    {                                                                                                 \
-        const double2 st_ = sqtab[(SCUR)];                                                            \
-        const double sqs = st_.x, rsqs = st_.y;                                                       \
-        c128 v[R];                                                                                    \
-        _Pragma("unroll") for (int r = 0; r < R; r++) {                                               \
-            v[r] = c_mul(b0, P1[r]);                                                                  \
-            v[r] = c_add(v[r], c_mul(c_scale(a00, sqm), P2[r]));                                      \
-            _Pragma("unroll") for (int jj = 0; jj < NPD; jj++) {                                      \
-                const c128 *src = ((hm[r] >> jj) & 1u) ? ring + (OFFH) : buf + (OFFP);                \
-                const c128 cf = COEF_REG ? coef[COEF_REG ? r : 0][jj]                                 \
-                                         : c_scale(c_triple[1 + jj], sqk[COEF_REG ? 0 : r][jj]);          \
-                v[r] = c_add(v[r], c_mul(cf, src[nbi[r][jj]]));                                       \
-            }                                                                                         \
-        }                                                                                             \
-        div_all_inplace<R>(v, sqs, rsqs);                                                             \
-        sqm = sqs;                                                                                    \
-        const bool xch = (SCUR) <= S - 2;   /* the last panel has no consumer */                      \
-        c128 *gpan = p.G + (long long)(SCUR) * P;                                                     \
-        c128 *xpan = p.X + (size_t)(SCUR) * p.hc_max;                                                 \
-        _Pragma("unroll") for (int r = 0; r < R; r++) {                                               \
-            P2[r] = v[r];                                                                             \
-            if (act[r]) {                                                                             \
-                gpan[gofs[r]] = v[r];                                                                 \
-                buf[(OFFC) + loc[r]] = v[r];                                                          \
-                _Pragma("unroll") for (int m = 0; m < 3; m++)                                         \
-                    if (xch && ((xm[r] >> m) & 1u))                                                   \
-                        MMH_XSTORE(xpan + xo_s[m * (R * TC) + r * TC + tidc], v[r]);                  \
-            }                                                                                         \
-        }                                                                                             \
-    }
-#define MMH_TILED_SYNC(SDONE)                                                                         \
-    {                                                                                                 \
-        if (p.trace && tidc == 0) p.trace[((size_t)tile * S + (SDONE)) * 4 + 2] = globaltimer_ns();   \
-        named_barrier_sync(1, TC);                                                                    \
-        if (tidc == 0) {                                                                              \
-            if (p.trace) p.trace[((size_t)tile * S + (SDONE)) * 4 + 1] = globaltimer_ns();            \
-            st_release_cta_shared(&sync_words[MMH_KRING], (SDONE));                                   \
-        }                                                                                             \
-    }
-#define MMH_TILED_WAIT(SNEED)                                                                         \
-    if (HC > 0 && (SNEED) >= 1) {                                                                     \
-        unsigned spins = 0;                                                                           \
-        while (ld_acquire_cta_shared(&sync_words[(SNEED) % MMH_KRING]) < (SNEED) && ++spins < (1u << 28)) { } \
-    }                                                                                                 \
-    if (p.trace && tidc == 0) p.trace[((size_t)tile * S + (SNEED) + 1) * 4 + 0] = globaltimer_ns();
-
-    double sqm = 0.0;
-    const int LSm = p.ls_max;
-    int s = 1;
-    for (; s + 1 < S; s += 2) {
-        MMH_TILED_WAIT(s - 1)
-        MMH_TILED_STEP(h1, h0, 0, LSm, ((s - 1) % MMH_KRING) * ringstride, s)
-        MMH_TILED_SYNC(s)
-        MMH_TILED_WAIT(s)
-        MMH_TILED_STEP(h0, h1, LSm, 0, (s % MMH_KRING) * ringstride, s + 1)
-        MMH_TILED_SYNC(s + 1)
-    }
-    if (s < S) {
-        MMH_TILED_WAIT(s - 1)
-        MMH_TILED_STEP(h1, h0, 0, LSm, ((s - 1) % MMH_KRING) * ringstride, s)
-        MMH_TILED_SYNC(s)
-    }
-#undef MMH_TILED_STEP
-#undef MMH_TILED_SYNC
-#undef MMH_TILED_WAIT
-#undef crow
-#undef b0
-#undef a00
-}
-
-template <int R>
-static cudaError_t launch_tiled_R(const TiledParams &p, int ntiles, size_t smem, cudaStream_t st) {
-    const int block = p.tc + 32 * MMH_NHW;
-#define MMH_CASE(N)                                                                                   \
-    case N:                                                                                           \
-        if (smem > 48 * 1024)                                                                         \
-            cudaFuncSetAttribute(k_march_tiled<R, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        return launch_pdl(k_march_tiled<R, N>, ntiles, block, smem, st, p.pdl != 0, p);
-    const int npd = p.d.D - 1 - p.stage;
-    switch (npd) {
-        MMH_CASE(1) MMH_CASE(2) MMH_CASE(3)
-        default: break;
-    }
-    if constexpr (R <= 2) {
-        switch (npd) { MMH_CASE(4) MMH_CASE(5) MMH_CASE(6) default: break; }
-    }
-    if constexpr (R == 1) {
-        switch (npd) { MMH_CASE(7) default: break; }
-    }
-#undef MMH_CASE
-    return cudaErrorInvalidValue;
-}
-
-cudaError_t mmh_launch_march_tiled(const TiledParams &p, int R, int ntiles, size_t smem, cudaStream_t st) {
-    switch (R) {
-        case 1: return launch_tiled_R<1>(p, ntiles, smem, st);
-        case 2: return launch_tiled_R<2>(p, ntiles, smem, st);
-        case 4: return launch_tiled_R<4>(p, ntiles, smem, st);
-        default: return cudaErrorInvalidValue;
-    }
 }

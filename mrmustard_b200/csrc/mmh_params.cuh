@@ -57,8 +57,6 @@ struct StageParams {
 
 struct TiledParams {
     LatticeDesc d;
-    int cslot;                   // reserved
-    int sqtab_off;               // offset (c128 units) of the (sqrt, 1/sqrt) table in shared memory
     const c128 *A, *b;           // one triple (device)
     c128 *G;                     // one lattice
     const double *sq, *rsq;
@@ -76,8 +74,6 @@ struct TiledParams {
     unsigned long long *timeline;   // per-launch debug stamps (mmh_common.cuh timeline_stamp), may be NULL
 };
 
-cudaError_t mmh_stage_constants(const c128 *A, const c128 *b, int D, int stage, int slot, cudaStream_t st);
-cudaError_t mmh_launch_march_tiled(const TiledParams &p, int R, int ntiles, size_t smem, cudaStream_t st);
 cudaError_t mmh_launch_march_tiled2(const TiledParams &p, int R, int ntiles, size_t smem, cudaStream_t st);
 size_t mmh_tiled2_smem(int ls_max, int hc_max, int S, int slots);
 cudaError_t mmh_launch_march_stage(const StageParams &p, int R, int grid, int block, size_t smem, cudaStream_t st);

@@ -65,11 +65,26 @@ __device__ __forceinline__ c128 lds_c128(unsigned addr) {
 __device__ __forceinline__ void sts_c128(unsigned addr, c128 v) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
 }
+// mbarrier (shared memory, CTA scope): split arrive / wait, so that the work after a thread's last shared-memory store of a
+// step (lattice store, exports, the register part of the next step) overlaps the wait for the slowest warp and for the halo
+__device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned addr) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
 // named barriers: hardware-blocked waits (a waiting warp takes no issue slots, unlike a spin on a shared-memory flag)
 __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-#define MMH_T2_BAR_STEP 1    // compute warps only (tiles without a halo)
-#define MMH_T2_BAR_FULL 2    // + k: panel buffer k holds the halo of its panel   (halo warp k arrives, compute warps sync)
+// (the step hand-off -- every compute thread has written panel s and the halo of panel s has arrived -- is an mbarrier per
+//  panel buffer: count = compute threads + 1 arrival of the buffer's halo warp)
 #define MMH_T2_BAR_HALO 10   // halo warps among themselves
 #define MMH_T2_BAR_FREE 6    // + k: panel buffer k has been read by every compute warp (compute warps arrive, halo warp k syncs)
 
@@ -154,7 +169,7 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
     const unsigned xo_base = sync_base + 32u;     // export offsets (c128 units inside X's panel row), [m][R * TC]
 
     // ---- tables that do not touch the lattice (overlap the previous stage's kernel under PDL) ---------------
-    if (tid < 8) ((int *)(sba + 2))[tid] = 0;
+    if (tid < NB) mbar_init(sync_base + 8u * (unsigned)tid, (unsigned)TC + (HC > 0 ? 1u : 0u));
     for (int s_ = tid; s_ < S; s_ += blockDim.x) sqtab[s_] = make_double2(p.sq[s_], p.rsq[s_]);
     if (tid < NB) { smem[(size_t)tid * p.ls_max + p.ls_max - 2] = c_make(0.0, 0.0); smem[(size_t)tid * p.ls_max + p.ls_max - 1] = c_make(0.0, 0.0); }
     if (tid == 0) { sba[0] = p.b[i]; sba[1] = p.A[i * D + i]; }
@@ -315,8 +330,8 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
                 }
             }
             if (p.trace && lane == 0) p.trace[((size_t)tile * S + u) * 8 + 4] = gtimer_ns();
-            __threadfence_block();   // (no global store of this warp is in flight here: the fence only orders the STS)
-            bar_arrive(MMH_T2_BAR_FULL + hw, TC + 32);
+            __syncwarp();            // the lanes' shared-memory stores are ordered before lane 0's (release) arrive
+            if (lane == 0) mbar_arrive(sync_base + 8u * (unsigned)hw);
             if (p.trace && lane == 0) p.trace[((size_t)tile * S + u) * 8 + 3] = gtimer_ns();
             // self-cleaning, off the critical path: put the sentinel back for the next launch
             for (int c = lane; c < HC; c += 32) stg_relaxed_v2(src + c, MMH_SENTINEL, MMH_SENTINEL);
@@ -357,10 +372,11 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
         div_all2<R>(v, st_.x, st_.y);                                                                 \
         if (p.trace && tidc == 0) p.trace[((size_t)tile * S + s_) * 8 + 7] = gtimer_ns() + 0 * (unsigned long long)__double_as_longlong(v[0].x + v[R - 1].y); \
         const bool xch = s_ <= S - 2;   /* the last panel has no consumer */                          \
+        _Pragma("unroll") for (int r = 0; r < R; r++) sts_c128(bcur + loco[r], v[r]);                 \
+        if (xch) mbar_arrive(sync_base + 8u * (unsigned)(s_ & (NB - 1)));   /* my part of panel s is in shared memory */ \
         _Pragma("unroll") for (int r = 0; r < R; r++) {                                               \
             P2[r] = v[r];                                                                             \
             if (flags[r] & 1u) gpan[gofs[r]] = v[r];                                                  \
-            sts_c128(bcur + loco[r], v[r]);                                                           \
             if (xch) {                                                                                \
                 _Pragma("unroll") for (int m = 0; m < 3; m++)                                         \
                     if (m < NPD && (flags[r] & (2u << m))) {                                          \
@@ -374,10 +390,8 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
         gpan += P; xpan += p.hc_max; sqm = st_.x;                                                     \
         if (p.trace && tidc == 0) p.trace[((size_t)tile * S + s_) * 8 + 2] = gtimer_ns();             \
         /* hand-off to step s+1: every compute warp has written panel s, and the halo of panel s has arrived */ \
-        if (have_halo) {                                                                              \
-            if (s_ + 3 <= S - 2) bar_arrive(MMH_T2_BAR_FREE + ((s_ - 1) & (NB - 1)), TC + 32);        \
-            if (s_ <= S - 2) bar_sync(MMH_T2_BAR_FULL + (s_ & (NB - 1)), TC + 32);                    \
-        } else if (s_ <= S - 2) bar_sync(MMH_T2_BAR_STEP, TC);                                        \
+        if (have_halo && s_ + 3 <= S - 2) bar_arrive(MMH_T2_BAR_FREE + ((s_ - 1) & (NB - 1)), TC + 32); \
+        if (xch) mbar_wait(sync_base + 8u * (unsigned)(s_ & (NB - 1)), (unsigned)((s_ - 1) >> 2) & 1u); \
         if (p.trace && tidc == 0) p.trace[((size_t)tile * S + s_) * 8 + 1] = gtimer_ns();             \
     }
 

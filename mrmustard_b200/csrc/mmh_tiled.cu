@@ -372,19 +372,21 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
         div_all2<R>(v, st_.x, st_.y);                                                                 \
         if (p.trace && tidc == 0) p.trace[((size_t)tile * S + s_) * 8 + 7] = gtimer_ns() + 0 * (unsigned long long)__double_as_longlong(v[0].x + v[R - 1].y); \
         const bool xch = s_ <= S - 2;   /* the last panel has no consumer */                          \
-        _Pragma("unroll") for (int r = 0; r < R; r++) sts_c128(bcur + loco[r], v[r]);                 \
-        if (xch) mbar_arrive(sync_base + 8u * (unsigned)(s_ & (NB - 1)));   /* my part of panel s is in shared memory */ \
-        _Pragma("unroll") for (int r = 0; r < R; r++) {                                               \
-            P2[r] = v[r];                                                                             \
-            if (flags[r] & 1u) gpan[gofs[r]] = v[r];                                                  \
-            if (xch) {                                                                                \
+        /* order: exports (the neighbours' critical path), shared-memory copy + arrive, then everything nobody waits for */ \
+        if (xch) {                                                                                    \
+            _Pragma("unroll") for (int r = 0; r < R; r++)                                             \
                 _Pragma("unroll") for (int m = 0; m < 3; m++)                                         \
                     if (m < NPD && (flags[r] & (2u << m))) {                                          \
                         unsigned xo_;                                                                 \
                         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(xo_) : "r"(xo_base + 4u * (unsigned)(m * R * TC + r * TC + tidc)) : "memory"); \
                         __stcg(xpan + xo_, v[r]);                                                     \
                     }                                                                                 \
-            }                                                                                         \
+        }                                                                                             \
+        _Pragma("unroll") for (int r = 0; r < R; r++) sts_c128(bcur + loco[r], v[r]);                 \
+        if (xch) mbar_arrive(sync_base + 8u * (unsigned)(s_ & (NB - 1)));   /* my part of panel s is in shared memory */ \
+        _Pragma("unroll") for (int r = 0; r < R; r++) {                                               \
+            P2[r] = v[r];                                                                             \
+            if (flags[r] & 1u) gpan[gofs[r]] = v[r];                                                  \
             if (MMH_T2_PRE_EARLY) pre[r] = c_add(c_mul(b0, v[r]), c_mul(a00s, P1[r]));                \
         }                                                                                             \
         gpan += P; xpan += p.hc_max; sqm = st_.x;                                                     \

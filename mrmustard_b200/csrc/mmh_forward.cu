@@ -158,6 +158,38 @@ __global__ void __launch_bounds__(256) k_stable_coop(FwdParams p) {
     for (int i = 0; i < D; i++) maxlevel += d.shape[i] - 1;
     int k[MMH_MAX_DIM];
     unsigned epoch = 0;
+    // A thread owns the same prefixes (k_0..k_{D-2}) on every level, so when it owns at most kOwn of them they are decoded
+    // once (the 64-bit divisions of the decode cost more than the update itself) and a level only derives k_{D-1} = n - sum.
+    constexpr int kOwn = 4;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    if (D <= 8 && Q <= kOwn * nthreads) {
+        int kk[kOwn][8], ksum[kOwn];
+        long long kbase[kOwn];
+        int nown = 0;
+        for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < Q && nown < kOwn; q += nthreads, nown++) {
+            long long rem = q * last;
+            int sum = 0;
+            for (int j = 0; j < D - 1; j++) {
+                kk[nown][j] = (int)(rem / d.strides[j]);
+                rem -= (long long)kk[nown][j] * d.strides[j];
+                sum += kk[nown][j];
+            }
+            ksum[nown] = sum;
+            kbase[nown] = q * last;
+        }
+        for (int n = 1; n <= maxlevel; n++) {
+            grid_barrier(p.barrier, epoch);
+            for (int o = 0; o < nown; o++) {
+                const int kl = n - ksum[o];
+                if (kl < 0 || kl >= last) continue;
+                for (int j = 0; j < D - 1; j++) k[j] = kk[o][j];
+                k[D - 1] = kl;
+                const long long flat = kbase[o] + kl;
+                G[flat] = stable_point(d, sA, sb, G, p.sq, k, flat);
+            }
+        }
+        return;
+    }
     for (int n = 1; n <= maxlevel; n++) {
         grid_barrier(p.barrier, epoch);
         for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < Q;

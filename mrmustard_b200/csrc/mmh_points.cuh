@@ -41,8 +41,46 @@ __device__ __forceinline__ c128 vanilla_point32(const LatticeDesc &d, const c128
     return c_div_table(val, sq[s], rsq[s]);
 }
 
-// stable point (core.py:183-211): average of the update over every pivot i with k_i > 0
-static __device__ c128 stable_point(const LatticeDesc &d, const c128 *sA, const c128 *sb,
+// stable point (core.py:183-211): average of the update over every pivot i with k_i > 0.
+// All neighbour amplitudes (k - e_i, and k - e_i - e_j once per unordered pair) are fetched FIRST, in one batch of
+// independent loads, and the arithmetic then runs on registers in the reference's order: fetched one by one inside the sum
+// they are D(D+1) dependent-looking L2 round trips per point (the level wavefront is L2-latency bound).
+template <int DMAX>
+static __device__ __forceinline__ c128 stable_point_batched(const LatticeDesc &d, const c128 *sA, const c128 *sb,
+                                                            const c128 *G, const double *__restrict__ sq, const int *k,
+                                                            long long flat) {
+    const int D = d.D;
+    c128 p1[DMAX], p2[DMAX][DMAX];   // p1[i] = G[k - e_i], p2[i][j] (i <= j) = G[k - e_i - e_j]
+#pragma unroll
+    for (int i = 0; i < DMAX; i++) {
+        if (i < D && k[i] > 0) p1[i] = __ldcg(G + (flat - d.strides[i]));
+        else p1[i] = c_make(0.0, 0.0);
+#pragma unroll
+        for (int j = i; j < DMAX; j++) {
+            const bool need = i < D && j < D && k[i] > 0 && (i == j ? k[i] > 1 : k[j] > 0);
+            if (need) p2[i][j] = __ldcg(G + (flat - d.strides[i] - d.strides[j]));
+            else p2[i][j] = c_make(0.0, 0.0);
+        }
+    }
+    c128 vals = c_make(0.0, 0.0);
+    int np = 0;
+#pragma unroll
+    for (int i = 0; i < DMAX; i++) {
+        if (i >= D || k[i] == 0) continue;
+        np++;
+        c128 val = c_mul(sb[i], p1[i]);
+#pragma unroll
+        for (int j = 0; j < DMAX; j++) {
+            if (j >= D) continue;
+            if (j == i) { if (k[i] > 1) val = c_add(val, c_mul(c_scale(sA[i * D + i], sq[k[i] - 1]), p2[i][i])); }
+            else if (k[j] > 0) val = c_add(val, c_mul(c_scale(sA[i * D + j], sq[k[j]]), j < i ? p2[j][i] : p2[i][j]));
+        }
+        vals = c_add(vals, c_div_real(val, sq[k[i]]));
+    }
+    return c_div_real(vals, (double)np);
+}
+
+static __device__ c128 stable_point_generic(const LatticeDesc &d, const c128 *sA, const c128 *sb,
                              const c128 *G, const double *__restrict__ sq, const int *k,
                              long long flat) {
     const int D = d.D;
@@ -61,5 +99,13 @@ static __device__ c128 stable_point(const LatticeDesc &d, const c128 *sA, const 
         vals = c_add(vals, c_div_real(val, sq[k[i]]));
     }
     return c_div_real(vals, (double)np);
+}
+
+static __device__ c128 stable_point(const LatticeDesc &d, const c128 *sA, const c128 *sb,
+                             const c128 *G, const double *__restrict__ sq, const int *k,
+                             long long flat) {
+    if (d.D <= 2) return stable_point_batched<2>(d, sA, sb, G, sq, k, flat);
+    if (d.D <= 4) return stable_point_batched<4>(d, sA, sb, G, sq, k, flat);
+    return stable_point_generic(d, sA, sb, G, sq, k, flat);
 }
 

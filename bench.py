@@ -429,6 +429,20 @@ def extras(torch, dev, lib, check, _lib, stream, sptr, flush):
         ms = timeit(lambda: check(lib.mmh_forward_batched(Bq, 4, sh, dA.data_ptr(), db.data_ptr(), dc.data_ptr(), dG.data_ptr(), 0, sptr)), 5, True)
         out["cfg2_batch8_forward"] = {"amps_per_s": Bq * n / (ms * 1e-3), "ms": ms, "hbm_frac": 16.0 * Bq * n / (ms * 1e-3) / 1e9 / peak}
         del dG
+        # lattice + derived-variable contraction, end to end through the numpy-facing call (host buffers):
+        # fused (only the contracted array is copied back) vs materialising the lattice on the host and einsum there
+        import mrmustard_b200 as mm
+        A4, b4, _ = random_triple(4, (), seed=21)
+        core, der = (48, 48), (8, 40)
+        cpoly = np.random.RandomState(3).standard_normal(der) + 0j
+        def wall(fn, reps=3):
+            fn(); best = 1e30
+            for _ in range(reps):
+                t0 = time.perf_counter(); fn(); best = min(best, time.perf_counter() - t0)
+            return best * 1e3
+        ms_f = wall(lambda: mm.hermite_renormalized_contracted(A4, b4, cpoly, core))
+        ms_m = wall(lambda: np.einsum("abk,k->ab", mm.strategies.vanilla_numba(core + der, A4, b4, 1.0).reshape(core + (-1,)), cpoly.reshape(-1)))
+        out["contract_48x48_x_8x40"] = {"fused_ms": ms_f, "materialised_ms": ms_m, "lattice_amplitudes": int(np.prod(core + der))}
         # cfg1: latency config
         A, b, c = gold["cfg1_A"], gold["cfg1_b"], gold["cfg1_c"].reshape(1)
         dA, db, dc = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (A, b, c))

@@ -17,7 +17,8 @@ _STRATEGY_NAMES = ["vanilla_numba", "stable_numba", "vanilla_batch_numba", "vani
 
 
 def install() -> None:
-    import mrmustard.math.lattice.strategies as ref_strategies
+    # (`import mrmustard.math.lattice.strategies as x` fails: `mrmustard.math` is the BackendManager instance, math/__init__.py:34)
+    from mrmustard.math.lattice import strategies as ref_strategies
     from mrmustard.math.backend_numpy import BackendNumpy
 
     if _saved:
@@ -42,7 +43,8 @@ def install() -> None:
 
 
 def uninstall() -> None:
-    import mrmustard.math.lattice.strategies as ref_strategies
+    # (`import mrmustard.math.lattice.strategies as x` fails: `mrmustard.math` is the BackendManager instance, math/__init__.py:34)
+    from mrmustard.math.lattice import strategies as ref_strategies
     from mrmustard.math.backend_numpy import BackendNumpy
 
     for (kind, name), fn in _saved.items():

@@ -22,10 +22,13 @@ class _Settings:
 settings = _Settings()
 
 
+_installed = False   # set by dropin.install() / uninstall()
+
+
 def _reference_settings():
-    """Use the live mrmustard settings object when the drop-in is installed, else ours."""
+    """The live mrmustard settings object while the drop-in is installed into a reference process, else ours."""
     import sys
-    mm = sys.modules.get("mrmustard")
+    mm = sys.modules.get("mrmustard") if _installed else None
     return getattr(mm, "settings", settings) if mm is not None else settings
 
 

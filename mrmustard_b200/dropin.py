@@ -40,6 +40,7 @@ def install() -> None:
     }.items():
         _saved[("b", name)] = getattr(BackendNumpy, name)
         setattr(BackendNumpy, name, fn)
+    backend._installed = True
 
 
 def uninstall() -> None:
@@ -50,3 +51,4 @@ def uninstall() -> None:
     for (kind, name), fn in _saved.items():
         setattr(ref_strategies if kind == "s" else BackendNumpy, name, fn)
     _saved.clear()
+    backend._installed = False

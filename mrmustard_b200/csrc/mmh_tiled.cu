@@ -1,26 +1,30 @@
-// mmh_tiled.cu — K1: tiled march of ONE lattice over many CTAs (second generation), sm_100a.
+// mmh_tiled.cu — K1: tiled march of ONE lattice over many CTAs, sm_100a.
 //
 // The panel of stage i (all k with k_<i = 0, k_i = s) is cut into a grid of boxes over its first nt (<= 3) dims;
 // CTA t owns box t for the whole march s = 1 .. shape[i]-1.  A point reads
 //     G[k - e_i], G[k - 2 e_i]        same panel position, panels s-1, s-2   -> registers of the owning thread
 //     G[k - e_i - e_j]  (j > i)       one cell lower in panel dim j, panel s-1 -> shared memory
-// The shared-memory copy of a panel is the box PLUS a one-cell low margin in every tiled dim; the margin holds the
-// halo owned by the lower neighbour box, so a neighbour read is one LDS at (own offset - stride_j) whether it is
-// interior or halo.  NB = 4 panel buffers rotate, so the halo warps can deliver the margins of up to three panels
-// ahead of the compute warps.
+// Shared memory holds NB = 4 rotating copies of the box: the box itself in slot order (consecutive slots = consecutive
+// cells, so the own-cell store and the neighbour loads of a warp are unit stride and bank-conflict free), followed by the
+// low halo faces owned by the lower neighbour boxes (in exchange order), a cell that always holds 0 (absent neighbours,
+// k_j = 0, point there with coefficient 0) and a trash cell (inactive slots).  Four buffers let the halo warps deliver
+// the halos of up to three panels ahead of the compute warps.
 //
-// Halo exchange without fences or flags (unchanged idea): a producer stores every amplitude on a high
-// face of its box also into X[consumer tile][panel][cell]; X is kept filled with a sentinel (all-ones, a NaN no FP64
-// instruction produces).  The consumer's halo warps poll with L1-bypassing loads until both 64-bit words of a cell
-// differ from the sentinel (64-bit stores are single-copy atomic, so every word validates itself), move the cell into
-// the margin of the right panel buffer and write the sentinel back (self-cleaning).  All NHW halo warps serve every
-// panel together, so a whole face set is fetched in one L2 round trip; one hop of the tile pipeline is one L2 write,
-// one polling read and a CTA-scope release/acquire.
+// Halo exchange without fences or flags: a producer stores every amplitude on a high face of its box also into
+// X[consumer tile][panel][cell]; X is kept filled with a sentinel (all-ones, a NaN no FP64 instruction produces).  The
+// consumer's halo warps -- one per panel buffer, so four panels are in flight -- load a whole panel's cells at once with
+// L1-bypassing loads; both 64-bit words of a cell must differ from the sentinel (64-bit stores are single-copy atomic, so
+// every word validates itself).  Missing cells are re-polled together after per-face canary cells have arrived.  The cells
+// go into the halo area of the panel's buffer and the sentinel is written back afterwards (self-cleaning).
 //
-// The compute step is written for a minimal instruction stream (the FP64 pipe needs 96 issue slots of ~170 per
-// thread-step at R = 2): per-slot constants live in registers, shared memory is addressed with 32-bit offsets,
-// absent neighbours (k_j = 0) point at a cell that always holds 0 with coefficient 0, inactive slots write to a
-// trash cell, and the register-only part of step s+1 (b_i P1 + A_ii sqrt(s) P2) is issued before the barrier of step s.
+// Hand-offs never spin on flags: "panel s is complete in shared memory" (all compute threads + the halo warp) is an
+// mbarrier per panel buffer with split arrive / wait, "buffer k may be overwritten" is a named barrier the compute warps
+// arrive on and the buffer's halo warp syncs on.  With TiledParams::poll0 the kernel does not wait for its predecessor
+// kernel at all but validates panel 0 by the same sentinel (stage overlap).
+//
+// The compute step is written for a short instruction stream (255 warp-instructions per warp-step at R = 2, 100 of them
+// FP64): per-slot constants live in registers, shared memory is addressed with 32-bit offsets, and the register-only part
+// of step s+1 (b_i P1 + A_ii sqrt(s) P2) is issued before the hand-off of step s.
 #include <cstring>
 
 #include "mmh_params.cuh"

@@ -443,6 +443,20 @@ def extras(torch, dev, lib, check, _lib, stream, sptr, flush):
         ms_f = wall(lambda: mm.hermite_renormalized_contracted(A4, b4, cpoly, core))
         ms_m = wall(lambda: np.einsum("abk,k->ab", mm.strategies.vanilla_numba(core + der, A4, b4, 1.0).reshape(core + (-1,)), cpoly.reshape(-1)))
         out["contract_48x48_x_8x40"] = {"fused_ms": ms_f, "materialised_ms": ms_m, "lattice_amplitudes": int(np.prod(core + der))}
+        # cfg4: (i) M = 4 diagonal and one-leftover-mode sweeps at cutoff 12 through the numpy-facing calls,
+        # (ii) the 8-mode ket as one vanilla lattice (12,)^8 = 430 M amplitudes, device resident
+        gd = np.load(os.path.join(ROOT, "tests", "golden", "diagonal_golden.npz"))
+        Ad, bd, cd = gd["d4_A"], gd["d4_b"], complex(gd["d4_c"])
+        out["cfg4_diagonal_M4_cutoff12_ms"] = wall(lambda: mm.hermite_renormalized_diagonal(Ad, bd, cd, (12,) * 4))
+        Al, bl, cl = gd["l4_A"], gd["l4_b"], complex(gd["l4_c"])
+        out["cfg4_1leftover_M4_cutoff12_ms"] = wall(lambda: mm.hermite_renormalized_1leftoverMode(Al, bl, cl, 11, (11, 11, 11)))
+        A8, b8, c8 = gold["cfg4_A"], gold["cfg4_b"], gold["cfg4_c"].reshape(1)
+        dA, db, dc = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (A8, b8, c8))
+        shape = (12,) * 8; sh = _lib.shape_array(shape); n = 12 ** 8
+        dG = torch.empty((n,), dtype=torch.complex128, device=dev)
+        ms = timeit(lambda: check(lib.mmh_forward(8, sh, dA.data_ptr(), db.data_ptr(), dc.data_ptr(), dG.data_ptr(), 0, sptr)), 2, False)
+        out["cfg4_vanilla_12p8_forward"] = {"amps_per_s": n / (ms * 1e-3), "ms": ms, "hbm_frac": 16.0 * n / (ms * 1e-3) / 1e9 / peak}
+        del dG
         # cfg1: latency config
         A, b, c = gold["cfg1_A"], gold["cfg1_b"], gold["cfg1_c"].reshape(1)
         dA, db, dc = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (A, b, c))

@@ -450,6 +450,10 @@ def extras(torch, dev, lib, check, _lib, stream, sptr, flush):
         out["cfg4_diagonal_M4_cutoff12_ms"] = wall(lambda: mm.hermite_renormalized_diagonal(Ad, bd, cd, (12,) * 4))
         Al, bl, cl = gd["l4_A"], gd["l4_b"], complex(gd["l4_c"])
         out["cfg4_1leftover_M4_cutoff12_ms"] = wall(lambda: mm.hermite_renormalized_1leftoverMode(Al, bl, cl, 11, (11, 11, 11)))
+        A8k, b8k, c8k = gold["cfg4_A"], gold["cfg4_b"], complex(gold["cfg4_c"])
+        Adm = np.zeros((16, 16), complex); Adm[:8, :8] = np.conj(A8k); Adm[8:, 8:] = A8k
+        bdm = np.concatenate([np.conj(b8k), b8k])
+        out["cfg4_diagonal_M8_cutoff6_ms"] = wall(lambda: mm.hermite_renormalized_diagonal(Adm, bdm, abs(c8k) ** 2, (6,) * 8), 2)
         A8, b8, c8 = gold["cfg4_A"], gold["cfg4_b"], gold["cfg4_c"].reshape(1)
         dA, db, dc = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (A8, b8, c8))
         shape = (12,) * 8; sh = _lib.shape_array(shape); n = 12 ** 8

@@ -140,3 +140,18 @@ def test_leftover_jacobians_finite_differences(mm, gd):
             if l != i: Ap[l, i] += eps
             want = dA[..., i, l] + (dA[..., l, i] if l != i else 0)
             assert np.allclose((fwd(Ap, b2, c) - G) / eps, want, rtol=1e-4, atol=1e-6), f"dA[{i},{l}]"
+
+
+def test_eight_mode_ket_diagonal_vs_vanilla_lattice(mm, golden):
+    """cfg4 as written in BASELINE.json (8-mode Gaussian ket, diagonal strategy): the diagonal of the density matrix of a ket is
+    |psi_n|^2, so the M = 8 diagonal sweep (A 16x16) must reproduce the squared moduli of the 8-mode vanilla lattice.  The reference
+    layout of the auxiliary arrays (137 arrays of prod(cutoffs) entries) fits one B200 up to cutoff 9; tested at cutoffs 3-4."""
+    A, b, c = golden["cfg4_A"], golden["cfg4_b"], complex(golden["cfg4_c"])
+    Adm = np.zeros((16, 16), complex); Adm[:8, :8] = np.conj(A); Adm[8:, 8:] = A
+    bdm = np.concatenate([np.conj(b), b]); cdm = abs(c) ** 2
+    for cut in [(3, 2, 3, 2, 2, 3, 2, 3), (4,) * 8]:
+        got = mm.hermite_renormalized_diagonal(Adm, bdm, cdm, cut)
+        psi = mm.strategies.vanilla_numba(cut, A, b, c)
+        want = np.abs(psi) ** 2
+        assert got.shape == cut
+        assert np.all(np.abs(got - want) <= 1e-14 + 1e-10 * np.abs(want)), cut

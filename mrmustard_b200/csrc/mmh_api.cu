@@ -188,7 +188,7 @@ static int forward_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st, b
 
 // K1 plan: tile grid over the first nt panel dims of `stage` (mmh_march.cu k_march_tiled)
 static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, TiledParams *tp, int *R_out,
-                             int *ntiles_out, size_t *smem_out) {
+                             int *ntiles_out, size_t *smem_out, double *cost_out = nullptr) {
     const int npd = d.D - 1 - stage;
     if (npd < 1 || npd > 7) return false;
     const long long P = d.strides[stage];
@@ -260,9 +260,9 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
 // The brute-force search above costs tens of microseconds of host time -- more than the GPU needs for a small stage, so an
 // uncached plan leaves the device idle between the launches of one lattice (measured: 12 us gaps on cfg2).  Plans are cached per
 // (shape, stage, SM count, tuning environment); callers hold g_mutex.
-struct TiledPlan { bool ok; TiledParams tp; int R, ntiles; size_t smem; };
+struct TiledPlan { bool ok; TiledParams tp; int R, ntiles; size_t smem; double cost_us; };
 static bool plan_march_tiled_cached(const LatticeDesc &d, int stage, int sm_count, TiledParams *tp, int *R_out,
-                                    int *ntiles_out, size_t *smem_out) {
+                                    int *ntiles_out, size_t *smem_out, double *cost_out = nullptr) {
     static std::map<std::string, TiledPlan> cache;
     std::string key((const char *)d.shape, sizeof(int) * (size_t)d.D);
     key.push_back((char)stage); key.push_back((char)d.D); key.append(std::to_string(sm_count));
@@ -275,13 +275,14 @@ static bool plan_march_tiled_cached(const LatticeDesc &d, int stage, int sm_coun
     if (it == cache.end()) {
         TiledPlan pl;
         memset(&pl, 0, sizeof(pl));
-        pl.ok = plan_march_tiled(d, stage, sm_count, &pl.tp, &pl.R, &pl.ntiles, &pl.smem);
+        pl.ok = plan_march_tiled(d, stage, sm_count, &pl.tp, &pl.R, &pl.ntiles, &pl.smem, &pl.cost_us);
         if (cache.size() > 4096) cache.clear();
         it = cache.emplace(key, pl).first;
     }
     const TiledPlan &pl = it->second;
     if (!pl.ok) return false;
     *tp = pl.tp; *R_out = pl.R; *ntiles_out = pl.ntiles; *smem_out = pl.smem;
+    if (cost_out) *cost_out = pl.cost_us;
     return true;
 }
 
@@ -364,7 +365,20 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
             CK(mmh_launch_warp_tail(sp, st));
             continue;
         }
-        if (!getenv("MMH_FORCE_TILED") && plan_march_stage(d, i, 1, &L, &R, &T, &sm)) {
+        // one CTA (K2) or many tiles (K1) for a panel that would fit one CTA?  One CTA marches ~1 ns per point and step
+        // (1.0 us at 1000 points, measured); tiles of 100-200 points step in ~0.15 us and pay ~1 us per pipeline hop once.
+        // Long marches of mid-size panels ((1000,1000): 999 steps of 1000 points) are 3x faster tiled.
+        bool prefer_tiled = false;
+        if (!getenv("MMH_FORCE_TILED") && !getenv("MMH_NO_PREFER_TILED") && d.strides[i] >= 192 && d.strides[i] <= 1024) {
+            double tcost = 0.0;
+            int R_, n_;
+            size_t sm_;
+            TiledParams t_;
+            const double k2cost = (d.shape[i] - 1) * (0.05 + 1.0e-3 * (double)d.strides[i]);
+            if (plan_march_tiled_cached(d, i, ctx->sm_count, &t_, &R_, &n_, &sm_, &tcost) && n_ > 1 && tcost < 0.6 * k2cost)
+                prefer_tiled = true;
+        }
+        if (!prefer_tiled && !getenv("MMH_FORCE_TILED") && plan_march_stage(d, i, 1, &L, &R, &T, &sm)) {
             StageParams sp;
             sp.d = d; sp.A = p.A; sp.b = p.b; sp.G = p.G; sp.sq = p.sq; sp.rsq = p.rsq;
             sp.batch = 1; sp.lat_stride = d.N; sp.stage = i; sp.L = L;

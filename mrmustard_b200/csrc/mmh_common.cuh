@@ -65,9 +65,20 @@ __device__ __forceinline__ double div_fast(double x, double s, double r) {
     e = __fma_rn(-s, q, x);
     return __fma_rn(e, r, q);
 }
+// x outside [2^-899, 2^900) and non-zero.  Amplitudes far out in a lattice are routinely that small (they decay towards the
+// cutoff), and the IEEE division is ~10x the fast sequence, so the two ranges where a power-of-two scaling is exact are taken
+// through the fast sequence as well:  RN(x / s) = 2^-600 RN(2^600 x / s)  for 2^-1008 <= |x| < 2^-899  (the quotient stays normal:
+// s = sqrt(k) < 2^12),  and  RN(x / s) = 2^200 RN(2^-200 x / s)  for 2^900 <= |x| < inf  (no overflow: s >= 1).  Only subnormal-range
+// quotients, inf and nan take the IEEE division.
+__device__ __forceinline__ double div_rare(double x, double s, double r) {
+    const unsigned ex = ((unsigned)__double2hiint(x) & 0x7fffffffu) >> 20;   // biased exponent
+    if (ex >= 1023u - 1008u && ex < 1023u - 899u) return __dmul_rn(div_fast(__dmul_rn(x, 0x1p600), s, r), 0x1p-600);
+    if (ex >= 1023u + 900u && ex < 2047u) return __dmul_rn(div_fast(__dmul_rn(x, 0x1p-200), s, r), 0x1p200);
+    return __ddiv_rn(x, s);
+}
 __device__ __forceinline__ double div_by_table(double x, double s, double r) {
     if (!div_needs_slow(x)) return div_fast(x, s, r);
-    return __ddiv_rn(x, s);
+    return div_rare(x, s, r);
 }
 // one range test for both components, so that the two 5-level quotient chains interleave instead of running one after
 // the other behind two data-dependent branches (the 1-D chain is a pure latency loop: 170 -> ~105 cycles per step)

@@ -36,8 +36,8 @@ __device__ __forceinline__ void div_all_inplace(c128 (&v)[R], double sqs, double
     } else {
 #pragma unroll
         for (int r = 0; r < R; r++)
-            v[r] = c_make(div_needs_slow(v[r].x) ? __ddiv_rn(v[r].x, sqs) : div_fast(v[r].x, sqs, rsqs),
-                          div_needs_slow(v[r].y) ? __ddiv_rn(v[r].y, sqs) : div_fast(v[r].y, sqs, rsqs));
+            v[r] = c_make(div_needs_slow(v[r].x) ? div_rare(v[r].x, sqs, rsqs) : div_fast(v[r].x, sqs, rsqs),
+                          div_needs_slow(v[r].y) ? div_rare(v[r].y, sqs, rsqs) : div_fast(v[r].y, sqs, rsqs));
     }
 }
 

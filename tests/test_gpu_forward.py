@@ -213,3 +213,33 @@ def test_stable_cutoff_1000(S, golden, tag):
         assert np.allclose(G.ravel()[::7919], golden["st_dg_closed_form_sample"])
     else:
         assert np.max(np.abs(G)) < 1
+
+
+def test_underflowing_and_overflowing_lattices_bit_exact(S, O):
+    """Amplitudes that run through the scaled-division ranges (|x| < 2^-899 down to subnormals and exact zeros; |x| > 2^900 up to the
+    largest finite doubles): the quotient must stay the correctly rounded IEEE quotient of the reference on every path (single CTA,
+    chain, tiled, batched), bit for bit."""
+    def triple(D, scale, seed=11):
+        rng = np.random.RandomState(seed)
+        A = rng.random((D, D)) + 1j * rng.random((D, D)); A = (A + A.T) * scale
+        return A, (rng.random(D) + 1j * rng.random(D)) * scale, 0.7 - 0.2j
+
+    # (Once an amplitude overflows to inf the reference's nan pattern is NOT reproduced: numba divides complex by a real promoted to
+    #  complex, which turns inf + i y into inf + i nan, the kernels divide the components.  The cases below stay finite.)
+    for shape, scale, kind in [((400, 500), 0.05, "tiny"), ((900,), 0.02, "tiny"), ((1200, 300), 0.08, "tiny"),
+                               ((225, 225), 9.0, "huge"), ((420,), 40.0, "huge")]:
+        A, b, c = triple(len(shape), scale)
+        want = O.vanilla(shape, A, b, c)
+        got = S.vanilla_numba(shape, A, b, c)
+        mag = np.abs(want)
+        assert np.isfinite(want).all(), shape
+        if kind == "tiny":
+            assert ((mag < 2.0 ** -899) & (mag > 0)).any(), shape          # the case really exercises the scaled range
+        else:
+            assert (mag > 2.0 ** 900).any(), shape
+        assert np.array_equal(got, want), shape
+    A, b, c = random_triple(2, (40,), seed=2)
+    A = A * 0.05; b = b * 0.05
+    want = O.vanilla_batch((300, 200), A, b, c)
+    assert ((np.abs(want) < 2.0 ** -899) & (np.abs(want) > 0)).any()
+    assert np.array_equal(S.vanilla_batch_numba((300, 200), A, b, c), want)

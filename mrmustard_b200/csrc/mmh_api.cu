@@ -238,9 +238,9 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
                 if (smem > 200 * 1024) continue;
                 // cost model (us): issue time of a step ~ points of the tile, floor = dependent chain of a step, plus the hops of
                 // the longest tile-pipeline path.  The constants are the ones the measured optimum of cfg2 follows from
-                // (stage 0: 5x5x5, stage 1: 3x3; a re-fit to the absolute step times picked 5x5 for stage 1 and lost 14 us).
+                // (stage 0: 5x5x5, stage 1: 4x4; a re-fit to the absolute step times picked 5x5 for stage 1 and lost 14 us).
                 double step_us = (double)TS * 0.55e-3;
-                if (step_us < 0.15) step_us = 0.15;
+                if (step_us < 0.12) step_us = 0.12;
                 const double cost = (S - 1) * step_us + (g0 + g1 + g2 - 3) * 0.7;
                 if (cost < best) {
                     best = cost; bg[0] = g0; bg[1] = g1; bg[2] = g2; bR = R; bTC = TC; bLS = (int)LS; bHC = (int)HC;
@@ -375,8 +375,12 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
             size_t sm_;
             TiledParams t_;
             const double k2cost = (d.shape[i] - 1) * (0.05 + 1.0e-3 * (double)d.strides[i]);
-            if (plan_march_tiled_cached(d, i, ctx->sm_count, &t_, &R_, &n_, &sm_, &tcost) && n_ > 1 && tcost < 0.6 * k2cost)
-                prefer_tiled = true;
+            if (plan_march_tiled_cached(d, i, ctx->sm_count, &t_, &R_, &n_, &sm_, &tcost) && n_ > 1) {
+                // measured step of a small tile WITH halos: ~0.27 us (hand-offs, not arithmetic), 1 ns per point above that
+                double tstep = 0.05 + 1.0e-3 * (double)d.strides[i] / n_;
+                if (tstep < 0.27) tstep = 0.27;
+                if ((d.shape[i] - 1) * tstep < 0.75 * k2cost) prefer_tiled = true;
+            }
         }
         if (!prefer_tiled && !getenv("MMH_FORCE_TILED") && plan_march_stage(d, i, 1, &L, &R, &T, &sm)) {
             StageParams sp;

@@ -472,7 +472,18 @@ static int forward_impl(long long batch, int ndim, const int64_t *shape, const v
     p.batch = batch; p.barrier = nullptr; p.small_stage_lo = 0;
     const size_t smem = sizeof(c128) * (size_t)(ndim * ndim + ndim);
 
-    const bool per_cta = (d.N <= kSingleCtaN && !getenv("MMH_FORCE_TILED")) || batch >= 2LL * ctx->sm_count;
+    // Batches of lattices too large for the one-CTA shared-memory march: either every lattice in turn on the whole device
+    // (tiled, pipelined: ~30 us + 0.03 ns per amplitude each, measured) or one CTA per lattice through L1/L2 (~3 ns per
+    // amplitude and CTA, two CTAs per SM).  The second wins from a few dozen lattices on (128 x (20,)^4: 0.50 vs 4.9 ms).
+    long long per_cta_batch = 2LL * ctx->sm_count;
+    if (!stable && d.N > kSingleCtaN && batch > 1) {
+        const double t_pipe = (double)batch * (30.0 + 3.0e-5 * (double)d.N);
+        const double waves = (double)((batch + 2LL * ctx->sm_count - 1) / (2LL * ctx->sm_count));
+        const double t_cta = waves * 3.0e-3 * (double)d.N;
+        if (t_cta < t_pipe) per_cta_batch = batch;
+    }
+    if (const char *e = getenv("MMH_PER_CTA_BATCH")) per_cta_batch = atoll(e);   // tuning hook
+    const bool per_cta = (d.N <= kSingleCtaN && !getenv("MMH_FORCE_TILED")) || batch >= per_cta_batch;
     if (!stable && (ndim == 1 || per_cta)) {
         bool done = false;
         if ((rc = forward_staged(p, ctx, st, &done))) return rc;

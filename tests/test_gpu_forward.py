@@ -137,6 +137,19 @@ def test_batched_medium_lattices_vs_oracle(S, O):
     assert np.array_equal(S.vanilla_batch_numba(shape, A, b, c, True), O.vanilla_batch(shape, A, b, c, stable=True))
 
 
+def test_batches_of_medium_lattices_both_schedules(S, O, monkeypatch):
+    # lattices above the one-CTA shared-memory size: a few dozen go one CTA per lattice, a handful go through the pipelined
+    # all-SM path (forward_impl's cost rule); both schedules must give the oracle's bits
+    shape = (14, 13, 12, 11)
+    A, b, c = random_triple(4, (40,), seed=17)
+    want = O.vanilla_batch(shape, A, b, c)
+    assert np.array_equal(S.vanilla_batch_numba(shape, A, b, c), want)
+    assert np.array_equal(S.vanilla_batch_numba(shape, A[:3].copy(), b[:3].copy(), c[:3].copy()), want[:3])
+    for thr in ("1", "1000000"):
+        monkeypatch.setenv("MMH_PER_CTA_BATCH", thr)
+        assert np.array_equal(S.vanilla_batch_numba(shape, A, b, c), want), thr
+
+
 @pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
 def test_binomial_golden(S, golden, tag):
     c0, c1, max_l2, gc = golden[f"bin_{tag}_args"]

@@ -179,6 +179,13 @@ static int forward_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st, b
         sp.c = p.c; sp.fuse_chain = 0; sp.pdl = 0; sp.timeline = nullptr; sp.fill_n = 0;
         const long long grid = (p.batch + L[i] - 1) / L[i];
         g_launches++;
+        // stage D-2 of a real batch: the warp-synchronous march (mmh_lanes.cu; no shared-memory neighbours, no CTA barrier)
+        int Rl, ln, Lw;
+        if (i == d.D - 2 && p.batch >= 256 && d.shape[i] <= 4096 && !getenv("MMH_NO_LANES") &&
+            mmh_plan_march_lanes(d.shape[d.D - 1], &Rl, &ln, &Lw)) {
+            CK(mmh_launch_march_lanes(sp, Rl, ln, Lw, st));
+            continue;
+        }
         CK(mmh_launch_march_stage(sp, R[i], (int)grid, T[i], sm[i], st));
     }
     (void)ctx;

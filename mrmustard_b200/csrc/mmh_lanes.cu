@@ -1,0 +1,166 @@
+// mmh_lanes.cu — warp-synchronous batched march of stage D-2 (sm_100a): the whole of a batch of 2-index lattices (cfg3,
+// vanilla_batch_numba over 2-mode kets, vanilla/batch.py:27-61) and the first marched stage of deeper batched lattices.
+//
+// The only neighbour of stage D-2 outside the marched index is k - e_{D-2} - e_{D-1}: the previous panel one position to the
+// left (vanilla/core.py:97-104 with i = D-2).  k_march_stage (mmh_march.cu) reads it from a shared-memory copy of the panel and
+// pays one CTA barrier per step -- the largest stall of the cfg3 profile (2.4 of 8.9 warp cycles per issue).  Here a lane owns
+// R CONSECUTIVE panel positions, so that neighbour is the lane's own register for R-1 of its R positions and one warp shuffle
+// for the first; ln = ceil(n1 / R) lanes hold one lattice row, a warp marches Lw = 32 / ln lattices, and nothing in the step
+// waits for another warp.  The amplitudes leave through a per-warp shared-memory transposition (lane-major in, warp-linear out:
+// one __syncwarp) so that the lattice stores stay coalesced along the last index, 16 B per amplitude written once.
+// The arithmetic is k_march_stage's, operation for operation (bit-identical results).
+#include <cstring>
+
+#include "mmh_params.cuh"
+
+__device__ __forceinline__ void pdl_launch_dependents_l() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <int R>
+__device__ __forceinline__ void div_all_inplace_l(c128 (&v)[R], double sqs, double rsqs) {
+    bool slow = false;
+#pragma unroll
+    for (int r = 0; r < R; r++) slow |= div_needs_slow(v[r].x) | div_needs_slow(v[r].y);
+    if (!slow) {
+#pragma unroll
+        for (int r = 0; r < R; r++) v[r] = c_make(div_fast(v[r].x, sqs, rsqs), div_fast(v[r].y, sqs, rsqs));
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            v[r] = c_make(div_needs_slow(v[r].x) ? div_rare(v[r].x, sqs, rsqs) : div_fast(v[r].x, sqs, rsqs),
+                          div_needs_slow(v[r].y) ? div_rare(v[r].y, sqs, rsqs) : div_fast(v[r].y, sqs, rsqs));
+    }
+}
+
+// transposition buffer index of warp-linear cell q: R odd is conflict free as it is (8 lanes x R cells hit 8 distinct 16-byte
+// bank groups), R even is skewed by one cell per 8
+template <int R>
+__device__ __forceinline__ int xp_index(int q) { return (R & 1) ? q : q + (q >> 3); }
+
+#define MMH_LANES_XP(R) (36 * (R))   // cells of one transposition buffer
+
+// smem: sqtab[S] double2 | xp[warps][2][MMH_LANES_XP(R)] c128
+template <int R>
+__global__ void __launch_bounds__(128) k_march_lanes(StageParams p, int ln, int Lw) {
+    extern __shared__ c128 smem[];
+    const LatticeDesc &d = p.d;
+    const int D = d.D, i = D - 2;
+    const int n1 = d.shape[D - 1], S = d.shape[i];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double2 *sqt = (double2 *)smem;
+    c128 *xp = smem + S + (size_t)warp * 2 * MMH_LANES_XP(R);
+    pdl_launch_dependents_l();
+    for (int n = threadIdx.x; n < S; n += blockDim.x) sqt[n] = make_double2(p.sq[n], p.rsq[n]);
+    __syncthreads();
+    const long long wl0 = ((long long)blockIdx.x * nw + warp) * Lw;   // first lattice of this warp
+    if (wl0 >= p.batch) return;
+    const int nlat = (int)(p.batch - wl0 < Lw ? p.batch - wl0 : Lw);
+
+    // ---- this lane's R consecutive positions ----
+    const int lw = lane / ln;
+    const bool lane_act = lw < nlat;
+    const int k0 = (lane - lw * ln) * R;
+    const long long l = wl0 + (lane_act ? lw : 0);
+    const c128 b0 = p.b[l * D + i], a00 = p.A[l * D * D + i * D + i], a01 = p.A[l * D * D + i * D + i + 1];
+    c128 h0[R], h1[R], coef[R];
+    {
+        const c128 *g0 = p.G + l * p.lat_stride;   // panel 0 (k_i = 0) was written by the chain kernel
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int k1 = k0 + r;
+            const bool act = lane_act && k1 < n1;
+            h0[r] = c_make(0.0, 0.0);
+            h1[r] = act ? g0[k1] : c_make(0.0, 0.0);
+            coef[r] = (act && k1 > 0) ? c_scale(a01, p.sq[k1]) : c_make(0.0, 0.0);   // A_ij sqrt(k_j), core.py:103
+        }
+    }
+    // ---- the cells this lane stores after the transposition: q = j * 32 + lane (warp-linear) ----
+    unsigned go[R];   // element offset from G + wl0 * lat_stride (panel 0), ~0u: padding cell
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        const int q = j * 32 + lane;
+        const int ql = q / R, qr = q - ql * R;
+        const int qw = ql / ln;
+        const int k1 = (ql - qw * ln) * R + qr;
+        go[j] = (qw < nlat && k1 < n1) ? (unsigned)((long long)qw * p.lat_stride + k1) : 0xFFFFFFFFu;
+    }
+    c128 *gs = p.G + wl0 * p.lat_stride;
+    const bool first = k0 == 0;   // position k_{D-1} = 0: no left neighbour (coefficient 0, own value as in k_march_stage)
+
+    // one panel step: new = (b_i P1 + A_ii sqrt(s-1) P2 + coef nb) / sqrt(s); the result replaces P2
+#define MMH_LANES_STEP(P1, P2, XB)                                                                      \
+    {                                                                                                   \
+        c128 v[R];                                                                                      \
+        const c128 up = make_double2(__shfl_up_sync(0xffffffffu, P1[R - 1].x, 1),                       \
+                                     __shfl_up_sync(0xffffffffu, P1[R - 1].y, 1));                      \
+        const c128 as = c_scale(a00, sqm);                                                              \
+        _Pragma("unroll") for (int r = 0; r < R; r++) {                                                 \
+            const c128 nb = r == 0 ? (first ? P1[0] : up) : P1[r > 0 ? r - 1 : 0];                      \
+            v[r] = c_mul(b0, P1[r]);                                                                    \
+            v[r] = c_add(v[r], c_mul(as, P2[r]));                                                       \
+            v[r] = c_add(v[r], c_mul(coef[r], nb));                                                     \
+        }                                                                                               \
+        div_all_inplace_l<R>(v, sqs, rsqs);                                                             \
+        gs += n1;                                                                                       \
+        _Pragma("unroll") for (int r = 0; r < R; r++) {                                                 \
+            P2[r] = v[r];                                                                               \
+            (XB)[xp_index<R>(lane * R + r)] = v[r];                                                     \
+        }                                                                                               \
+        __syncwarp();                                                                                   \
+        _Pragma("unroll") for (int j = 0; j < R; j++) {                                                 \
+            const c128 w = (XB)[xp_index<R>(j * 32 + lane)];                                            \
+            if (go[j] != 0xFFFFFFFFu) gs[go[j]] = w;                                                    \
+        }                                                                                               \
+    }
+
+    c128 *xb0 = xp, *xb1 = xp + MMH_LANES_XP(R);
+    double sqm = 0.0;
+    double2 t = sqt[S > 1 ? 1 : 0];
+    double sqs = t.x, rsqs = t.y;
+    int s = 1;
+#pragma unroll 1
+    for (; s + 1 < S; s += 2) {
+        const double2 t1 = sqt[s + 1];
+        const double2 t2 = sqt[s + 2 < S ? s + 2 : s + 1];
+        MMH_LANES_STEP(h1, h0, xb0)
+        sqm = sqs; sqs = t1.x; rsqs = t1.y;
+        MMH_LANES_STEP(h0, h1, xb1)
+        sqm = sqs; sqs = t2.x; rsqs = t2.y;
+    }
+    if (s < S) MMH_LANES_STEP(h1, h0, xb0)
+#undef MMH_LANES_STEP
+}
+
+// plan: R positions per lane, ln lanes per lattice row, Lw lattices per warp; false when a row does not fit one warp
+bool mmh_plan_march_lanes(int n1, int *R_out, int *ln_out, int *Lw_out) {
+    double best = -1.0;
+    const char *eR = getenv("MMH_LANES_R");
+    for (int R = 2; R <= 8; R++) {
+        if (eR && atoi(eR) != R) continue;
+        const int ln = (n1 + R - 1) / R;
+        if (ln > 32) continue;
+        const int Lw = 32 / ln;
+        // slot efficiency; a slight preference for 4-5 positions per lane (enough independent chains, no register spills)
+        const double score = (double)Lw * n1 / (32.0 * R) - 0.01 * (R > 5 ? R - 5 : (R < 4 ? 4 - R : 0));
+        if (score > best) { best = score; *R_out = R; *ln_out = ln; *Lw_out = Lw; }
+    }
+    return best > 0.0;
+}
+
+cudaError_t mmh_launch_march_lanes(const StageParams &p, int R, int ln, int Lw, cudaStream_t st) {
+    const int block = 128, nw = block / 32;
+    const long long grid = (p.batch + (long long)nw * Lw - 1) / ((long long)nw * Lw);
+    if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
+    const int S = p.d.shape[p.d.D - 2];
+#define MMH_CASE(N)                                                                                                    \
+    case N: {                                                                                                          \
+        const size_t smem = sizeof(c128) * ((size_t)S + (size_t)nw * 2 * MMH_LANES_XP(N));                             \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_march_lanes<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        k_march_lanes<N><<<(unsigned)grid, block, smem, st>>>(p, ln, Lw);                                              \
+        return cudaGetLastError();                                                                                     \
+    }
+    switch (R) {
+        MMH_CASE(2) MMH_CASE(3) MMH_CASE(4) MMH_CASE(5) MMH_CASE(6) MMH_CASE(7) MMH_CASE(8)
+        default: return cudaErrorInvalidValue;
+    }
+#undef MMH_CASE
+}

@@ -137,6 +137,19 @@ def test_batched_medium_lattices_vs_oracle(S, O):
     assert np.array_equal(S.vanilla_batch_numba(shape, A, b, c, True), O.vanilla_batch(shape, A, b, c, stable=True))
 
 
+@pytest.mark.parametrize("shape", [(40, 40), (5, 2), (9, 31), (6, 33), (4, 100), (3, 256), (3, 257), (1, 17), (17, 1),
+                                   (3, 4, 40), (2, 3, 5, 7)])
+def test_lane_march_same_bits_as_stage_march(S, O, shape, monkeypatch):
+    # stage D-2 of a batch >= 256 goes through the warp-synchronous kernel (mmh_lanes.cu); 257 + 3 triples leave a ragged
+    # last warp.  Oracle on a sample, the shared-memory stage march (MMH_NO_LANES) on everything.
+    A, b, c = random_triple(len(shape), (260,), seed=29)
+    G = S.vanilla_batch_numba(shape, A, b, c)
+    for l in (0, 1, 127, 255, 256, 259):
+        assert np.array_equal(G[l], O.vanilla(shape, A[l], b[l], c[l])), l
+    monkeypatch.setenv("MMH_NO_LANES", "1")
+    assert sha(G) == sha(S.vanilla_batch_numba(shape, A, b, c))
+
+
 def test_batches_of_medium_lattices_both_schedules(S, O, monkeypatch):
     # lattices above the one-CTA shared-memory size: a few dozen go one CTA per lattice, a handful go through the pipelined
     # all-SM path (forward_impl's cost rule); both schedules must give the oracle's bits

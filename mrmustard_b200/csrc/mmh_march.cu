@@ -12,6 +12,7 @@
 //     k_fwd_chain   : stage D-1 (a 1-D chain), one thread per lattice.
 //     k_warp_tail   : the two trailing stages of ONE lattice by one warp.
 // K1  (one lattice over many tile-owner CTAs) lives in mmh_tiled.cu.
+#include <cstdlib>
 #include <cstring>
 
 #include "mmh_params.cuh"
@@ -201,6 +202,46 @@ __global__ void __launch_bounds__(128) k_fwd_chain(FwdParams p, int tab) {
         v = c_div_table(v, t.x, t.y);
         g[s] = v;
         p2 = p1; p1 = v; sqm = t.x;
+    }
+}
+
+// The same chain for a batch, rows staged in shared memory: a thread that stores its own amplitude every step writes 16 bytes a
+// lattice stride away from its neighbour's (2.6 M half-sector writes for cfg3, 28 us).  Here the CTA's T rows are collected in
+// shared memory (odd pitch: conflict free) and leave as whole rows, coalesced along the last index.
+// dynamic shared memory: sqtab[S] double2 | rows[T][S | 1] c128
+__global__ void __launch_bounds__(128) k_fwd_chain_rows(FwdParams p) {
+    extern __shared__ double2 sqt_rows[];
+    pdl_launch_dependents();
+    const int D = p.d.D, i = D - 1;
+    const int S = p.d.shape[i], pitch = S | 1, T = blockDim.x;
+    c128 *rows = (c128 *)(sqt_rows + S);
+    for (int n = threadIdx.x; n < S; n += T) sqt_rows[n] = make_double2(p.sq[n], p.rsq[n]);
+    __syncthreads();
+    const long long lat0 = (long long)blockIdx.x * T;
+    const long long l = lat0 + threadIdx.x;
+    if (l < p.batch) {
+        const c128 A = p.A[l * D * D + i * D + i], b = p.b[l * D + i];
+        c128 *row = rows + (size_t)threadIdx.x * pitch;
+        c128 p1 = p.c[l], p2 = c_make(0.0, 0.0);
+        row[0] = p1;
+        double sqm = 0.0;
+        for (int s = 1; s < S; s++) {
+            const double2 t = sqt_rows[s];
+            c128 v = c_mul(b, p1);
+            if (s >= 2) v = c_add(v, c_mul(c_scale(A, sqm), p2));
+            v = c_div_table(v, t.x, t.y);
+            row[s] = v;
+            p2 = p1; p1 = v; sqm = t.x;
+        }
+    }
+    __syncthreads();
+    const int nlat = (int)(p.batch - lat0 < T ? p.batch - lat0 : T);
+    int r = threadIdx.x / S, k = threadIdx.x - r * S;   // cell tid of the CTA's nlat * S cells, then T cells further each time
+    const int dr = T / S, dk = T - dr * S;
+    while (r < nlat) {
+        p.G[(lat0 + r) * p.d.N + k] = rows[(size_t)r * pitch + k];
+        r += dr; k += dk;
+        if (k >= S) { k -= S; r++; }
     }
 }
 
@@ -401,6 +442,17 @@ cudaError_t mmh_launch_march_stage(const StageParams &p, int R, int grid, int bl
 }
 
 cudaError_t mmh_launch_chain(const FwdParams &p, cudaStream_t st) {
+    const int S_ = p.d.shape[p.d.D - 1];
+    if (p.batch >= 256 && S_ >= 4 && !getenv("MMH_NO_CHAIN_ROWS")) {   // batches: rows staged in shared memory, coalesced stores
+        int T = (int)((64 * 1024 - sizeof(double2) * (size_t)S_) / (sizeof(c128) * (size_t)(S_ | 1)));
+        T = T > 128 ? 128 : T / 32 * 32;
+        if (T >= 32 && sizeof(double2) * (size_t)S_ < 32 * 1024) {
+            const size_t smem_ = sizeof(double2) * (size_t)S_ + sizeof(c128) * (size_t)T * (S_ | 1);
+            if (smem_ > 48 * 1024) cudaFuncSetAttribute(k_fwd_chain_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);
+            k_fwd_chain_rows<<<(unsigned)((p.batch + T - 1) / T), T, smem_, st>>>(p);
+            return cudaGetLastError();
+        }
+    }
     const int block = 128;
     const long long grid = (p.batch + block - 1) / block;
     size_t smem = sizeof(double2) * (size_t)p.d.shape[p.d.D - 1];

@@ -16,8 +16,8 @@ dG = torch.empty((B, n), dtype=torch.complex128, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 def run(): _lib.check(_lib.lib.mmh_forward_batched(B, D, sh, dA.data_ptr(), db.data_ptr(), dc.data_ptr(), dG.data_ptr(), 0, None))
 hs = []
-for tag, env in (("stage march", {"MMH_NO_LANES": "1"}), ("lane march", {}), ("lane R=4", {"MMH_LANES_R": "4"}), ("lane R=8", {"MMH_LANES_R": "8"})):
-    for k in ("MMH_NO_LANES", "MMH_LANES_R"): os.environ.pop(k, None)
+for tag, env in (("stage march", {"MMH_NO_LANES": "1"}), ("lane, old chain", {"MMH_NO_CHAIN_ROWS": "1"}), ("lane march", {}), ("lane R=4", {"MMH_LANES_R": "4"})):
+    for k in ("MMH_NO_LANES", "MMH_LANES_R", "MMH_NO_CHAIN_ROWS"): os.environ.pop(k, None)
     os.environ.update(env)
     for _ in range(3): run()
     torch.cuda.synchronize(); ms = []
@@ -26,5 +26,5 @@ for tag, env in (("stage march", {"MMH_NO_LANES": "1"}), ("lane march", {}), ("l
         a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); run(); e.record(); torch.cuda.synchronize(); ms.append(a.elapsed_time(e))
     h = hashlib.sha256(dG.cpu().numpy().tobytes()).hexdigest(); hs.append(h)
-    print(f"{shape} x {B} {tag:12s}: median {np.median(ms):.4f} ms  min {min(ms):.4f} ms  {B*n/np.median(ms)/1e6:.1f} G amp/s  "
+    print(f"{shape} x {B} {tag:18s}: median {np.median(ms):.4f} ms  min {min(ms):.4f} ms  {B*n/np.median(ms)/1e6:.1f} G amp/s  "
           f"hbm frac {16*B*n/np.median(ms)/1e6/6534.8:.3f}  {'same bits' if h == hs[0] else 'MISMATCH'}", flush=True)

@@ -561,6 +561,15 @@ static int vjp_impl(long long batch, int ndim, const int64_t *shape, const void 
     p.sq = ctx->sq;
     p.batch = batch;
     p.nacc = ndim + ndim * (ndim + 1) / 2 + 1;
+    // batches of 2-index lattices: warp-synchronous row walk, every amplitude loaded once (k_vjp_lanes)
+    {
+        int Rl, ln, Lw;
+        if (ndim == 2 && batch >= 256 && d.shape[0] > 1 && !getenv("MMH_NO_LANES") && mmh_plan_march_lanes(d.shape[1], &Rl, &ln, &Lw)) {
+            g_launches++;
+            CK(mmh_launch_vjp_lanes(p, Rl, ln, Lw, st));
+            return MMH_OK;
+        }
+    }
     // batched small lattices: few warps per lattice (long per-thread walks amortise the reduction); one large lattice:
     // 256-thread CTAs, ~8 per SM
     int block = 256;

@@ -197,6 +197,120 @@ __global__ void __launch_bounds__(128) k_vjp_finish(VjpParams p) {
     if (lane == 0) vjp_write_entry(p, lat, e, s);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Batches of 2-index lattices (vanilla_batch_vjp_numba over 2-mode kets, gradients.py:85-116; cfg3): warp-synchronous row walk.
+// k_vjp_partial fetches the five neighbours of every point through L1 (seven 16-byte loads per amplitude: L1 wavefronts bound
+// it at 0.6 of the HBM roofline).  Here a lane owns R consecutive positions of a lattice row (the layout of k_march_lanes,
+// mmh_lanes.cu) and the warp walks the rows k_0 = 0 .. S-1: G[k - e_0], G[k - 2 e_0] are the lane's registers of the two previous
+// rows, G[k - e_1], G[k - 2 e_1], G[k - e_0 - e_1] its own registers or two shuffles from the lane below, so G and dLdG are each
+// loaded exactly once (32 B per amplitude) and nothing is re-read through L1.  The six complex accumulators stay in
+// registers; the ln lanes of a lattice are summed once at the end in a fixed order (deterministic) and the gradients are
+// written directly (no partials, no finish kernel).
+// ---------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(128) k_vjp_lanes(VjpParams p, int ln, int Lw) {
+    __shared__ double red[4][32][13];
+    const LatticeDesc &d = p.d;
+    const int n1 = d.shape[1], S = d.shape[0];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const long long wl0 = ((long long)blockIdx.x * nw + warp) * Lw;
+    if (wl0 >= p.batch) return;
+    const int nlat = (int)(p.batch - wl0 < Lw ? p.batch - wl0 : Lw);
+    const double *__restrict__ sq = p.sq;
+    const int lw = lane / ln;
+    const bool lane_act = lw < nlat;
+    const int k0 = (lane - lw * ln) * R;
+    const long long l = wl0 + (lane_act ? lw : 0);
+    const c128 *Gr = p.G + l * d.N + k0;
+    const c128 *gr = p.g + l * d.N + k0;
+    bool act[R];
+    double w1[R], w11[R];   // sqrt(k_1), 1/2 sqrt(k_1 (k_1 - 1))
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int k1 = k0 + r;
+        act[r] = lane_act && k1 < n1;
+        w1[r] = act[r] ? sq[k1] : 0.0;
+        w11[r] = (act[r] && k1 >= 2) ? 0.5 * sq[k1] * sq[k1 - 1] : 0.0;
+    }
+    const bool first = k0 == 0;   // no left neighbours: the lane below belongs to another lattice
+    c128 acc[6];                  // db_0, db_1, U_00, U_01, U_11, sum G g
+#pragma unroll
+    for (int e = 0; e < 6; e++) acc[e] = c_make(0.0, 0.0);
+    c128 Ra[R], Rb[R], Rc[R];     // three rows in rotation: current, previous, the one before
+#pragma unroll
+    for (int r = 0; r < R; r++) Ra[r] = Rb[r] = Rc[r] = c_make(0.0, 0.0);
+    c128 upP = c_make(0.0, 0.0);  // G[k_0 - 1, k0 - 1]: left neighbour of slot 0 in the previous row
+
+    // one row: C is loaded, P1 / P2 are the two previous rows (gradients.py:68-75)
+#define MMH_VJP_ROW(C, P1, P2)                                                                                  \
+    {                                                                                                           \
+        c128 gk[R];                                                                                             \
+        _Pragma("unroll") for (int r = 0; r < R; r++) {                                                         \
+            C[r] = act[r] ? Gr[r] : c_make(0.0, 0.0);                                                           \
+            gk[r] = act[r] ? gr[r] : c_make(0.0, 0.0);                                                          \
+        }                                                                                                       \
+        Gr += n1; gr += n1;                                                                                     \
+        const double w0 = sq[s], w00 = s >= 2 ? 0.5 * w0 * sq[s - 1] : 0.0;                                     \
+        c128 l1 = make_double2(__shfl_up_sync(0xffffffffu, C[R - 1].x, 1), __shfl_up_sync(0xffffffffu, C[R - 1].y, 1)); \
+        c128 l2 = make_double2(__shfl_up_sync(0xffffffffu, C[R - 2].x, 1), __shfl_up_sync(0xffffffffu, C[R - 2].y, 1)); \
+        if (first) { l1 = c_make(0.0, 0.0); l2 = c_make(0.0, 0.0); }                                            \
+        _Pragma("unroll") for (int r = 0; r < R; r++) {                                                         \
+            const c128 L1 = r == 0 ? l1 : C[r >= 1 ? r - 1 : 0];                                                \
+            const c128 L2 = r == 0 ? l2 : (r == 1 ? l1 : C[r >= 2 ? r - 2 : 0]);                                \
+            const c128 PL = r == 0 ? upP : P1[r >= 1 ? r - 1 : 0];                                              \
+            const c128 x = make_double2(gk[r].x * w0, gk[r].y * w0);                                            \
+            c_fma(acc[5], C[r], gk[r]);                                                                         \
+            c_fma(acc[0], P1[r], x);                                                                            \
+            c_fma(acc[2], P2[r], make_double2(gk[r].x * w00, gk[r].y * w00));                                   \
+            c_fma(acc[1], L1, make_double2(gk[r].x * w1[r], gk[r].y * w1[r]));                                  \
+            c_fma(acc[4], L2, make_double2(gk[r].x * w11[r], gk[r].y * w11[r]));                                \
+            c_fma(acc[3], PL, make_double2(x.x * w1[r], x.y * w1[r]));                                          \
+        }                                                                                                       \
+        upP = l1;                                                                                               \
+    }
+    int s = 0;
+#pragma unroll 1
+    for (; s + 2 < S; s += 3) {
+        MMH_VJP_ROW(Ra, Rb, Rc)
+        s++;
+        MMH_VJP_ROW(Rc, Ra, Rb)
+        s++;
+        MMH_VJP_ROW(Rb, Rc, Ra)
+        s -= 2;
+    }
+    if (s < S) { MMH_VJP_ROW(Ra, Rb, Rc) s++; }
+    if (s < S) { MMH_VJP_ROW(Rc, Ra, Rb) s++; }
+#undef MMH_VJP_ROW
+
+    // the ln lanes of a lattice, summed in lane order by one thread per (lattice, accumulator)
+#pragma unroll
+    for (int e = 0; e < 6; e++) { red[warp][lane][2 * e] = acc[e].x; red[warp][lane][2 * e + 1] = acc[e].y; }
+    __syncwarp();
+    for (int idx = lane; idx < nlat * 6; idx += 32) {
+        const int q = idx / 6, e = idx - q * 6;
+        c128 t = c_make(0.0, 0.0);
+        for (int m = 0; m < ln; m++) { t.x += red[warp][q * ln + m][2 * e]; t.y += red[warp][q * ln + m][2 * e + 1]; }
+        vjp_write_entry(p, wl0 + q, e, t);
+    }
+}
+
+cudaError_t mmh_launch_vjp_lanes(const VjpParams &p, int R, int ln, int Lw, cudaStream_t st) {
+    const int block = 128, nw = block / 32;
+    const long long grid = (p.batch + (long long)nw * Lw - 1) / ((long long)nw * Lw);
+    if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
+    switch (R) {
+        case 2: k_vjp_lanes<2><<<(unsigned)grid, block, 0, st>>>(p, ln, Lw); break;
+        case 3: k_vjp_lanes<3><<<(unsigned)grid, block, 0, st>>>(p, ln, Lw); break;
+        case 4: k_vjp_lanes<4><<<(unsigned)grid, block, 0, st>>>(p, ln, Lw); break;
+        case 5: k_vjp_lanes<5><<<(unsigned)grid, block, 0, st>>>(p, ln, Lw); break;
+        case 6: k_vjp_lanes<6><<<(unsigned)grid, block, 0, st>>>(p, ln, Lw); break;
+        case 7: k_vjp_lanes<7><<<(unsigned)grid, block, 0, st>>>(p, ln, Lw); break;
+        case 8: k_vjp_lanes<8><<<(unsigned)grid, block, 0, st>>>(p, ln, Lw); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 template <typename IT>
 static void launch_partial(const VjpParams &p, dim3 grid, int block, cudaStream_t st) {
     switch (p.d.D) {

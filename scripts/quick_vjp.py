@@ -34,5 +34,13 @@ if which in ("cfg3", "both"):
     c = torch.ones(B, dtype=torch.complex128, device=dev)
     sh = _lib.shape_array((40, 40))
     oA = torch.empty((B, 2, 2), dtype=torch.complex128, device=dev); ob = torch.empty((B, 2), dtype=torch.complex128, device=dev); oc = torch.empty(B, dtype=torch.complex128, device=dev)
-    ms = timeit(lambda: check(lib.mmh_vjp_batched(B, 2, sh, G.data_ptr(), c.data_ptr(), g.data_ptr(), oA.data_ptr(), ob.data_ptr(), oc.data_ptr(), None)), 5, False)
-    print(f"cfg3 vjp: {ms*1e3:.1f} us  {B*n/ms/1e6:.2f} G amp/s  hbm frac {32*B*n/ms/1e6/6534.8:.3f}")
+    ref = None
+    for tag, env in (("partial kernel", {"MMH_NO_LANES": "1"}), ("row walk", {}), ("row walk R=4", {"MMH_LANES_R": "4"}), ("row walk R=3", {"MMH_LANES_R": "3"})):
+        for k in ("MMH_NO_LANES", "MMH_LANES_R"): os.environ.pop(k, None)
+        os.environ.update(env)
+        ms = timeit(lambda: check(lib.mmh_vjp_batched(B, 2, sh, G.data_ptr(), c.data_ptr(), g.data_ptr(), oA.data_ptr(), ob.data_ptr(), oc.data_ptr(), None)), 5, False)
+        out = np.concatenate([oA.cpu().numpy().ravel(), ob.cpu().numpy().ravel(), oc.cpu().numpy().ravel()])
+        if ref is None: ref = out
+        err = np.max(np.abs(out - ref) / (1e-14 / 1e-10 + np.abs(ref)))
+        print(f"cfg3 vjp {tag:14s}: {ms*1e3:.1f} us  {B*n/ms/1e6:.2f} G amp/s  hbm frac {32*B*n/ms/1e6/6534.8:.3f}  max rel dev vs partial kernel {err:.1e}", flush=True)
+    for k in ("MMH_NO_LANES", "MMH_LANES_R"): os.environ.pop(k, None)

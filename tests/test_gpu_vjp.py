@@ -101,6 +101,15 @@ def test_cfg3_batched(S, O, golden):
     _check(S.vanilla_batch_vjp_numba(G, c, g), O.vanilla_batch_vjp(G, c, g), "B=70000")
 
 
+@pytest.mark.parametrize("shape", [(40, 40), (5, 2), (9, 31), (6, 33), (4, 100), (3, 256), (3, 257), (2, 17), (17, 3)])
+def test_row_walk_batched_2d(S, O, shape):
+    # batches >= 256 of 2-index lattices go through the warp-synchronous row walk (k_vjp_lanes); 260 leaves a ragged last warp
+    A, b, c = random_triple(2, (260,), seed=31)
+    G = O.vanilla_batch(shape, A, b, c)
+    g = np.random.RandomState(4).standard_normal(G.shape) + 1j * np.random.RandomState(5).standard_normal(G.shape)
+    _check(S.vanilla_batch_vjp_numba(G, c, g), O.vanilla_batch_vjp(G, c, g), f"row walk {shape}")
+
+
 def test_linearity_in_cotangent(S):
     """Size-independent property: the VJP is linear in dLdG."""
     A, b, c = random_triple(3, (), seed=21)

@@ -335,7 +335,7 @@ def main():
     # algorithmic bytes over the whole step's device time (a lower bound of the dominant kernel's own figure)
     kernel_name = ("mmh_forward: memset(panel 0) + k_warp_tail + k_march_tiled2<1,2> + k_march_tiled2<2,3> (dominant, 66% of the serialised "
                    "kernel time; the three kernels overlap)"
-                   if w["batch"] is None else "mmh_forward_batched: k_fwd_chain + k_march_stage<2,1> (dominant, >95% of the step)")
+                   if w["batch"] is None else "mmh_forward_batched: k_fwd_chain_rows + k_march_lanes<5> (dominant, >90% of the step)")
     traffic_note = None
     if os.path.exists(tpath):
         try:

@@ -577,7 +577,10 @@ static int vjp_impl(long long batch, int ndim, const int64_t *shape, const void 
     else block = 128;
     if (const char *e = getenv("MMH_VJP_BLOCK")) block = atoi(e);
     long long want = (d.N + block * 4 - 1) / (block * 4);   // ~4 points per thread
-    long long cap = (4LL * ctx->sm_count + batch - 1) / batch; // ~4 CTAs per SM over the whole batch
+    // one wave of resident CTAs over the whole batch (at most 4 per SM)
+    int per_sm = mmh_vjp_blocks_per_sm(p, block);
+    if (per_sm > 4) per_sm = 4;
+    long long cap = ((long long)per_sm * ctx->sm_count + batch - 1) / batch;
     if (const char *e = getenv("MMH_VJP_CTAS_PER_SM")) cap = ((long long)atoi(e) * ctx->sm_count + batch - 1) / batch;
     if (cap < 1) cap = 1;
     if (want > cap) want = cap;

@@ -79,6 +79,7 @@ size_t mmh_tiled2_smem(int ls_max, int hc_max, int S, int slots);
 cudaError_t mmh_launch_march_stage(const StageParams &p, int R, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t mmh_launch_warp_tail(const StageParams &p, cudaStream_t st);
 bool mmh_plan_march_lanes(int n1, int *R_out, int *ln_out, int *Lw_out);
+int mmh_vjp_blocks_per_sm(const VjpParams &p, int block);
 cudaError_t mmh_launch_vjp_lanes(const VjpParams &p, int R, int ln, int Lw, cudaStream_t st);
 cudaError_t mmh_launch_march_lanes(const StageParams &p, int R, int ln, int Lw, cudaStream_t st);
 cudaError_t mmh_launch_contract_last(const c128 *G, const c128 *cp, c128 *out, long long nout, long long ncore, int nd, cudaStream_t st);

@@ -82,20 +82,32 @@ __global__ void __launch_bounds__(256, MMH_VJP_MINB) k_vjp_partial(VjpParams p) 
         for (int i = 0; i < DT; i++) { k[i] = (int)(rem / st[i]); rem -= (IT)k[i] * st[i]; }
     }
     for (; f < N; f += stride) {
+        // Every neighbour is fetched unconditionally in one batch of independent loads (a missing neighbour, k_i = 0, reads
+        // G[f] instead and meets a zero weight: sq[0] = 0), so that the ~D(D+1)/2 + D + 2 loads of a point are all in flight
+        // together instead of one load -> fma pair per data-dependent branch.
         const c128 gk = g[f];
-        c_fma(acc[NACC - 1], G[f], gk);  // dLdc numerator (gradients.py:80)
+        const c128 Gf = G[f];
+        c128 Gi[DT], Gii[DT], Gij[NACC];
+        double wi[DT];
+#pragma unroll
+        for (int i = 0; i < DT; i++) {
+            const bool ok = k[i] >= 1;
+            const IT pivot = ok ? f - st[i] : f;
+            wi[i] = sq[k[i]];
+            Gi[i] = G[pivot];
+            Gii[i] = G[k[i] >= 2 ? pivot - st[i] : f];
+#pragma unroll
+            for (int j = i + 1; j < DT; j++) Gij[i * DT + j - (i + 1) * (i + 2) / 2] = G[(ok && k[j] >= 1) ? pivot - st[j] : f];
+        }
+        c_fma(acc[NACC - 1], Gf, gk);  // dLdc numerator (gradients.py:80)
         int e = DT;
 #pragma unroll
         for (int i = 0; i < DT; i++) {
-            if (k[i] >= 1) {
-                const IT pivot = f - st[i];
-                const double wi = sq[k[i]];
-                c_fma(acc[i], c_scale(G[pivot], wi), gk);                                   // :68
-                if (k[i] > 1) c_fma(acc[e], c_scale(G[pivot - st[i]], 0.5 * wi * sq[k[i] - 1]), gk);  // :69-73
+            c_fma(acc[i], c_scale(Gi[i], wi[i]), gk);                                                   // :68
+            c_fma(acc[e], c_scale(Gii[i], 0.5 * wi[i] * sq[k[i] >= 1 ? k[i] - 1 : 0]), gk);             // :69-73
 #pragma unroll
-                for (int j = i + 1; j < DT; j++)
-                    if (k[j] >= 1) c_fma(acc[e + (j - i)], c_scale(G[pivot - st[j]], wi * sq[k[j]]), gk);  // :74-75
-            }
+            for (int j = i + 1; j < DT; j++)
+                c_fma(acc[e + (j - i)], c_scale(Gij[i * DT + j - (i + 1) * (i + 2) / 2], wi[i] * wi[j]), gk);   // :74-75
             e += DT - i;
         }
         // advance the multi-index by `stride` (mixed-radix add with carry, last mode first)
@@ -324,6 +336,29 @@ static void launch_partial(const VjpParams &p, dim3 grid, int block, cudaStream_
         case 8: k_vjp_partial<8, IT><<<grid, block, 0, st>>>(p); break;
         default: break;
     }
+}
+
+// resident CTAs per SM of the partial kernel (register bound: the batched loads of D >= 4 take 160+ registers)
+template <typename IT>
+static int partial_blocks_per_sm(int D, int block) {
+    int n = 0;
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (D) {
+        case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_vjp_partial<1, IT>, block, 0); break;
+        case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_vjp_partial<2, IT>, block, 0); break;
+        case 3: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_vjp_partial<3, IT>, block, 0); break;
+        case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_vjp_partial<4, IT>, block, 0); break;
+        case 5: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_vjp_partial<5, IT>, block, 0); break;
+        case 6: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_vjp_partial<6, IT>, block, 0); break;
+        case 7: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_vjp_partial<7, IT>, block, 0); break;
+        case 8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_vjp_partial<8, IT>, block, 0); break;
+        default: break;
+    }
+    return (e == cudaSuccess && n > 0) ? n : 1;
+}
+int mmh_vjp_blocks_per_sm(const VjpParams &p, int block) {
+    if (p.d.D > 8) return 4;
+    return p.d.N < 0x7fffffffLL ? partial_blocks_per_sm<unsigned>(p.d.D, block) : partial_blocks_per_sm<long long>(p.d.D, block);
 }
 
 cudaError_t mmh_launch_vjp(const VjpParams &p_in, int grid_y, int block, cudaStream_t st) {

@@ -205,43 +205,50 @@ __global__ void __launch_bounds__(128) k_fwd_chain(FwdParams p, int tab) {
     }
 }
 
-// The same chain for a batch, rows staged in shared memory: a thread that stores its own amplitude every step writes 16 bytes a
-// lattice stride away from its neighbour's (2.6 M half-sector writes for cfg3, 28 us).  Here the CTA's T rows are collected in
-// shared memory (odd pitch: conflict free) and leave as whole rows, coalesced along the last index.
-// dynamic shared memory: sqtab[S] double2 | rows[T][S | 1] c128
+// The same chain for a batch, staged in shared memory: a thread that stores its own amplitude every step writes 16 bytes a
+// lattice stride away from its neighbour's (2.6 M half-sector writes for cfg3, 28 us).  Here the CTA's T chains advance 8 steps
+// at a time into a double-buffered [T][8] tile (pitch 9: conflict free both ways) that leaves as 128-byte row segments, eight
+// lanes per lattice.  The tile is small (18 KB per buffer pair), so every chain of a 65,536-lattice batch is resident at once:
+// with whole rows staged (64 KB per CTA) the batch needed two waves at two warps per scheduler, 24 us, issue-latency bound.
+// dynamic shared memory: sqtab[S] double2 | tile[2][T][9] c128
+#define MMH_CHAIN_CH 8
 __global__ void __launch_bounds__(128) k_fwd_chain_rows(FwdParams p) {
     extern __shared__ double2 sqt_rows[];
     pdl_launch_dependents();
     const int D = p.d.D, i = D - 1;
-    const int S = p.d.shape[i], pitch = S | 1, T = blockDim.x;
-    c128 *rows = (c128 *)(sqt_rows + S);
+    const int S = p.d.shape[i], T = blockDim.x;
+    constexpr int CH = MMH_CHAIN_CH, PITCH = CH + 1;
+    c128 *tile = (c128 *)(sqt_rows + S);
     for (int n = threadIdx.x; n < S; n += T) sqt_rows[n] = make_double2(p.sq[n], p.rsq[n]);
     __syncthreads();
     const long long lat0 = (long long)blockIdx.x * T;
     const long long l = lat0 + threadIdx.x;
-    if (l < p.batch) {
-        const c128 A = p.A[l * D * D + i * D + i], b = p.b[l * D + i];
-        c128 *row = rows + (size_t)threadIdx.x * pitch;
-        c128 p1 = p.c[l], p2 = c_make(0.0, 0.0);
-        row[0] = p1;
-        double sqm = 0.0;
-        for (int s = 1; s < S; s++) {
-            const double2 t = sqt_rows[s];
-            c128 v = c_mul(b, p1);
-            if (s >= 2) v = c_add(v, c_mul(c_scale(A, sqm), p2));
-            v = c_div_table(v, t.x, t.y);
-            row[s] = v;
-            p2 = p1; p1 = v; sqm = t.x;
-        }
-    }
-    __syncthreads();
+    const bool act = l < p.batch;
     const int nlat = (int)(p.batch - lat0 < T ? p.batch - lat0 : T);
-    int r = threadIdx.x / S, k = threadIdx.x - r * S;   // cell tid of the CTA's nlat * S cells, then T cells further each time
-    const int dr = T / S, dk = T - dr * S;
-    while (r < nlat) {
-        p.G[(lat0 + r) * p.d.N + k] = rows[(size_t)r * pitch + k];
-        r += dr; k += dk;
-        if (k >= S) { k -= S; r++; }
+    const long long lc = act ? l : lat0;
+    const c128 A = p.A[lc * D * D + i * D + i], b = p.b[lc * D + i];
+    c128 p1 = p.c[lc], p2 = c_make(0.0, 0.0);
+    double sqm = 0.0;
+    for (int c0 = 0, buf = 0; c0 < S; c0 += CH, buf ^= 1) {
+        const int cw = S - c0 < CH ? S - c0 : CH;
+        c128 *mine = tile + ((size_t)buf * T + threadIdx.x) * PITCH;
+        for (int j = 0; j < cw; j++) {
+            const int s = c0 + j;
+            if (s > 0) {
+                const double2 t = sqt_rows[s];
+                c128 v = c_mul(b, p1);
+                if (s >= 2) v = c_add(v, c_mul(c_scale(A, sqm), p2));
+                v = c_div_table(v, t.x, t.y);
+                p2 = p1; p1 = v; sqm = t.x;
+            }
+            mine[j] = p1;
+        }
+        __syncthreads();   // one barrier per chunk: the other buffer is rewritten only after everybody has passed this one
+        const c128 *src = tile + (size_t)buf * T * PITCH;
+        for (int idx = threadIdx.x; idx < nlat * cw; idx += T) {
+            const int r = idx / cw, k = idx - r * cw;
+            p.G[(lat0 + r) * p.d.N + c0 + k] = src[r * PITCH + k];
+        }
     }
 }
 
@@ -443,15 +450,12 @@ cudaError_t mmh_launch_march_stage(const StageParams &p, int R, int grid, int bl
 
 cudaError_t mmh_launch_chain(const FwdParams &p, cudaStream_t st) {
     const int S_ = p.d.shape[p.d.D - 1];
-    if (p.batch >= 256 && S_ >= 4 && !getenv("MMH_NO_CHAIN_ROWS")) {   // batches: rows staged in shared memory, coalesced stores
-        int T = (int)((64 * 1024 - sizeof(double2) * (size_t)S_) / (sizeof(c128) * (size_t)(S_ | 1)));
-        T = T > 128 ? 128 : T / 32 * 32;
-        if (T >= 32 && sizeof(double2) * (size_t)S_ < 32 * 1024) {
-            const size_t smem_ = sizeof(double2) * (size_t)S_ + sizeof(c128) * (size_t)T * (S_ | 1);
-            if (smem_ > 48 * 1024) cudaFuncSetAttribute(k_fwd_chain_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);
-            k_fwd_chain_rows<<<(unsigned)((p.batch + T - 1) / T), T, smem_, st>>>(p);
-            return cudaGetLastError();
-        }
+    if (p.batch >= 256 && S_ >= 4 && S_ <= 8192 && !getenv("MMH_NO_CHAIN_ROWS")) {   // batches: staged chunks, coalesced stores
+        const int T = 128;
+        const size_t smem_ = sizeof(double2) * (size_t)S_ + sizeof(c128) * (size_t)2 * T * (MMH_CHAIN_CH + 1);
+        if (smem_ > 48 * 1024) cudaFuncSetAttribute(k_fwd_chain_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);
+        k_fwd_chain_rows<<<(unsigned)((p.batch + T - 1) / T), T, smem_, st>>>(p);
+        return cudaGetLastError();
     }
     const int block = 128;
     const long long grid = (p.batch + block - 1) / block;

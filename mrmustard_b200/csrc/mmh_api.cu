@@ -167,12 +167,26 @@ static int forward_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st, b
     *done = false;
     int L[MMH_MAX_DIM], R[MMH_MAX_DIM], T[MMH_MAX_DIM];
     size_t sm[MMH_MAX_DIM];
-    for (int i = d.D - 2; i >= 0; i--)
-        if (!plan_march_stage(d, i, p.batch, &L[i], &R[i], &T[i], &sm[i])) return MMH_OK;
+    bool box[MMH_MAX_DIM];
+    BoxParams bp[MMH_MAX_DIM];
+    for (int i = d.D - 2; i >= 0; i--) {
+        box[i] = false;
+        if (plan_march_stage(d, i, p.batch, &L[i], &R[i], &T[i], &sm[i])) continue;
+        // panels beyond one CTA's shared memory: the same CTA marches the lattice box by box (mmh_box.cu)
+        if (d.shape[i] == 1 || getenv("MMH_NO_BOX") || !mmh_plan_march_box(d, i, &bp[i], &T[i], &sm[i])) return MMH_OK;
+        box[i] = true;
+    }
     g_launches++;
     CK(mmh_launch_chain(p, st));
     for (int i = d.D - 2; i >= 0; i--) {
         if (d.shape[i] == 1) continue;   // nothing to march
+        if (box[i]) {
+            BoxParams &q = bp[i];
+            q.A = p.A; q.b = p.b; q.G = p.G; q.sq = p.sq; q.rsq = p.rsq; q.batch = p.batch; q.lat_stride = d.N;
+            g_launches++;
+            CK(mmh_launch_march_box(q, ctx->sm_count, T[i], sm[i], st));
+            continue;
+        }
         StageParams sp;
         sp.d = d; sp.A = p.A; sp.b = p.b; sp.G = p.G; sp.sq = p.sq; sp.rsq = p.rsq;
         sp.batch = p.batch; sp.lat_stride = d.N; sp.stage = i; sp.L = L[i];
@@ -188,7 +202,6 @@ static int forward_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st, b
         }
         CK(mmh_launch_march_stage(sp, R[i], (int)grid, T[i], sm[i], st));
     }
-    (void)ctx;
     *done = true;
     return MMH_OK;
 }
@@ -480,13 +493,18 @@ static int forward_impl(long long batch, int ndim, const int64_t *shape, const v
     const size_t smem = sizeof(c128) * (size_t)(ndim * ndim + ndim);
 
     // Batches of lattices too large for the one-CTA shared-memory march: either every lattice in turn on the whole device
-    // (tiled, pipelined: ~30 us + 0.03 ns per amplitude each, measured) or one CTA per lattice through L1/L2 (~3 ns per
-    // amplitude and CTA, two CTAs per SM).  The second wins from a few dozen lattices on (128 x (20,)^4: 0.50 vs 4.9 ms).
+    // (tiled, pipelined: ~30 us + 0.03 ns per amplitude each, measured) or one CTA per lattice -- the box march (mmh_box.cu,
+    // ~1.1 ns per amplitude and CTA, one CTA per SM; (20,)^4: 0.18 ms per wave of 148 lattices) or, for panels of more than four
+    // dims, the L1/L2 kernel (~3 ns per amplitude and CTA, two CTAs per SM).  One CTA per lattice wins from a handful of lattices
+    // on (32 x (30,)^4: 0.77 vs 1.78 ms; 8 x (30,)^4: 0.73 vs 0.45 ms).
     long long per_cta_batch = 2LL * ctx->sm_count;
     if (!stable && d.N > kSingleCtaN && batch > 1) {
+        const bool boxed = ndim <= 5 && !getenv("MMH_NO_BOX");
+        const double rate = boxed ? 1.1e-3 : 3.0e-3;   // us per amplitude and CTA
+        const long long slots = (boxed ? 1LL : 2LL) * ctx->sm_count;
         const double t_pipe = (double)batch * (30.0 + 3.0e-5 * (double)d.N);
-        const double waves = (double)((batch + 2LL * ctx->sm_count - 1) / (2LL * ctx->sm_count));
-        const double t_cta = waves * 3.0e-3 * (double)d.N;
+        const double waves = (double)((batch + slots - 1) / slots);
+        const double t_cta = waves * rate * (double)d.N;
         if (t_cta < t_pipe) per_cta_batch = batch;
     }
     if (const char *e = getenv("MMH_PER_CTA_BATCH")) per_cta_batch = atoll(e);   // tuning hook

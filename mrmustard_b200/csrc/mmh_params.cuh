@@ -55,6 +55,18 @@ struct StageParams {
     long long fill_n;            // k_warp_tail: pre-fill G[0, fill_n) with the all-ones sentinel first (stage overlap), 0 = no
 };
 
+struct BoxParams {               // k_march_box (mmh_box.cu): one CTA marches a lattice's stage box by box
+    LatticeDesc d;
+    const c128 *A, *b;           // [batch, D, D], [batch, D]
+    c128 *G;                     // [batch, lat_stride]
+    const double *sq, *rsq;
+    long long batch, lat_stride;
+    int stage;                   // i: the index being marched
+    int nt;                      // number of boxed panel dims (1..3): dims stage+1 .. stage+nt
+    int g[3];                    // box grid
+    int ls;                      // shared-memory cells of one panel buffer: box + halo faces + zero cell + trash cell
+};
+
 struct TiledParams {
     LatticeDesc d;
     const c128 *A, *b;           // one triple (device)
@@ -78,6 +90,8 @@ cudaError_t mmh_launch_march_tiled2(const TiledParams &p, int R, int ntiles, siz
 size_t mmh_tiled2_smem(int ls_max, int hc_max, int S, int slots);
 cudaError_t mmh_launch_march_stage(const StageParams &p, int R, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t mmh_launch_warp_tail(const StageParams &p, cudaStream_t st);
+bool mmh_plan_march_box(const LatticeDesc &d, int stage, BoxParams *bp, int *T_out, size_t *smem_out);
+cudaError_t mmh_launch_march_box(const BoxParams &p, int sm_count, int T, size_t smem, cudaStream_t st);
 bool mmh_plan_march_lanes(int n1, int *R_out, int *ln_out, int *Lw_out);
 int mmh_vjp_blocks_per_sm(const VjpParams &p, int block);
 cudaError_t mmh_launch_vjp_lanes(const VjpParams &p, int R, int ln, int Lw, cudaStream_t st);

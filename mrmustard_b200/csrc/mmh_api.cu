@@ -493,7 +493,7 @@ static int forward_impl(long long batch, int ndim, const int64_t *shape, const v
     const size_t smem = sizeof(c128) * (size_t)(ndim * ndim + ndim);
 
     // Batches of lattices too large for the one-CTA shared-memory march: either every lattice in turn on the whole device
-    // (tiled, pipelined: ~30 us + 0.03 ns per amplitude each, measured) or one CTA per lattice -- the box march (mmh_box.cu,
+    // (tiled, pipelined) or one CTA per lattice -- the box march (mmh_box.cu,
     // ~1.1 ns per amplitude and CTA, one CTA per SM; (20,)^4: 0.18 ms per wave of 148 lattices) or, for panels of more than four
     // dims, the L1/L2 kernel (~3 ns per amplitude and CTA, two CTAs per SM).  One CTA per lattice wins from a handful of lattices
     // on (32 x (30,)^4: 0.77 vs 1.78 ms; 8 x (30,)^4: 0.73 vs 0.45 ms).
@@ -502,7 +502,10 @@ static int forward_impl(long long batch, int ndim, const int64_t *shape, const v
         const bool boxed = ndim <= 5 && !getenv("MMH_NO_BOX");
         const double rate = boxed ? 1.1e-3 : 3.0e-3;   // us per amplitude and CTA
         const long long slots = (boxed ? 1LL : 2LL) * ctx->sm_count;
-        const double t_pipe = (double)batch * (30.0 + 3.0e-5 * (double)d.N);
+        long long steps = 0;
+        for (int i = 0; i < ndim; i++) steps += d.shape[i] - 1;
+        // per lattice, pipelined (measured: (20,)^4 39 us, (30,)^4 56 us, (64,)^3 52 us, (50,)^4 85 us)
+        const double t_pipe = (double)batch * (25.0 + 0.1 * (double)steps + 8.0e-6 * (double)d.N);
         const double waves = (double)((batch + slots - 1) / slots);
         const double t_cta = waves * rate * (double)d.N;
         if (t_cta < t_pipe) per_cta_batch = batch;

@@ -429,6 +429,15 @@ def extras(torch, dev, lib, check, _lib, stream, sptr, flush):
         ms = timeit(lambda: check(lib.mmh_forward_batched(Bq, 4, sh, dA.data_ptr(), db.data_ptr(), dc.data_ptr(), dG.data_ptr(), 0, sptr)), 5, True)
         out["cfg2_batch8_forward"] = {"amps_per_s": Bq * n / (ms * 1e-3), "ms": ms, "hbm_frac": 16.0 * Bq * n / (ms * 1e-3) / 1e9 / peak}
         del dG
+        # a batch of 2-mode unitaries at cutoff 20: 148 x (20,)^4 through hermite_renormalized_batched (box march, mmh_box.cu)
+        Bq = 148
+        A, b, c = random_triple(4, (Bq,), seed=3)
+        dA, db, dc = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (A, b, c))
+        shape = (20,) * 4; sh = _lib.shape_array(shape); n = 20 ** 4
+        dG = torch.empty((Bq, n), dtype=torch.complex128, device=dev)
+        ms = timeit(lambda: check(lib.mmh_forward_batched(Bq, 4, sh, dA.data_ptr(), db.data_ptr(), dc.data_ptr(), dG.data_ptr(), 0, sptr)), 5, True)
+        out["batch148_20p4_forward"] = {"amps_per_s": Bq * n / (ms * 1e-3), "ms": ms, "hbm_frac": 16.0 * Bq * n / (ms * 1e-3) / 1e9 / peak}
+        del dG
         # lattice + derived-variable contraction, end to end through the numpy-facing call (host buffers):
         # fused (only the contracted array is copied back) vs materialising the lattice on the host and einsum there
         import mrmustard_b200 as mm

@@ -236,6 +236,9 @@ bool mmh_plan_march_box(const LatticeDesc &d, int stage, BoxParams *bp, int *T_o
     // (10 points = 160 bytes) leave partially written 64-byte DRAM atoms, and once a batch outgrows L2 (126 MB) those cost
     // read-modify-writes (148 x (20,)^4 in 10 x 10 x 10 boxes: 0.69 ms; in 5 x 10 x 20 boxes: 0.20 ms; 32 lattices, L2
     // resident: 0.19 ms either way)
+    long long max_ts = 1024;
+    if (const char *e_ = getenv("MMH_BOX_MAXTS")) max_ts = atoll(e_);   // tuning hook
+    if (inner > max_ts) return false;
     double best_cost = 1e300;
     long long best_tiles = -1;
     int bg[3] = { 1, 1, 1 }, bT = 0, bLS = 0;
@@ -247,7 +250,7 @@ bool mmh_plan_march_box(const LatticeDesc &d, int stage, BoxParams *bp, int *T_o
                 const int g[3] = { g0, g1, g2 };
                 long long e[3], TS = inner;
                 for (int m = 0; m < 3; m++) { e[m] = (shp[m] + g[m] - 1) / g[m]; TS *= e[m]; }
-                if (TS > 1024) continue;
+                if (TS > max_ts) continue;
                 long long HC = 0;
                 for (int m = 0; m < 3; m++) if (g[m] > 1) HC += TS / e[m];
                 int T = (int)((TS + 1) / 2 + 31) / 32 * 32;

@@ -9,7 +9,7 @@ from mrmustard_b200 import _lib
 dev = torch.device("cuda:0")
 for shape in [(20,) * 4, (30,) * 4, (64, 64, 64)]:
     D = len(shape); n = int(np.prod(shape)); sh = _lib.shape_array(shape)
-    for B in (8, 32, 148, 512):
+    for B in [int(x) for x in os.environ.get('QB', '8,32,148,512').split(',')]:
         A, b, c = random_triple(D, (B,), seed=3)
         dA, db, dc = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (A, b, c))
         dG = torch.empty((B, n), dtype=torch.complex128, device=dev)

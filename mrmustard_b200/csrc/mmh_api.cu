@@ -196,7 +196,7 @@ static int forward_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st, b
         // stage D-2 of a real batch: the warp-synchronous march (mmh_lanes.cu; no shared-memory neighbours, no CTA barrier)
         int Rl, ln, Lw;
         if (i == d.D - 2 && p.batch >= 256 && d.shape[i] <= 4096 && !getenv("MMH_NO_LANES") &&
-            mmh_plan_march_lanes(d.shape[d.D - 1], &Rl, &ln, &Lw)) {
+            mmh_plan_march_lanes(d.shape[d.D - 1], &Rl, &ln, &Lw) && (long long)Lw * d.N < (1LL << 32)) {   // 32-bit store offsets
             CK(mmh_launch_march_lanes(sp, Rl, ln, Lw, st));
             continue;
         }

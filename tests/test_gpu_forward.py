@@ -138,7 +138,7 @@ def test_batched_medium_lattices_vs_oracle(S, O):
 
 
 @pytest.mark.parametrize("shape", [(40, 40), (5, 2), (9, 31), (6, 33), (4, 100), (3, 256), (3, 257), (1, 17), (17, 1),
-                                   (3, 4, 40), (2, 3, 5, 7)])
+                                   (3, 4, 40), (2, 3, 5, 7), (200,), (5,), (3,)])
 def test_lane_march_same_bits_as_stage_march(S, O, shape, monkeypatch):
     # stage D-2 of a batch >= 256 goes through the warp-synchronous kernel (mmh_lanes.cu); 257 + 3 triples leave a ragged
     # last warp.  Oracle on a sample, the shared-memory stage march (MMH_NO_LANES) on everything.

@@ -170,6 +170,12 @@ int mmh_1leftover_host(int M, const int64_t *cutoffs, const void *A, const void 
  * exit of CTA 0) of the last single-lattice forward's kernels; synchronises the device.                          */
 int mmh_debug_timeline(unsigned long long *out64);
 
+/* debug aid, host only (no device needed): the launch plans of the batched kernels, for the CPU tests of the planners.
+ * what = 0: lane layout of a lattice row of n1 = shape[ndim-1] positions (mmh_lanes.cu)  -> out = {R, ln, Lw}
+ * what = 1: box grid of stage `stage` (mmh_box.cu)                                       -> out = {g0, g1, g2, threads, nt, ls}
+ * returns MMH_ERR_UNSUPPORTED when the kernel does not take the shape (the caller then uses another kernel).          */
+int mmh_debug_plan(int what, int ndim, const int64_t *shape, int stage, int *out6);
+
 #ifdef __cplusplus
 }
 #endif

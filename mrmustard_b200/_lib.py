@@ -29,7 +29,7 @@ SYMBOLS = [
     "mmh_binomial", "mmh_binomial_host",
     "mmh_diagonal", "mmh_diagonal_host", "mmh_1leftover", "mmh_1leftover_host",
     "mmh_diagonal_grad", "mmh_diagonal_grad_host", "mmh_1leftover_grad", "mmh_1leftover_grad_host",
-    "mmh_forward_contract", "mmh_forward_contract_host", "mmh_debug_timeline",
+    "mmh_forward_contract", "mmh_forward_contract_host", "mmh_debug_timeline", "mmh_debug_plan",
 ]
 
 
@@ -62,6 +62,7 @@ def _load() -> ctypes.CDLL:
         "mmh_forward_contract": ([i64, ci, p64, ci, vp, vp, vp, vp, ci, vp], ci),
         "mmh_forward_contract_host": ([i64, ci, p64, ci, vp, vp, vp, vp, ci], ci),
         "mmh_debug_timeline": ([vp], ci),
+        "mmh_debug_plan": ([ci, ci, p64, ci, ctypes.POINTER(ci)], ci),
         "mmh_forward_panel_range": ([ci, p64, vp, vp, vp, ci, i64, i64, i64, vp], ci),
         "mmh_forward_batched_host": ([i64, ci, p64, vp, vp, vp, vp, ci], ci),
         "mmh_vjp": ([ci, p64, vp, vp, vp, vp, vp, vp, vp], ci),

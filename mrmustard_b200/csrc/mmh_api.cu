@@ -1078,6 +1078,30 @@ extern "C" int mmh_debug_timeline(unsigned long long *out64) {
     return MMH_OK;
 }
 
+// debug aid, host only: the launch plans of the batched lane / box kernels (tests/test_host_logic.py)
+extern "C" int mmh_debug_plan(int what, int ndim, const int64_t *shape, int stage, int *out6) {
+    if (!shape || !out6) return MMH_ERR_NULL_POINTER;
+    LatticeDesc d;
+    int mx;
+    int rc = make_desc(ndim, shape, &d, &mx);
+    if (rc) return rc;
+    for (int k = 0; k < 6; k++) out6[k] = 0;
+    if (what == 0) {
+        if (!mmh_plan_march_lanes(d.shape[ndim - 1], &out6[0], &out6[1], &out6[2])) return MMH_ERR_UNSUPPORTED;
+        return MMH_OK;
+    }
+    if (what == 1) {
+        if (stage < 0 || stage > ndim - 2) return MMH_ERR_BAD_SHAPE;
+        BoxParams bp;
+        int T;
+        size_t smem;
+        if (!mmh_plan_march_box(d, stage, &bp, &T, &smem)) return MMH_ERR_UNSUPPORTED;
+        out6[0] = bp.g[0]; out6[1] = bp.g[1]; out6[2] = bp.g[2]; out6[3] = T; out6[4] = bp.nt; out6[5] = bp.ls;
+        return MMH_OK;
+    }
+    return MMH_ERR_UNSUPPORTED;
+}
+
 // ---- lattice + derived-variable contraction ---------------------------------------------------------
 static int forward_contract_impl(long long batch, int ndim, const int64_t *shape, int ncore_dims, const void *dA, const void *db,
                                  const void *dcp, void *dout, int stable, cudaStream_t st) {

@@ -163,7 +163,7 @@ def test_batches_of_medium_lattices_both_schedules(S, O, monkeypatch):
         assert np.array_equal(S.vanilla_batch_numba(shape, A, b, c), want), thr
 
 
-@pytest.mark.parametrize("shape,batch", [((20, 20, 20, 20), 3), ((5, 40, 41), 7), ((3, 6, 6, 6, 6, 6), 4), ((4, 1100), 5),
+@pytest.mark.parametrize("shape,batch", [((20, 20, 20, 20), 3), ((5, 40, 41), 7), ((3, 6, 6, 6, 6, 6), 4), ((3, 6, 6, 6, 6), 4), ((4, 1100), 5),
                                          ((7, 2, 3, 300), 3), ((9, 33, 1, 37), 6)])
 def test_box_march_vs_oracle(S, O, shape, batch, monkeypatch):
     # panels above 1024 points in the one-CTA-per-lattice schedule: the box march (mmh_box.cu); MMH_PER_CTA_BATCH=1 forces

@@ -65,3 +65,55 @@ def test_binomial_defaults(backend, golden):
     G = backend.hermite_renormalized_binomial(A, b, c, (6, 6), None, None)
     want = oracle.binomial((6, 6), A, b, c, 0.99999, 11)[0]
     assert np.array_equal(G, want)
+
+
+# ---- launch plans of the batched lane / box kernels (host only, through the mmh_debug_plan export) ------------------
+def _plan(what, shape, stage=0):
+    import ctypes
+    from mrmustard_b200 import _lib
+    out = (ctypes.c_int * 6)()
+    rc = _lib.lib.mmh_debug_plan(what, len(shape), _lib.shape_array(shape), stage, out)
+    return rc, list(out)
+
+
+@pytest.mark.parametrize("n1", [1, 2, 3, 5, 16, 17, 31, 32, 33, 40, 63, 64, 100, 129, 255, 256])
+def test_lane_plan_covers_the_row(n1):
+    # mmh_lanes.cu: a lane owns R consecutive positions, ln lanes hold a row, a warp marches Lw rows
+    rc, (R, ln, Lw, *_) = _plan(0, (7, n1))
+    assert rc == 0
+    assert 2 <= R <= 8 and ln * R >= n1 > (ln - 1) * R
+    assert 1 <= Lw == 32 // ln
+
+
+def test_lane_plan_rejects_rows_beyond_a_warp():
+    assert _plan(0, (7, 257))[0] != 0      # 8 positions x 32 lanes is the widest row
+    assert _plan(0, (3, 40))[1][:3] == [5, 8, 4]   # cfg3: five positions per lane, four lattices per warp, no idle lane
+
+
+@pytest.mark.parametrize("shape", [(20, 20, 20, 20), (30, 30, 30, 30), (50, 50, 50, 50), (64, 64, 64), (5, 40, 41), (4, 1100),
+                                   (3, 6, 6, 6, 6), (7, 2, 3, 300), (9, 33, 1, 37), (12, 2000, 3)])
+def test_box_plan_invariants(shape):
+    # mmh_box.cu: boxes of <= 1024 points over the first <= 3 panel dims, two points per thread, halo <= 2 cells per thread,
+    # the shared-memory panel buffer holds box + halo + zero cell + trash cell
+    rc, (g0, g1, g2, T, nt, ls) = _plan(1, shape, 0)
+    assert rc == 0
+    g = [g0, g1, g2]
+    panel = shape[1:]
+    assert nt == min(3, len(panel))
+    inner = int(np.prod(panel[nt:]))
+    e = [-(-panel[m] // g[m]) if m < nt else 1 for m in range(3)]
+    assert all(g[m] == 1 for m in range(nt, 3)) and all(1 <= g[m] <= panel[m] for m in range(nt))
+    TS = inner * e[0] * e[1] * e[2]
+    HC = sum(TS // e[m] for m in range(3) if g[m] > 1)
+    assert TS <= 1024 and T % 32 == 0 and 64 <= T <= 512 and 2 * T >= TS and HC <= 2 * T
+    assert ls == TS + HC + 2
+    # the last index of the lattice stays whole whenever a row of it fits a box (write granularity)
+    if inner == 1 and panel[nt - 1] <= 1024:
+        assert g[nt - 1] == 1
+
+
+def test_box_plan_limits():
+    assert _plan(1, (4, 5, 6, 7, 8, 9, 10), 0)[0] != 0      # more than four panel dims: not boxed
+    assert _plan(1, (4, 2000, 2000), 1)[0] == 0             # stage 1: a 1-D panel of 2000 points, two boxes
+    assert _plan(1, (4, 2000, 2000), 1)[1][:3] == [2, 1, 1]
+    assert _plan(1, (4, 3, 2000), 5)[0] != 0                # bad stage

@@ -28,8 +28,10 @@ __device__ __forceinline__ void sts_c128_b(unsigned addr, c128 v) {
 template <int R>
 __device__ __forceinline__ void div_all_box(c128 (&v)[R], double sqs, double rsqs) {
     bool slow = false;
+#ifndef MMH_BOX_EXPERIMENT_NO_RANGE_TEST   /* timing experiment only: results are wrong for tiny / huge numerators */
 #pragma unroll
     for (int r = 0; r < R; r++) slow |= div_needs_slow(v[r].x) | div_needs_slow(v[r].y);
+#endif
     if (!slow) {
 #pragma unroll
         for (int r = 0; r < R; r++) v[r] = c_make(div_fast(v[r].x, sqs, rsqs), div_fast(v[r].y, sqs, rsqs));

@@ -46,8 +46,13 @@ __device__ __forceinline__ void div_all_box(c128 (&v)[R], double sqs, double rsq
 #define MMH_BOX_HPT 2   // halo cells per thread (the plan keeps the halo of a box <= MMH_BOX_HPT * threads)
 
 // smem (c128 cells): buf[2][ls] | sqtab[S] double2.   buf: [0, TS) own cells | [TS, TS + HC) low halo faces | zero | trash
-template <int R, int NPD>
-__global__ void __launch_bounds__(512, 1) k_march_box(BoxParams p) {
+// HIST: the two previous panels of a slot are re-read from shared memory (three rotating panel buffers) instead of living in
+// registers.  A slot then holds ~17 registers (coefficients, offsets) instead of ~63, so four slots per thread fit 128 registers
+// and two 256-thread CTAs are resident: twice the independent dependency chains per scheduler (the step is bound by the
+// instruction-level parallelism in flight), for two more shared-memory loads per amplitude.
+template <int R, int NPD, bool HIST>
+__global__ void __launch_bounds__(HIST ? 256 : 512, HIST ? 2 : 1) k_march_box(BoxParams p) {
+    constexpr int NBUF = HIST ? 3 : 2;
     extern __shared__ c128 smem[];
     const LatticeDesc &d = p.d;
     const int D = d.D, i = p.stage;
@@ -56,9 +61,9 @@ __global__ void __launch_bounds__(512, 1) k_march_box(BoxParams p) {
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
     const unsigned bstride = (unsigned)p.ls * 16u;
     const unsigned zero_off = (unsigned)(p.ls - 2) * 16u, trash_off = (unsigned)(p.ls - 1) * 16u;
-    double2 *sqtab = (double2 *)(smem + (size_t)2 * p.ls);
+    double2 *sqtab = (double2 *)(smem + (size_t)NBUF * p.ls);
     for (int s_ = tid; s_ < S; s_ += T) sqtab[s_] = make_double2(p.sq[s_], p.rsq[s_]);
-    if (tid < 2) { smem[(size_t)tid * p.ls + p.ls - 2] = c_make(0.0, 0.0); smem[(size_t)tid * p.ls + p.ls - 1] = c_make(0.0, 0.0); }
+    if (tid < NBUF) { smem[(size_t)tid * p.ls + p.ls - 2] = c_make(0.0, 0.0); smem[(size_t)tid * p.ls + p.ls - 1] = c_make(0.0, 0.0); }
     int g[3], shp[3], gst[3];
 #pragma unroll
     for (int m = 0; m < 3; m++) {
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(512, 1) k_march_box(BoxParams p) {
                 x[2] = q1 % e[2]; q1 /= e[2];
                 x[1] = q1 % e[1];
                 x[0] = q1 / e[1];
-                loco[r] = act[r] ? (unsigned)qq * 16u : trash_off;
+                loco[r] = act[r] ? (unsigned)qq * 16u : (HIST ? zero_off : trash_off);   // HIST reads through it: zero cell
                 gofs[r] = (unsigned)((lo[0] + x[0]) * gst[0] + (lo[1] + x[1]) * gst[1] + (lo[2] + x[2]) * gst[2] + rr);
                 int rem = rr;
 #pragma unroll
@@ -164,7 +169,8 @@ __global__ void __launch_bounds__(512, 1) k_march_box(BoxParams p) {
             for (int r = 0; r < R; r++) {
                 h0[r] = c_make(0.0, 0.0);
                 h1[r] = act[r] ? __ldcg(G + gofs[r]) : c_make(0.0, 0.0);
-                sts_c128_b(sbase + loco[r], h1[r]);
+                sts_c128_b(sbase + (act[r] ? loco[r] : trash_off), h1[r]);
+                if (HIST) sts_c128_b(sbase + 2u * bstride + (act[r] ? loco[r] : trash_off), c_make(0.0, 0.0));   // "panel -1"
             }
 #pragma unroll
             for (int w = 0; w < MMH_BOX_HPT; w++)
@@ -206,6 +212,42 @@ __global__ void __launch_bounds__(512, 1) k_march_box(BoxParams p) {
             double2 tq = sqtab[S > 1 ? 1 : 0];
             double sqs = tq.x, rsqs = tq.y;
             int s = 1;
+            if constexpr (HIST) {
+                unsigned bpp = sbase + 2u * bstride, bprev = sbase, bcur = sbase + bstride;   // panels s-2, s-1, s
+#pragma unroll 1
+                for (; s < S; s++) {
+                    const double2 tn = sqtab[s + 1 < S ? s + 1 : s];
+                    c128 hv[MMH_BOX_HPT];
+#pragma unroll
+                    for (int w = 0; w < MMH_BOX_HPT; w++) hv[w] = hact[w] ? __ldcg(gpan + hgo[w]) : c_make(0.0, 0.0);
+                    c128 v[R];
+                    const c128 as = c_scale(a00, sqm);
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        c128 nbv[NPD];
+                        const c128 P1 = lds_c128_b(bprev + loco[r]), P2 = lds_c128_b(bpp + loco[r]);
+#pragma unroll
+                        for (int jj = 0; jj < NPD; jj++) nbv[jj] = lds_c128_b(bprev + nbo[r][jj]);
+                        v[r] = c_mul(b0, P1);
+                        v[r] = c_add(v[r], c_mul(as, P2));
+#pragma unroll
+                        for (int jj = 0; jj < NPD; jj++) v[r] = c_add(v[r], c_mul(coef[r][jj], nbv[jj]));
+                    }
+                    div_all_box<R>(v, sqs, rsqs);
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        sts_c128_b(bcur + (act[r] ? loco[r] : trash_off), v[r]);
+                        if (act[r]) gpan[gofs[r]] = v[r];
+                    }
+#pragma unroll
+                    for (int w = 0; w < MMH_BOX_HPT; w++)
+                        if (hact[w]) sts_c128_b(bcur + halo_off + 16u * (unsigned)(w * T + tid), hv[w]);
+                    gpan += P;
+                    sqm = sqs; sqs = tn.x; rsqs = tn.y;
+                    const unsigned tmp = bpp; bpp = bprev; bprev = bcur; bcur = tmp;
+                    __syncthreads();
+                }
+            }
 #pragma unroll 1
             for (; s + 1 < S; s += 2) {
                 const double2 t1 = sqtab[s + 1];
@@ -223,7 +265,16 @@ __global__ void __launch_bounds__(512, 1) k_march_box(BoxParams p) {
 }
 
 // plan: boxes of <= 2 * 512 points (R = 2) over the first <= 3 panel dims, halo <= MMH_BOX_HPT * threads
+// slots per thread: 2 = the two previous panels in registers (default), 4 = in shared memory (HIST, MMH_BOX_R=4).  Measured,
+// 592 lattices: (20,)^4 0.693 / 0.751 ms, (30,)^4 3.85 / 3.91 ms, (64,)^3 0.862 / 0.808 ms (R = 2 / R = 4): twice the chains in
+// flight buy nothing, an SM marches ~1000 points per microsecond either way.
+int mmh_box_slots() {
+    const char *e = getenv("MMH_BOX_R");
+    return (e && atoi(e) == 4) ? 4 : 2;
+}
+
 bool mmh_plan_march_box(const LatticeDesc &d, int stage, BoxParams *bp, int *T_out, size_t *smem_out) {
+    const int Rb = mmh_box_slots();
     const int npd = d.D - 1 - stage;
     if (npd < 1 || npd > 4) return false;
     const long long P = d.strides[stage];
@@ -255,7 +306,7 @@ bool mmh_plan_march_box(const LatticeDesc &d, int stage, BoxParams *bp, int *T_o
                 if (TS > max_ts) continue;
                 long long HC = 0;
                 for (int m = 0; m < 3; m++) if (g[m] > 1) HC += TS / e[m];
-                int T = (int)((TS + 1) / 2 + 31) / 32 * 32;
+                int T = (int)((TS + Rb - 1) / Rb + 31) / 32 * 32;
                 if (T < 64) T = 64;
                 if (HC > (long long)MMH_BOX_HPT * T) continue;
                 const long long tiles = (long long)g0 * g1 * g2;
@@ -269,7 +320,7 @@ bool mmh_plan_march_box(const LatticeDesc &d, int stage, BoxParams *bp, int *T_o
         }
     }
     if (best_tiles < 0) return false;
-    const size_t smem = sizeof(c128) * ((size_t)2 * bLS + (size_t)S);
+    const size_t smem = sizeof(c128) * ((size_t)(Rb == 4 ? 3 : 2) * bLS + (size_t)S);
     if (smem > 200 * 1024) return false;
     memset(bp, 0, sizeof(*bp));
     bp->d = d; bp->stage = stage; bp->nt = nt; bp->ls = bLS;
@@ -279,21 +330,25 @@ bool mmh_plan_march_box(const LatticeDesc &d, int stage, BoxParams *bp, int *T_o
 }
 
 // grid: one CTA per lattice up to one resident wave (the CTAs then take further lattices in turn)
+template <int R, int NPD, bool HIST>
+static cudaError_t launch_box(const BoxParams &p, int sm_count, int T, size_t smem, cudaStream_t st) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_march_box<R, NPD, HIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_march_box<R, NPD, HIST>, T, smem) != cudaSuccess || occ < 1) occ = 1;
+    long long grid = (long long)occ * sm_count;
+    if (grid > p.batch) grid = p.batch;
+    k_march_box<R, NPD, HIST><<<(unsigned)grid, T, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t mmh_launch_march_box(const BoxParams &p, int sm_count, int T, size_t smem, cudaStream_t st) {
     const int npd = p.d.D - 1 - p.stage;
-#define MMH_CASE(N)                                                                                                      \
-    case N: {                                                                                                            \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_march_box<2, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        int occ = 1;                                                                                                     \
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_march_box<2, N>, T, smem) != cudaSuccess || occ < 1) occ = 1; \
-        long long grid = (long long)occ * sm_count;                                                                      \
-        if (grid > p.batch) grid = p.batch;                                                                              \
-        k_march_box<2, N><<<(unsigned)grid, T, smem, st>>>(p);                                                           \
-        return cudaGetLastError();                                                                                       \
-    }
+    const bool hist = mmh_box_slots() == 4;
     switch (npd) {
-        MMH_CASE(1) MMH_CASE(2) MMH_CASE(3) MMH_CASE(4)
+        case 1: return hist ? launch_box<4, 1, true>(p, sm_count, T, smem, st) : launch_box<2, 1, false>(p, sm_count, T, smem, st);
+        case 2: return hist ? launch_box<4, 2, true>(p, sm_count, T, smem, st) : launch_box<2, 2, false>(p, sm_count, T, smem, st);
+        case 3: return hist ? launch_box<4, 3, true>(p, sm_count, T, smem, st) : launch_box<2, 3, false>(p, sm_count, T, smem, st);
+        case 4: return hist ? launch_box<4, 4, true>(p, sm_count, T, smem, st) : launch_box<2, 4, false>(p, sm_count, T, smem, st);
         default: return cudaErrorInvalidValue;
     }
-#undef MMH_CASE
 }

@@ -172,6 +172,8 @@ def test_box_march_vs_oracle(S, O, shape, batch, monkeypatch):
     A, b, c = random_triple(len(shape), (batch,), seed=41)
     G = S.vanilla_batch_numba(shape, A, b, c)
     assert np.array_equal(G, O.vanilla_batch(shape, A, b, c))
+    monkeypatch.setenv("MMH_BOX_R", "4")     # panel history in shared memory, four slots per thread
+    assert np.array_equal(G, S.vanilla_batch_numba(shape, A, b, c))
     monkeypatch.setenv("MMH_NO_BOX", "1")
     assert np.array_equal(G, S.vanilla_batch_numba(shape, A, b, c))
 

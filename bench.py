@@ -357,7 +357,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                 "wall_ms_per_step": e2e_wall_ms / e2e_steps,
                 "h2d_bytes_per_step": int(hA.nbytes + hb.nbytes + hc.nbytes), "d2h_bytes_per_step": int(amps_per_step * 16),
-                "api": "mrmustard_b200.strategies.vanilla_numba -> mmh_forward_host (pinned result buffer)"},
+                "api": ("mrmustard_b200.strategies.vanilla_numba -> mmh_forward_host (pinned result buffer)" if w["batch"] is None else
+                        "mrmustard_b200.strategies.vanilla_batch_numba -> mmh_forward_batched_host (pinned result buffer)")},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,

@@ -35,6 +35,8 @@ extern "C" {
 #define MMH_ERR_UNSUPPORTED (-5)   /* combination not implemented by the CUDA path               -> NotImplementedError */
 #define MMH_ERR_NO_DEVICE (-6)     /* no CUDA device / wrong architecture                        -> RuntimeError */
 #define MMH_ERR_TOO_LARGE (-7)     /* lattice does not fit the index type / device memory        -> MemoryError */
+#define MMH_ERR_TIMEOUT (-8)       /* a device-side watchdog of an EARLIER call on this device expired (its result is
+                                      invalid); the library state has been reset, the call may be retried -> RuntimeError */
 
 #define MMH_MAX_DIM 32
 

@@ -17,7 +17,7 @@ SO_PATH = os.path.join(_HERE, "csrc", "libmmhermite.so")
 MMH_OK = 0
 _EXC = {
     -1: ValueError, -2: ValueError, -3: ValueError, -4: ValueError,
-    -5: NotImplementedError, -6: RuntimeError, -7: MemoryError,
+    -5: NotImplementedError, -6: RuntimeError, -7: MemoryError, -8: RuntimeError,
 }
 
 # every symbol include/mmhermite.h declares (tests/test_abi.py checks the header against this list)

@@ -1,6 +1,6 @@
 """Operator-level mirror of the reference's `math.hermite_renormalized*` entry points.
 
-`hermite_renormalized` reproduces BackendManager.hermite_renormalized's batching semantics
+`hermite_renormalized` is restated from BackendManager.hermite_renormalized's batching semantics
 (mrmustard/math/backend_manager.py:643-727: fully batched / b-batched / unbatched, batch flatten and
 reshape, `stable or settings.STABLE_FOCK_CONVERSION`, the out-shape check and its ValueError);
 `hermite_renormalized_batched` and `hermite_renormalized_binomial` reproduce the BackendNumpy methods
@@ -81,8 +81,13 @@ def hermite_renormalized_1leftoverMode(A, b, c, output_cutoff, pnr_cutoffs, stab
         (-2, -1, *tuple(range(len(pnr_cutoffs)))))
 
 
-def hermite_renormalized(A, b, c, shape, stable=False, out=None):
-    """BackendManager.hermite_renormalized (backend_manager.py:643-727)."""
+def hermite_renormalized(A, b, c, shape, stable=False, out=None, device=False):
+    """BackendManager.hermite_renormalized, restated from backend_manager.py:643-727 (same three batching branches, same
+    out-shape check and error strings).  device=True is this package's extension: A, b, c are CUDA tensors, the result is a CUDA
+    tensor on the same device with autograd attached and nothing crosses PCIe (mrmustard_b200.device)."""
+    if device:
+        from . import device as _device
+        return _device.hermite_renormalized(A, b, c, shape, stable or _reference_settings().STABLE_FOCK_CONVERSION, out)
     A = np.asarray(A)
     b = np.asarray(b)
     c = np.asarray(c)

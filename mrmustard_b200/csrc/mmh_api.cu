@@ -15,10 +15,16 @@
 
 
 
+// A failed runtime call leaves its code in the runtime's last-error slot; clear it so that the NEXT API call does not fail at its
+// first cudaGetLastError() for something that happened here.  Device out-of-memory is the documented MemoryError class.
+static inline int ck_fail(cudaError_t e) {
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? MMH_ERR_TOO_LARGE : (int)e;
+}
 #define CK(call)                                   \
     do {                                           \
         cudaError_t e_ = (call);                   \
-        if (e_ != cudaSuccess) return (int)e_;     \
+        if (e_ != cudaSuccess) return ck_fail(e_); \
     } while (0)
 
 static std::atomic<long long> g_launches{0};
@@ -45,6 +51,11 @@ struct DeviceCtx {
     Scratch lattice_ws;           // lattice kept on the device by mmh_forward_contract
     Scratch ones;                 // vacuum amplitudes c = 1 of mmh_forward_contract
     Scratch host_slots[8];        // staging for the *_host entry points
+    int *err_host = nullptr;      // mapped page-locked word the watchdogs of the polling kernels set when they give up
+    int *err_dev = nullptr;       // its device alias
+    cudaStream_t last_stream = nullptr;   // stream of the previous call that used the shared scratch (see enter_stream)
+    bool have_last = false;
+    cudaEvent_t xstream_ev = nullptr;
 };
 static DeviceCtx g_ctx[64];
 
@@ -71,6 +82,9 @@ static int ensure_tables(DeviceCtx &c, int need) {
     CK(cudaMalloc(&c.rsq, sizeof(double) * len));
     CK(cudaMemcpy(c.sq, hs.data(), sizeof(double) * len, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c.rsq, hr.data(), sizeof(double) * len, cudaMemcpyHostToDevice));
+    // the copies ran on the legacy default stream, which non-blocking streams (every torch side stream) do not synchronise
+    // with: make the tables globally visible before any caller's stream can read them (once per table growth)
+    CK(cudaDeviceSynchronize());
     c.table_len = len;
     return 0;
 }
@@ -92,11 +106,53 @@ static int get_ctx(DeviceCtx **out) {
         c.cc_major = prop.major;
         CK(cudaMalloc(&c.barrier, 64 * sizeof(unsigned)));
         CK(cudaMemset(c.barrier, 0, 64 * sizeof(unsigned)));
+        CK(cudaHostAlloc((void **)&c.err_host, sizeof(int), cudaHostAllocMapped));
+        *c.err_host = 0;
+        CK(cudaHostGetDevicePointer((void **)&c.err_dev, c.err_host, 0));
+        CK(cudaEventCreateWithFlags(&c.xstream_ev, cudaEventDisableTiming));
+        CK(cudaDeviceSynchronize());   // legacy-stream initialisation done before any non-blocking stream runs
         c.init = true;
     }
     *out = &c;
     return 0;
 }
+
+// The per-device scratch (exchange buffer + its sentinel state, VJP partials, compactFock workspace, lattice workspace, grid-barrier
+// counters) is ONE set shared by every call.  Calls on one stream are ordered by the stream; a call on a DIFFERENT stream than the
+// previous one first waits (on the device, no host block) for everything enqueued so far on the previous stream, so two streams
+// never run library kernels on the same scratch concurrently.  Single-stream callers pay nothing.  Callers hold g_mutex.
+static int enter_stream(DeviceCtx *ctx, cudaStream_t st) {
+    if (ctx->have_last && ctx->last_stream != st) {
+        cudaError_t e = cudaEventRecord(ctx->xstream_ev, ctx->last_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ctx->xstream_ev, 0);
+        if (e != cudaSuccess) {   // the previous stream was destroyed meanwhile: its work is complete or abandoned; order by a full sync
+            cudaGetLastError();
+            CK(cudaDeviceSynchronize());
+        }
+    }
+    ctx->last_stream = st;
+    ctx->have_last = true;
+    return MMH_OK;
+}
+
+// A polling kernel whose watchdog expired (a producer never delivered: a bug or a lost CTA) marched on with sentinel NaNs and left
+// the exchange buffer dirty.  The flag it raised is reported by the next call on the device (and by the host-pointer entry points
+// right after their own synchronisation): the exchange buffer is re-filled with the sentinel and MMH_ERR_TIMEOUT is returned.
+static int check_watchdog(DeviceCtx *ctx, cudaStream_t st) {
+    if (!ctx->err_host || *(volatile int *)ctx->err_host == 0) return MMH_OK;
+    CK(cudaDeviceSynchronize());
+    *(volatile int *)ctx->err_host = 0;
+    if (ctx->xbuf.ptr) CK(cudaMemsetAsync(ctx->xbuf.ptr, 0xFF, ctx->xbuf.bytes, st));
+    return MMH_ERR_TIMEOUT;
+}
+
+static int begin_call(DeviceCtx *ctx, cudaStream_t st) {
+    int rc = check_watchdog(ctx, st);
+    if (rc) return rc;
+    return enter_stream(ctx, st);
+}
+// host-pointer entry points: after their own synchronisation, report a watchdog that expired during THIS call
+static int end_host_call(DeviceCtx *ctx) { return check_watchdog(ctx, 0); }
 
 static int make_desc(int ndim, const int64_t *shape, LatticeDesc *d, int *maxdim) {
     if (ndim < 1 || ndim > MMH_MAX_DIM) return MMH_ERR_BAD_NDIM;
@@ -176,8 +232,17 @@ static int forward_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st, b
         if (d.shape[i] == 1 || getenv("MMH_NO_BOX") || !mmh_plan_march_box(d, i, &bp[i], &T[i], &sm[i])) return MMH_OK;
         box[i] = true;
     }
-    g_launches++;
-    CK(mmh_launch_chain(p, st));
+    // stage D-2 of a real batch runs on the warp-synchronous lane march (mmh_lanes.cu), which then also computes the chain
+    // (stage D-1) of its lattices itself: one launch instead of two, panel 0 never re-read from HBM
+    int Rl = 0, ln = 0, Lw = 0;
+    const bool lanes = d.D >= 2 && !box[d.D - 2] && p.batch >= 256 && d.shape[d.D - 2] > 1 && d.shape[d.D - 2] <= 4096 &&
+                       !getenv("MMH_NO_LANES") && mmh_plan_march_lanes(d.shape[d.D - 1], &Rl, &ln, &Lw) &&
+                       (long long)Lw * d.N < (1LL << 32);   // 32-bit store offsets
+    const bool fuse_chain = lanes && !getenv("MMH_NO_FUSE_CHAIN");
+    if (!fuse_chain) {
+        g_launches++;
+        CK(mmh_launch_chain(p, st));
+    }
     for (int i = d.D - 2; i >= 0; i--) {
         if (d.shape[i] == 1) continue;   // nothing to march
         if (box[i]) {
@@ -193,10 +258,8 @@ static int forward_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st, b
         sp.c = p.c; sp.fuse_chain = 0; sp.pdl = 0; sp.timeline = nullptr; sp.fill_n = 0;
         const long long grid = (p.batch + L[i] - 1) / L[i];
         g_launches++;
-        // stage D-2 of a real batch: the warp-synchronous march (mmh_lanes.cu; no shared-memory neighbours, no CTA barrier)
-        int Rl, ln, Lw;
-        if (i == d.D - 2 && p.batch >= 256 && d.shape[i] <= 4096 && !getenv("MMH_NO_LANES") &&
-            mmh_plan_march_lanes(d.shape[d.D - 1], &Rl, &ln, &Lw) && (long long)Lw * d.N < (1LL << 32)) {   // 32-bit store offsets
+        if (i == d.D - 2 && lanes) {
+            sp.fuse_chain = fuse_chain ? 1 : 0;
             CK(mmh_launch_march_lanes(sp, Rl, ln, Lw, st));
             continue;
         }
@@ -324,7 +387,7 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
     if (!ctx->timeline.ptr) {
         int rc0;
         if ((rc0 = ensure_scratch(ctx->timeline, 256 * sizeof(unsigned long long)))) return rc0;
-        CK(cudaMemset(ctx->timeline.ptr, 0, 256 * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(ctx->timeline.ptr, 0, 256 * sizeof(unsigned long long), st));
     }
     bool chain_done = false, first = true;
     int rc;
@@ -358,7 +421,7 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
             const size_t xtotal = xslot * (size_t)kMaxInFlight;
             if (ctx->xbuf.bytes < xtotal || !ctx->xbuf.ptr) {   // every kernel's exchange buffer, before any is launched
                 if ((rc = ensure_scratch(ctx->xbuf, xtotal))) return rc;
-                CK(cudaMemset(ctx->xbuf.ptr, 0xFF, ctx->xbuf.bytes));
+                CK(cudaMemsetAsync(ctx->xbuf.ptr, 0xFF, ctx->xbuf.bytes, st));   // on the caller's stream: ordered before its kernels
             }
             xbase = xslot * (size_t)(seq % kMaxInFlight);
             pipelined = overlap1;   // the first kernel is then the one-warp tail, which fills panel 0 with the sentinel itself
@@ -419,6 +482,7 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
         }
         if (0) {
         } else if (plan_march_tiled_cached(d, i, ctx->sm_count, &tp, &R, &ntiles, &sm)) {
+            tp.err = ctx->err_dev;
             tp.A = p.A; tp.b = p.b; tp.G = p.G; tp.sq = p.sq; tp.rsq = p.rsq; tp.timeline = (unsigned long long *)ctx->timeline.ptr + 64 * (seq % kMaxInFlight);
             tp.pdl = (use_pdl && !first) ? 1 : 0;
             first = false;
@@ -428,7 +492,7 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
                 const size_t xbytes = xoff + sizeof(c128) * (size_t)ntiles * d.shape[i] * tp.hc_max;
                 if (ctx->xbuf.bytes < xbytes || !ctx->xbuf.ptr) {
                     if ((rc = ensure_scratch(ctx->xbuf, xbytes))) return rc;
-                    CK(cudaMemset(ctx->xbuf.ptr, 0xFF, ctx->xbuf.bytes));
+                    CK(cudaMemsetAsync(ctx->xbuf.ptr, 0xFF, ctx->xbuf.bytes, st));
                 }
                 tp.X = (c128 *)((char *)ctx->xbuf.ptr + xoff);
             }
@@ -483,6 +547,7 @@ static int forward_impl(long long batch, int ndim, const int64_t *shape, const v
     if (!dA || !db || !dc || !dG) return MMH_ERR_NULL_POINTER;
     DeviceCtx *ctx;
     if ((rc = get_ctx(&ctx))) return rc;
+    if ((rc = begin_call(ctx, st))) return rc;
     if ((rc = ensure_tables(*ctx, mx + 1))) return rc;
 
     FwdParams p;
@@ -574,6 +639,7 @@ static int vjp_impl(long long batch, int ndim, const int64_t *shape, const void 
     if (!dG || !dc || !dg || !oA || !ob || !oc) return MMH_ERR_NULL_POINTER;
     DeviceCtx *ctx;
     if ((rc = get_ctx(&ctx))) return rc;
+    if ((rc = begin_call(ctx, st))) return rc;
     if ((rc = ensure_tables(*ctx, mx + 1))) return rc;
     VjpParams p;
     p.d = d;
@@ -625,6 +691,7 @@ static int binomial_impl(int ndim, const int64_t *shape, const void *dA, const v
     if (!dA || !db || !dc || !dG) return MMH_ERR_NULL_POINTER;
     DeviceCtx *ctx;
     if ((rc = get_ctx(&ctx))) return rc;
+    if ((rc = begin_call(ctx, st))) return rc;
     if ((rc = ensure_tables(*ctx, mx + 1))) return rc;
     if ((rc = ensure_scratch(ctx->norm, sizeof(double)))) return rc;
     long long maxlevel = 0;
@@ -682,6 +749,7 @@ static int diagonal_impl(int M, const int64_t *cutoffs, int L0, const void *dA, 
     DeviceCtx *ctx;
     int rc;
     if ((rc = get_ctx(&ctx))) return rc;
+    if ((rc = begin_call(ctx, st))) return rc;
     if ((rc = ensure_tables(*ctx, mx + 3))) return rc;
     const long long naux = 2LL * Md + Md + 2LL * Md * (Md > 1 ? Md - 1 : 1);
     const size_t bytes = sizeof(c128) * (size_t)naux * (size_t)q.E;
@@ -748,6 +816,7 @@ static int diagonal_grad_impl(int Mtot, const int64_t *cutoffs, int L0, const vo
     DeviceCtx *ctx;
     int rc;
     if ((rc = get_ctx(&ctx))) return rc;
+    if ((rc = begin_call(ctx, st))) return rc;
     if ((rc = ensure_tables(*ctx, mx + 3))) return rc;
     const long long naux = 2LL * M + M + 2LL * M * (M > 1 ? M - 1 : 1);   // arr1, arr2, arr1010, arr1001
     const size_t nval = (size_t)(naux + 1) * (size_t)Pv;
@@ -803,7 +872,7 @@ static int diagonal_host_impl(int M, const int64_t *cutoffs, int L0, const void 
     if ((rc = diagonal_impl(M, cutoffs, L0, dA, dB, nbatch, dG0, dout, 0))) return rc;
     CK(cudaMemcpyAsync(out, dout, sizeof(c128) * n, cudaMemcpyDeviceToHost, 0));
     CK(cudaStreamSynchronize(0));
-    return MMH_OK;
+    return end_host_call(ctx);
 }
 
 // ---- host staging ---------------------------------------------------------------------------------
@@ -829,6 +898,7 @@ const char *mmh_error_string(int status) {
         case MMH_ERR_UNSUPPORTED: return "not supported by the CUDA path";
         case MMH_ERR_NO_DEVICE: return "no usable CUDA device (an sm_100 GPU is required; there is no CPU fallback)";
         case MMH_ERR_TOO_LARGE: return "lattice too large";
+        case MMH_ERR_TIMEOUT: return "a device-side watchdog of an earlier call expired (that call's result is invalid); state reset, retry";
         default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "unknown error";
     }
 }
@@ -871,6 +941,7 @@ int mmh_forward_panel_range(int ndim, const int64_t *shape, const void *dA, cons
     if (f_lo == f_hi) return MMH_OK;
     DeviceCtx *ctx;
     if ((rc = get_ctx(&ctx))) return rc;
+    if ((rc = begin_call(ctx, (cudaStream_t)stream))) return rc;
     if ((rc = ensure_tables(*ctx, mx + 1))) return rc;
     FwdParams p;
     memset(&p, 0, sizeof(p));
@@ -911,7 +982,7 @@ int mmh_forward_batched_host(int64_t batch, int ndim, const int64_t *shape, cons
     if ((rc = forward_impl(batch, ndim, shape, dA, db, dc, dG, stable, 0))) return rc;
     CK(cudaMemcpyAsync(G, dG, sizeof(c128) * batch * (size_t)d.N, cudaMemcpyDeviceToHost, 0));
     CK(cudaStreamSynchronize(0));
-    return MMH_OK;
+    return end_host_call(ctx);
 }
 
 int mmh_forward_host(int ndim, const int64_t *shape, const void *A, const void *b, const void *c, void *G,
@@ -955,7 +1026,7 @@ int mmh_vjp_batched_host(int64_t batch, int ndim, const int64_t *shape, const vo
     CK(cudaMemcpyAsync(ob, dbo, sizeof(c128) * batch * D, cudaMemcpyDeviceToHost, 0));
     CK(cudaMemcpyAsync(oc, dco, sizeof(c128) * batch, cudaMemcpyDeviceToHost, 0));
     CK(cudaStreamSynchronize(0));
-    return MMH_OK;
+    return end_host_call(ctx);
 }
 
 int mmh_vjp_host(int ndim, const int64_t *shape, const void *G, const void *c, const void *dLdG, void *oA,
@@ -1023,7 +1094,7 @@ static int diagonal_grad_host_impl(int M, const int64_t *cutoffs, int L0, const 
     CK(cudaMemcpyAsync(o_dA, d1, sizeof(c128) * P * n2 * n2, cudaMemcpyDeviceToHost, 0));
     CK(cudaMemcpyAsync(o_dB, d2, sizeof(c128) * P * n2, cudaMemcpyDeviceToHost, 0));
     CK(cudaStreamSynchronize(0));
-    return MMH_OK;
+    return end_host_call(ctx);
 }
 int mmh_1leftover(int M, const int64_t *cutoffs, const void *dA, const void *dB, const void *dG0, void *dout,
                   void *stream) {
@@ -1061,7 +1132,7 @@ int mmh_binomial_host(int ndim, const int64_t *shape, const void *A, const void 
     if ((rc = binomial_impl(ndim, shape, dA, db, dc, max_l2, global_cutoff, dG, norm_out, 0))) return rc;
     CK(cudaMemcpyAsync(G, dG, sizeof(c128) * (size_t)d.N, cudaMemcpyDeviceToHost, 0));
     CK(cudaStreamSynchronize(0));
-    return MMH_OK;
+    return end_host_call(ctx);
 }
 
 }  // extern "C"
@@ -1118,6 +1189,7 @@ static int forward_contract_impl(long long batch, int ndim, const int64_t *shape
     if (nd > (1LL << 30)) return MMH_ERR_TOO_LARGE;
     DeviceCtx *ctx;
     if ((rc = get_ctx(&ctx))) return rc;
+    if ((rc = begin_call(ctx, st))) return rc;
     if ((size_t)batch * (size_t)d.N > ((size_t)150 << 30) / sizeof(c128)) return MMH_ERR_TOO_LARGE;
     if ((rc = ensure_scratch(ctx->lattice_ws, sizeof(c128) * (size_t)batch * (size_t)d.N))) return rc;
     if (ctx->ones.bytes < sizeof(c128) * (size_t)batch) {
@@ -1160,5 +1232,5 @@ extern "C" int mmh_forward_contract_host(int64_t batch, int ndim, const int64_t 
     if ((rc = forward_contract_impl(batch, ndim, shape, ncore_dims, dA, db, dcp, dout, stable, 0))) return rc;
     CK(cudaMemcpyAsync(out, dout, sizeof(c128) * batch * ncore, cudaMemcpyDeviceToHost, 0));
     CK(cudaStreamSynchronize(0));
-    return MMH_OK;
+    return end_host_call(ctx);
 }

@@ -38,19 +38,46 @@ __device__ __forceinline__ int xp_index(int q) { return (R & 1) ? q : q + (q >> 
 
 #define MMH_LANES_XP(R) (36 * (R))   // cells of one transposition buffer
 
-// smem: sqtab[S] double2 | xp[warps][2][MMH_LANES_XP(R)] c128
-template <int R>
+// FUSE: the CTA first computes stage D-1 of its nw * Lw lattices itself -- the 1-D chain G[n] = (b G[n-1] + A sqrt(n-1) G[n-2]) /
+// sqrt(n) along the last index (vanilla/core.py:85-104 with i = D-1; arithmetic of k_fwd_chain, operation for operation), one
+// thread per lattice, into a shared-memory row per lattice -- instead of a separate chain kernel writing panel 0 to HBM and this
+// kernel reading it back: one launch per batch, no 39-step latency-bound kernel in front of the march (cfg3: 24 of 302 us), and
+// panel 0 leaves through the same coalesced transposition as every other panel.
+// smem: sqtab[max(S, FUSE ? n1 : 0)] double2 | xp[warps][2][MMH_LANES_XP(R)] c128 | FUSE: chain[nw * Lw][n1 | 1] c128
+template <int R, bool FUSE>
 __global__ void __launch_bounds__(128) k_march_lanes(StageParams p, int ln, int Lw) {
     extern __shared__ c128 smem[];
     const LatticeDesc &d = p.d;
     const int D = d.D, i = D - 2;
     const int n1 = d.shape[D - 1], S = d.shape[i];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int ntab = (FUSE && n1 > S) ? n1 : S;
     double2 *sqt = (double2 *)smem;
-    c128 *xp = smem + S + (size_t)warp * 2 * MMH_LANES_XP(R);
+    c128 *xp = smem + ntab + (size_t)warp * 2 * MMH_LANES_XP(R);
+    c128 *chain = smem + ntab + (size_t)nw * 2 * MMH_LANES_XP(R);
+    const int cpitch = n1 | 1;
     pdl_launch_dependents_l();
-    for (int n = threadIdx.x; n < S; n += blockDim.x) sqt[n] = make_double2(p.sq[n], p.rsq[n]);
+    for (int n = threadIdx.x; n < ntab; n += blockDim.x) sqt[n] = make_double2(p.sq[n], p.rsq[n]);
     __syncthreads();
+    if (FUSE) {
+        const long long cl = (long long)blockIdx.x * nw * Lw + threadIdx.x;   // this thread's chain
+        if ((int)threadIdx.x < nw * Lw && cl < p.batch) {
+            const c128 Ac = p.A[cl * D * D + (D - 1) * D + (D - 1)], bc = p.b[cl * D + (D - 1)];
+            c128 *row = chain + (size_t)threadIdx.x * cpitch;
+            c128 p1 = p.c[cl], p2 = c_make(0.0, 0.0);
+            row[0] = p1;
+            double sqm = 0.0;
+            for (int s = 1; s < n1; s++) {
+                const double2 t = sqt[s];
+                c128 v = c_mul(bc, p1);
+                if (s >= 2) v = c_add(v, c_mul(c_scale(Ac, sqm), p2));
+                v = c_div_table(v, t.x, t.y);
+                row[s] = v;
+                p2 = p1; p1 = v; sqm = t.x;
+            }
+        }
+        __syncthreads();
+    }
     const long long wl0 = ((long long)blockIdx.x * nw + warp) * Lw;   // first lattice of this warp
     if (wl0 >= p.batch) return;
     const int nlat = (int)(p.batch - wl0 < Lw ? p.batch - wl0 : Lw);
@@ -63,7 +90,8 @@ __global__ void __launch_bounds__(128) k_march_lanes(StageParams p, int ln, int 
     const c128 b0 = p.b[l * D + i], a00 = p.A[l * D * D + i * D + i], a01 = p.A[l * D * D + i * D + i + 1];
     c128 h0[R], h1[R], coef[R];
     {
-        const c128 *g0 = p.G + l * p.lat_stride;   // panel 0 (k_i = 0) was written by the chain kernel
+        // panel 0 (k_i = 0): this CTA's chain rows (FUSE) or what the chain kernel wrote
+        const c128 *g0 = FUSE ? chain + (size_t)(warp * Lw + (lane_act ? lw : 0)) * cpitch : p.G + l * p.lat_stride;
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int k1 = k0 + r;
@@ -113,6 +141,17 @@ __global__ void __launch_bounds__(128) k_march_lanes(StageParams p, int ln, int 
     }
 
     c128 *xb0 = xp, *xb1 = xp + MMH_LANES_XP(R);
+    if (FUSE) {   // panel 0 leaves like every other panel: lane-major in, warp-linear (coalesced) out
+#pragma unroll
+        for (int r = 0; r < R; r++) xb1[xp_index<R>(lane * R + r)] = h1[r];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const c128 w = xb1[xp_index<R>(j * 32 + lane)];
+            if (go[j] != 0xFFFFFFFFu) gs[go[j]] = w;
+        }
+        __syncwarp();
+    }
     double sqm = 0.0;
     double2 t = sqt[S > 1 ? 1 : 0];
     double sqs = t.x, rsqs = t.y;
@@ -150,17 +189,26 @@ cudaError_t mmh_launch_march_lanes(const StageParams &p, int R, int ln, int Lw, 
     const int block = 128, nw = block / 32;
     const long long grid = (p.batch + (long long)nw * Lw - 1) / ((long long)nw * Lw);
     if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-    const int S = p.d.shape[p.d.D - 2];
-#define MMH_CASE(N)                                                                                                    \
-    case N: {                                                                                                          \
-        const size_t smem = sizeof(c128) * ((size_t)S + (size_t)nw * 2 * MMH_LANES_XP(N));                             \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_march_lanes<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        k_march_lanes<N><<<(unsigned)grid, block, smem, st>>>(p, ln, Lw);                                              \
+    const int S = p.d.shape[p.d.D - 2], n1 = p.d.shape[p.d.D - 1];
+    const bool fuse = p.fuse_chain != 0;
+    const size_t ntab = (fuse && n1 > S) ? n1 : S;
+#define MMH_LAUNCH(N, F)                                                                                               \
+    {                                                                                                                  \
+        const size_t smem = sizeof(c128) * (ntab + (size_t)nw * 2 * MMH_LANES_XP(N) +                                  \
+                                            ((F) ? (size_t)nw * Lw * (size_t)(n1 | 1) : 0));                           \
+        if (smem > 200 * 1024) return cudaErrorInvalidValue;                                                           \
+        if (smem > 48 * 1024) {                                                                                        \
+            cudaError_t e = cudaFuncSetAttribute(k_march_lanes<N, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                                            \
+        }                                                                                                              \
+        k_march_lanes<N, F><<<(unsigned)grid, block, smem, st>>>(p, ln, Lw);                                           \
         return cudaGetLastError();                                                                                     \
     }
+#define MMH_CASE(N) case N: if (fuse) MMH_LAUNCH(N, true) else MMH_LAUNCH(N, false)
     switch (R) {
         MMH_CASE(2) MMH_CASE(3) MMH_CASE(4) MMH_CASE(5) MMH_CASE(6) MMH_CASE(7) MMH_CASE(8)
         default: return cudaErrorInvalidValue;
     }
 #undef MMH_CASE
+#undef MMH_LAUNCH
 }

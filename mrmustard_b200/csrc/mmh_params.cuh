@@ -82,6 +82,7 @@ struct TiledParams {
     int pdl;                     // 1: launched with programmatic stream serialization
     int poll0;                   // 1: the previous stage's kernel is still running: do not wait for its completion, validate
                                  //    every panel-0 amplitude by the sentinel the host pre-filled it with (stage overlap)
+    int *err;                    // device alias of the context's watchdog word: set to 1 when a poll gives up (mmh_api.cu check_watchdog)
     unsigned long long *trace;   // debug timeline [tile][step][8] of %globaltimer stamps (MMH_TRACE_FILE), else NULL
     unsigned long long *timeline;   // per-launch debug stamps (mmh_common.cuh timeline_stamp), may be NULL
 };

@@ -50,7 +50,7 @@ __device__ __forceinline__ void stg_relaxed_v2(void *p, unsigned long long a, un
     asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 // panel-0 amplitude that may not have been written yet (stage overlap): poll until both words differ from the sentinel
-__device__ __forceinline__ c128 poll_c128(const c128 *p, unsigned long long t_giveup) {
+__device__ __forceinline__ c128 poll_c128(const c128 *p, unsigned long long t_giveup, int *err) {
     unsigned long long a, b;
     unsigned spins = 0;
     ldg_relaxed_v2(p, a, b);
@@ -58,6 +58,7 @@ __device__ __forceinline__ c128 poll_c128(const c128 *p, unsigned long long t_gi
         __nanosleep(100);
         ldg_relaxed_v2(p, a, b);
     }
+    if ((a == MMH_SENTINEL || b == MMH_SENTINEL) && err) *(volatile int *)err = 1;   // watchdog expired: reported by the next API call
     return make_double2(__longlong_as_double((long long)a), __longlong_as_double((long long)b));
 }
 // shared memory through 32-bit addresses (byte offsets in the shared window)
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
         if (tid == 0) {
             const long long last = (long long)(lo[0] + e[0] - 1) * gst[0] + (long long)(lo[1] + e[1] - 1) * gst[1] +
                                    (long long)(lo[2] + e[2] - 1) * gst[2] + inner - 1;
-            (void)poll_c128(p.G + last, t_giveup0);
+            (void)poll_c128(p.G + last, t_giveup0, p.err);
         }
         __syncthreads();
     }
@@ -272,12 +273,12 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
         const int loa = a == 0 ? lo[0] : lo[1], ga = a == 0 ? gst[0] : gst[1];
         const int lob = b == 1 ? lo[1] : lo[2], gb = b == 1 ? gst[1] : gst[2];
         const int go = (lom - 1) * gm + (loa + xa) * ga + (lob + xb) * gb + rr;
-        sts_c128(sbase + halo_off + 16u * (unsigned)c, p.poll0 ? poll_c128(p.G + go, t_giveup0) : __ldcg(p.G + go));
+        sts_c128(sbase + halo_off + 16u * (unsigned)c, p.poll0 ? poll_c128(p.G + go, t_giveup0, p.err) : __ldcg(p.G + go));
     }
 #pragma unroll
     for (int r = 0; r < R; r++) {
         h0[r] = c_make(0.0, 0.0);
-        h1[r] = (flags[r] & 1u) ? (p.poll0 ? poll_c128(p.G + gofs[r], t_giveup0) : __ldcg(p.G + gofs[r])) : c_make(0.0, 0.0);
+        h1[r] = (flags[r] & 1u) ? (p.poll0 ? poll_c128(p.G + gofs[r], t_giveup0, p.err) : __ldcg(p.G + gofs[r])) : c_make(0.0, 0.0);
         if (tidc >= 0) sts_c128(sbase + loco[r], h1[r]);
     }
     __syncthreads();
@@ -323,7 +324,10 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
                             sts_c128(dst + 16u * (unsigned)(c0 + 32 * w), make_double2(__longlong_as_double((long long)a[w]), __longlong_as_double((long long)b[w])));
                         }
                     if (!__any_sync(0xffffffffu, pend != 0u)) break;
-                    if ((++rounds & 255u) == 0u && gtimer_ns() > t_giveup) break;
+                    if ((++rounds & 255u) == 0u && gtimer_ns() > t_giveup) {
+                        if (p.err) *(volatile int *)p.err = 1;
+                        break;
+                    }
                     if (lane < 3 && can_h) {   // wait for the faces' canaries before polling whole faces again
                         unsigned long long a_, b_;
                         unsigned spins = 0;

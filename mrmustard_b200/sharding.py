@@ -132,57 +132,78 @@ class CudaPanelOps:
                                               G.data_ptr(), 0, int(step), int(f_lo), int(f_hi), self._stream()))
 
 
+class SingleLatticePlan:
+    """ONE lattice, stage 0 sharded over the ranks of the default process group by panel ranges; `run()` fills this rank's
+    full-size buffer `G` (the complete sub-lattice k_0 = 0 plus this rank's range of every panel and its halos) and can be
+    called repeatedly (bench.py --workload cfg4).  Device buffers and the send/recv schedule are built once."""
+
+    def __init__(self, shape, A, b, c, ops=None):
+        self.shape = tuple(int(s) for s in shape)
+        if len(self.shape) < 2:
+            raise ValueError("forward_single_sharded needs at least two modes")
+        self.dist, self.rank, self.world = _dist()
+        self.ops = ops if ops is not None else CudaPanelOps()
+        self.A, self.b, self.c = A, b, c
+        self.N = int(np.prod(self.shape, dtype=np.int64))
+        self.S0 = self.shape[0]
+        self.P = self.N // self.S0
+        self.H = int(np.prod(self.shape[2:], dtype=np.int64))    # strides[1]: the deepest look-back inside panel s - 1
+        self.G = self.ops.alloc(self.N)
+        self.ranges = [shard_range(self.P, r, self.world) for r in range(self.world)]
+        self.f_lo, self.f_hi = self.ranges[self.rank]
+        # halo schedule of one step: (peer, lo, hi, is_send); rank q needs [f_lo_q - H, f_lo_q) of panel s from the ranks below it
+        self.sched = []
+        for q in range(self.world):
+            need_lo, need_hi = max(self.ranges[q][0] - self.H, 0), self.ranges[q][0]
+            for r in range(q):
+                lo, hi = max(self.ranges[r][0], need_lo), min(self.ranges[r][1], need_hi)
+                if hi <= lo:
+                    continue
+                if self.rank == r:
+                    self.sched.append((q, lo, hi, True))
+                elif self.rank == q:
+                    self.sched.append((r, lo, hi, False))
+        self.ops.prepare(self.shape, A, b)
+
+    def run(self):
+        import torch
+        dist, ops, G, P = self.dist, self.ops, self.G, self.P
+        ops.sublattice(G, self.shape, self.A, self.b, self.c)                 # panel 0, redundantly on every rank
+        Gr = torch.view_as_real(G)                                            # NCCL/gloo p2p on the (re, im) view
+        for s in range(1, self.S0):
+            ops.panel_range(G, self.shape, s, self.f_lo, self.f_hi)
+            if self.sched and s < self.S0 - 1:
+                reqs = [dist.P2POp(dist.isend if snd else dist.irecv, Gr[s * P + lo: s * P + hi], peer)
+                        for peer, lo, hi, snd in self.sched]
+                for w in dist.batch_isend_irecv(reqs):
+                    w.wait()
+        return G
+
+    def gather(self):
+        """The full lattice on every rank: rank r owns columns [f_lo_r, f_hi_r) of the (S0 - 1, P) matrix of panels 1..S0-1."""
+        import torch
+        if self.world == 1:
+            return self.G
+        dist, G, P, S0 = self.dist, self.G, self.P, self.S0
+        maxw = max(hi - lo for lo, hi in self.ranges)
+        body = G[P:].view(S0 - 1, P)
+        send = torch.zeros((S0 - 1, maxw), dtype=torch.complex128, device=G.device)
+        send[:, : self.f_hi - self.f_lo] = body[:, self.f_lo:self.f_hi]
+        recv = [torch.empty_like(torch.view_as_real(send)) for _ in range(self.world)]
+        dist.all_gather(recv, torch.view_as_real(send).contiguous())
+        for r, (lo, hi) in enumerate(self.ranges):
+            if r != self.rank:
+                body[:, lo:hi] = torch.view_as_complex(recv[r])[:, : hi - lo]
+        return G
+
+
 def forward_single_sharded(shape, A, b, c, gather=True, ops=None):
     """hermite_renormalized (vanilla rule) of ONE lattice, stage 0 sharded over the ranks of the default process group.
 
     Returns the full lattice on every rank (gather=True) or (G_local, (f_lo, f_hi)) where G_local is this rank's full-size
     buffer holding the complete sub-lattice k_0 = 0 and, for k_0 >= 1, this rank's range of every panel (plus halos)."""
-    import torch
-    shape = tuple(int(s) for s in shape)
-    D = len(shape)
-    if D < 2:
-        raise ValueError("forward_single_sharded needs at least two modes")
-    dist, rank, world = _dist()
-    if ops is None:
-        ops = CudaPanelOps()
-    N = int(np.prod(shape, dtype=np.int64))
-    S0 = shape[0]
-    P = N // S0
-    H = int(np.prod(shape[2:], dtype=np.int64))          # strides[1]: the deepest look-back inside panel s - 1
-    G = ops.alloc(N)
-    ops.sublattice(G, shape, A, b, c)                     # panel 0, redundantly on every rank
-    ops.prepare(shape, A, b)
-    ranges = [shard_range(P, r, world) for r in range(world)]
-    f_lo, f_hi = ranges[rank]
-    Gr = torch.view_as_real(G)                            # NCCL/gloo p2p on the (re, im) view
-    for s in range(1, S0):
-        ops.panel_range(G, shape, s, f_lo, f_hi)
-        if world > 1 and s < S0 - 1:
-            reqs = []
-            for q in range(world):                        # rank q needs [f_lo_q - H, f_lo_q) of panel s from lower ranks
-                need_lo, need_hi = max(ranges[q][0] - H, 0), ranges[q][0]
-                for r in range(q):
-                    lo, hi = max(ranges[r][0], need_lo), min(ranges[r][1], need_hi)
-                    if hi <= lo:
-                        continue
-                    view = Gr[s * P + lo: s * P + hi]
-                    if rank == r:
-                        reqs.append(dist.P2POp(dist.isend, view, q))
-                    elif rank == q:
-                        reqs.append(dist.P2POp(dist.irecv, view, r))
-            if reqs:
-                for w in dist.batch_isend_irecv(reqs):
-                    w.wait()
-    if not gather or world == 1:
-        return (G, (f_lo, f_hi)) if not gather else G
-    # gather: rank r owns columns [f_lo_r, f_hi_r) of the (S0 - 1, P) matrix of panels 1..S0-1
-    maxw = max(hi - lo for lo, hi in ranges)
-    body = G[P:].view(S0 - 1, P)
-    send = torch.zeros((S0 - 1, maxw), dtype=torch.complex128, device=G.device)
-    send[:, : f_hi - f_lo] = body[:, f_lo:f_hi]
-    recv = [torch.empty_like(torch.view_as_real(send)) for _ in range(world)]
-    dist.all_gather(recv, torch.view_as_real(send).contiguous())
-    for r, (lo, hi) in enumerate(ranges):
-        if r != rank:
-            body[:, lo:hi] = torch.view_as_complex(recv[r])[:, : hi - lo]
-    return G
+    plan = SingleLatticePlan(shape, A, b, c, ops)
+    plan.run()
+    if not gather:
+        return plan.G, (plan.f_lo, plan.f_hi)
+    return plan.gather()

@@ -15,7 +15,33 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("MMH_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# baseline/_ref: `pip install --no-index --no-deps --target baseline/_ref /root/reference` (git-ignored, travels to the GPU
+# box with the gpurun snapshot) -- the unmodified reference package, used by `bench.py --impl reference`, by bench.py's
+# cpu_baseline leg and by tests/test_dropin_gpu.py where /root/reference itself does not exist.
+STAGED_ROOT = os.path.join(_REPO, "baseline", "_ref")
+
+
+def _pick_root() -> str:
+    for cand in (os.environ.get("MMH_REFERENCE_ROOT"), "/root/reference", STAGED_ROOT):
+        if cand and os.path.isdir(os.path.join(cand, "mrmustard")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
+
+
+def stage(force: bool = False) -> bool:
+    """Install the unmodified reference into baseline/_ref (build container only; needs /root/reference)."""
+    import subprocess
+    if os.path.isdir(os.path.join(STAGED_ROOT, "mrmustard")) and not force:
+        return True
+    if not os.path.isdir("/root/reference/mrmustard"):
+        return False
+    cmd = [sys.executable, "-m", "pip", "install", "--no-index", "--no-build-isolation", "--no-deps", "--find-links",
+           "/opt/wheelhouse", "--target", STAGED_ROOT, "--upgrade", "/root/reference"]
+    return subprocess.call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) == 0
 
 
 def available() -> bool:
@@ -45,6 +71,7 @@ def install_shims(with_lab: bool = False) -> None:
         raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
     if not _done:
         os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/mmh_numba_cache")
+        os.environ.setdefault("NUMBA_NUM_THREADS", str(os.cpu_count() or 1))
         _v = _md.version
         _md.version = lambda n: "1.0.0a1" if n == "mrmustard" else _v(n)
         if "opt_einsum" not in sys.modules:

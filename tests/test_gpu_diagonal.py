@@ -142,6 +142,26 @@ def test_leftover_jacobians_finite_differences(mm, gd):
             assert np.allclose((fwd(Ap, b2, c) - G) / eps, want, rtol=1e-4, atol=1e-6), f"dA[{i},{l}]"
 
 
+@pytest.fixture(scope="module")
+def glg():
+    return np.load(os.path.join(GOLDEN, "leftover_grad_golden.npz"))
+
+
+def test_leftover_jacobians_golden(mm, glg):
+    """grad_hermite_multidimensional_1leftoverMode vs the reference's own forward-mode Jacobians
+    (singleLeftoverMode_grad.py:560-724, run as plain Python by tests/golden/gen_golden_leftover_grad.py) at the north_star
+    gate 1e-10 rel / 1e-14 abs.  Inputs are stored already interleaved."""
+    for name in glg["cases"]:
+        A2, b2, c = glg[f"{name}_A"], glg[f"{name}_b"], complex(glg[f"{name}_c"])
+        cut = tuple(int(x) for x in glg[f"{name}_cut"])
+        G = mm.strategies.hermite_multidimensional_1leftoverMode(A2, b2, c, cut)
+        assert_parity(np.ascontiguousarray(G), glg[f"{name}_G"], name + " amplitudes")
+        dG0, dA, dB = mm.strategies.grad_hermite_multidimensional_1leftoverMode(A2, b2, c, G)
+        assert_parity(dG0, glg[f"{name}_dG0"], name + " dG0")
+        assert_parity(dA, glg[f"{name}_dA"], name + " dA")
+        assert_parity(dB, glg[f"{name}_dB"], name + " dB")
+
+
 def test_eight_mode_ket_diagonal_vs_vanilla_lattice(mm, golden):
     """cfg4 as written in BASELINE.json (8-mode Gaussian ket, diagonal strategy): the diagonal of the density matrix of a ket is
     |psi_n|^2, so the M = 8 diagonal sweep (A 16x16) must reproduce the squared moduli of the 8-mode vanilla lattice.  The reference

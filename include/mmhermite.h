@@ -168,6 +168,41 @@ int mmh_1leftover(int M, const int64_t *cutoffs, const void *dA, const void *dB,
 int mmh_1leftover_host(int M, const int64_t *cutoffs, const void *A, const void *B, const void *G0,
                        void *arr0_out);
 
+/* gate-specific Fock strategies -------------------------------------------------------------
+ * What Dgate / Sgate / BSgate / SqueezedVacuum.fock_array call instead of the generic lattice (BackendNumpy.displacement /
+ * beamsplitter / squeezed / squeezer, math/backend_numpy.py:452-475).  Device-pointer entry points enqueue on `stream`.
+ *
+ * replaces: strategies.squeezer(shape=(M, N), r, theta)   (strategies/squeezer.py:29-66)    -> S[M, N]
+ *           strategies.squeezed(cutoff, r, theta)         (squeezer.py:127-147)             -> S[cutoff]
+ *           strategies.beamsplitter(shape4, theta, phi)   (strategies/beamsplitter.py:37-91; stable = 0)
+ *           strategies.stable_beamsplitter(shape4, ...)   (beamsplitter.py:94-172;          stable = 1) -> G[M, N, P, Q]
+ *           strategies.displacement(cutoffs=(c0, c1), alpha) (strategies/displacement.py:24-65) -> D[c0, c1]
+ * The squeezer / squeezed / beamsplitter results are bit-identical to the numba strategies (same IEEE operations in the same
+ * order, libm scalars); the displacement evaluates log / exp per element and agrees within 1e-10 relative.                 */
+int mmh_squeezer(int64_t M, int64_t N, double r, double theta, void *dS, void *stream);
+int mmh_squeezed(int64_t cutoff, double r, double theta, void *dS, void *stream);
+int mmh_beamsplitter(const int64_t *shape4, double theta, double phi, int stable, void *dG, void *stream);
+int mmh_displacement(int64_t c0, int64_t c1, double alpha_re, double alpha_im, void *dD, void *stream);
+/* what = 0 squeezer(shape2, r, theta) | 1 squeezed(shape1, r, theta) | 2 beamsplitter(shape4, theta, phi) |
+ *        3 stable_beamsplitter(shape4, theta, phi) | 4 displacement(shape2, Re alpha, Im alpha); HOST output pointer             */
+int mmh_gate_host(int what, const int64_t *shape, double a0, double a1, void *out);
+
+/* replaces: strategies.jacobian_displacement(D[M, N], alpha) -> (dD/dalpha, dD/dconj(alpha))     (displacement.py:117-139)
+ *           strategies.grad_displacement(T[c, c], r, phi)    -> (dT/dr, dT/dphi)                 (displacement.py:85-114)       */
+int mmh_displacement_jacobian(int64_t M, int64_t N, const void *dD, double alpha_re, double alpha_im, void *d_jac_alpha,
+                              void *d_jac_alphac, void *stream);
+int mmh_displacement_grad(int64_t cutoff, const void *dT, double r, double phi, void *d_grad_r, void *d_grad_phi, void *stream);
+/* what = 0 jacobian (a0, a1 = Re alpha, Im alpha) | 1 grad (a0, a1 = r, phi); HOST pointers                                     */
+int mmh_displacement_derivs_host(int what, int64_t M, int64_t N, const void *D, double a0, double a1, void *o1, void *o2);
+
+/* replaces: the lattice reductions of strategies.beamsplitter_vjp (kind 0, ndim 4; beamsplitter.py:175-243), squeezer_vjp (kind 1,
+ *           ndim 2; squeezer.py:69-124) and squeezed_vjp (kind 2, ndim 1; squeezer.py:150-191): the sums over the gate's support
+ *           of dLdG[k] * vanilla_step_grad(G, k) (lattice/steps.py:145-171).
+ * out[ndim*ndim + ndim + 1] = un-symmetrised upper-triangular dLdA | dLdb | sum(G * dLdG); the chain rule to (theta, phi) /
+ * (r, phi) is a handful of scalar operations done by the caller (mrmustard_b200/strategies.py).                               */
+int mmh_gate_vjp(int kind, int ndim, const int64_t *shape, const void *dG, const void *ddLdG, void *dout, void *stream);
+int mmh_gate_vjp_host(int kind, int ndim, const int64_t *shape, const void *G, const void *dLdG, void *out);
+
 /* debug aid, not part of the reference interface: 4 (lattice index mod 4) x 16 x 4 %globaltimer stamps (entry, dependency wait passed, first step,
  * exit of CTA 0) of the last single-lattice forward's kernels; synchronises the device.                          */
 int mmh_debug_timeline(unsigned long long *out64);

@@ -30,6 +30,8 @@ SYMBOLS = [
     "mmh_diagonal", "mmh_diagonal_host", "mmh_1leftover", "mmh_1leftover_host",
     "mmh_diagonal_grad", "mmh_diagonal_grad_host", "mmh_1leftover_grad", "mmh_1leftover_grad_host",
     "mmh_forward_contract", "mmh_forward_contract_host", "mmh_debug_timeline", "mmh_debug_plan",
+    "mmh_squeezer", "mmh_squeezed", "mmh_beamsplitter", "mmh_displacement", "mmh_gate_host",
+    "mmh_displacement_jacobian", "mmh_displacement_grad", "mmh_displacement_derivs_host", "mmh_gate_vjp", "mmh_gate_vjp_host",
 ]
 
 
@@ -79,6 +81,16 @@ def _load() -> ctypes.CDLL:
         "mmh_1leftover_grad_host": ([ci, p64, vp, vp, vp, vp, vp, vp], ci),
         "mmh_1leftover": ([ci, p64, vp, vp, vp, vp, vp], ci),
         "mmh_1leftover_host": ([ci, p64, vp, vp, vp, vp], ci),
+        "mmh_squeezer": ([i64, i64, dbl, dbl, vp, vp], ci),
+        "mmh_squeezed": ([i64, dbl, dbl, vp, vp], ci),
+        "mmh_beamsplitter": ([p64, dbl, dbl, ci, vp, vp], ci),
+        "mmh_displacement": ([i64, i64, dbl, dbl, vp, vp], ci),
+        "mmh_gate_host": ([ci, p64, dbl, dbl, vp], ci),
+        "mmh_displacement_jacobian": ([i64, i64, vp, dbl, dbl, vp, vp, vp], ci),
+        "mmh_displacement_grad": ([i64, vp, dbl, dbl, vp, vp, vp], ci),
+        "mmh_displacement_derivs_host": ([ci, i64, i64, vp, dbl, dbl, vp, vp], ci),
+        "mmh_gate_vjp": ([ci, ci, p64, vp, vp, vp, vp], ci),
+        "mmh_gate_vjp_host": ([ci, ci, p64, vp, vp, vp], ci),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)

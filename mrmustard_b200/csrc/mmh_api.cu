@@ -50,6 +50,7 @@ struct DeviceCtx {
     Scratch timeline;             // 16 x 4 debug stamps of the last forward launches
     Scratch lattice_ws;           // lattice kept on the device by mmh_forward_contract
     Scratch ones;                 // vacuum amplitudes c = 1 of mmh_forward_contract
+    Scratch gate_ws;              // gate strategies: log-factorial table, transposition buffer, masked cotangent
     Scratch host_slots[8];        // staging for the *_host entry points
     int *err_host = nullptr;      // mapped page-locked word the watchdogs of the polling kernels set when they give up
     int *err_dev = nullptr;       // its device alias
@@ -260,7 +261,7 @@ static int forward_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st, b
         g_launches++;
         if (i == d.D - 2 && lanes) {
             sp.fuse_chain = fuse_chain ? 1 : 0;
-            CK(mmh_launch_march_lanes(sp, Rl, ln, Lw, st));
+            CK(mmh_launch_march_lanes(sp, Rl, ln, Lw, ctx->sm_count, st));
             continue;
         }
         CK(mmh_launch_march_stage(sp, R[i], (int)grid, T[i], sm[i], st));
@@ -653,7 +654,7 @@ static int vjp_impl(long long batch, int ndim, const int64_t *shape, const void 
         int Rl, ln, Lw;
         if (ndim == 2 && batch >= 256 && d.shape[0] > 1 && !getenv("MMH_NO_LANES") && mmh_plan_march_lanes(d.shape[1], &Rl, &ln, &Lw)) {
             g_launches++;
-            CK(mmh_launch_vjp_lanes(p, Rl, ln, Lw, st));
+            CK(mmh_launch_vjp_lanes(p, Rl, ln, Lw, ctx->sm_count, st));
             return MMH_OK;
         }
     }
@@ -1234,3 +1235,241 @@ extern "C" int mmh_forward_contract_host(int64_t batch, int ndim, const int64_t 
     CK(cudaStreamSynchronize(0));
     return end_host_call(ctx);
 }
+
+// ---- gate-specific strategies (mmh_gates.cu) ----------------------------------------------
+// The transcendental scalars are computed here, once, with libm -- the functions numba's lowering of np.cos / np.sin / np.tanh /
+// np.cosh / np.exp(1j x) on scalars calls -- so that the device recurrences start from the reference's own bits.
+static int gate_ctx(DeviceCtx **ctx, cudaStream_t st, int maxdim) {
+    int rc;
+    if ((rc = get_ctx(ctx))) return rc;
+    if ((rc = begin_call(*ctx, st))) return rc;
+    return ensure_tables(**ctx, maxdim + 2);
+}
+static int check_dims(const int64_t *shape, int n, int *mx, long long *total) {
+    if (!shape) return MMH_ERR_NULL_POINTER;
+    *mx = 1; *total = 1;
+    for (int i = 0; i < n; i++) {
+        if (shape[i] < 1 || shape[i] > (1 << 20)) return MMH_ERR_BAD_SHAPE;
+        if (shape[i] > *mx) *mx = (int)shape[i];
+        if (*total > (1LL << 36) / shape[i]) return MMH_ERR_TOO_LARGE;
+        *total *= shape[i];
+    }
+    return MMH_OK;
+}
+
+static int squeezer_impl(int64_t M, int64_t N, double r, double theta, void *dS, cudaStream_t st) {
+    const int64_t shape[2] = { M, N };
+    int mx; long long total; int rc;
+    if ((rc = check_dims(shape, 2, &mx, &total))) return rc;
+    if (!dS) return MMH_ERR_NULL_POINTER;
+    DeviceCtx *ctx;
+    if ((rc = gate_ctx(&ctx, st, mx))) return rc;
+    GateParams p; memset(&p, 0, sizeof(p));
+    p.shape[0] = (int)M; p.shape[1] = (int)N; p.sq = ctx->sq; p.out = (c128 *)dS;
+    const double t = std::tanh(r);
+    p.z0 = make_double2(std::cos(theta) * t, std::sin(theta) * t);       // np.exp(1j * theta) * np.tanh(r)   (squeezer.py:49)
+    p.r0 = 1.0 / std::cosh(r);                                          // sechr                              (:51)
+    p.r1 = std::sqrt(p.r0);                                             // S[0, 0]                            (:53)
+    g_launches++;
+    CK(mmh_launch_squeezer(p, st));
+    return MMH_OK;
+}
+static int squeezed_impl(int64_t cutoff, double r, double theta, void *dS, cudaStream_t st) {
+    const int64_t shape[1] = { cutoff };
+    int mx; long long total; int rc;
+    if ((rc = check_dims(shape, 1, &mx, &total))) return rc;
+    if (!dS) return MMH_ERR_NULL_POINTER;
+    DeviceCtx *ctx;
+    if ((rc = gate_ctx(&ctx, st, mx))) return rc;
+    GateParams p; memset(&p, 0, sizeof(p));
+    p.shape[0] = (int)cutoff; p.sq = ctx->sq; p.out = (c128 *)dS;
+    const double t = -std::tanh(r);
+    p.z0 = make_double2(std::cos(theta) * t, std::sin(theta) * t);       // np.exp(1j * theta) * -np.tanh(r)  (squeezer.py:140)
+    p.r1 = std::sqrt(1.0 / std::cosh(r));                               // S[0]                               (:141)
+    g_launches++;
+    CK(mmh_launch_squeezed(p, st));
+    return MMH_OK;
+}
+static int beamsplitter_impl(const int64_t *shape, double theta, double phi, int stable, void *dG, cudaStream_t st) {
+    int mx; long long total; int rc;
+    if ((rc = check_dims(shape, 4, &mx, &total))) return rc;
+    if (!dG) return MMH_ERR_NULL_POINTER;
+    DeviceCtx *ctx;
+    if ((rc = gate_ctx(&ctx, st, mx))) return rc;
+    GateParams p; memset(&p, 0, sizeof(p));
+    for (int i = 0; i < 4; i++) p.shape[i] = (int)shape[i];
+    p.sq = ctx->sq; p.out = (c128 *)dG;
+    p.r0 = std::cos(theta);                                             // ct                                 (beamsplitter.py:59)
+    const double s = std::sin(theta);
+    p.z0 = make_double2(s * std::cos(phi), s * std::sin(phi));          // st = np.sin(theta) * np.exp(1j * phi) (:60)
+    long long launches = 0;
+    CK(mmh_launch_beamsplitter(p, stable != 0, &launches, st));
+    g_launches += launches;
+    return MMH_OK;
+}
+static int displacement_impl(int64_t c0, int64_t c1, double are, double aim, void *dD, cudaStream_t st) {
+    const int64_t shape[2] = { c0, c1 };
+    int mx; long long total; int rc;
+    if ((rc = check_dims(shape, 2, &mx, &total))) return rc;
+    if (!dD) return MMH_ERR_NULL_POINTER;
+    DeviceCtx *ctx;
+    if ((rc = gate_ctx(&ctx, st, mx))) return rc;
+    const bool flipped = c0 < c1;                                       // displacement.py:40-43
+    const int N = (int)(flipped ? c1 : c0), M = (int)(flipped ? c0 : c1);
+    // log_k_fac = cumsum(log(arange(max) with rng[0] = 1))  (displacement.py:46-48), built on the host, staged per call
+    std::vector<double> lf(mx);
+    double acc = 0.0;
+    for (int k = 0; k < mx; k++) { acc += std::log(k == 0 ? 1.0 : (double)k); lf[k] = acc; }
+    const size_t lf_bytes = (sizeof(double) * (size_t)mx + 255) / 256 * 256;
+    if ((rc = ensure_scratch(ctx->gate_ws, lf_bytes + (flipped ? sizeof(c128) * (size_t)total : 0)))) return rc;
+    CK(cudaMemcpyAsync(ctx->gate_ws.ptr, lf.data(), sizeof(double) * (size_t)mx, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));   // lf is a local
+    GateParams p; memset(&p, 0, sizeof(p));
+    p.shape[0] = N; p.shape[1] = M; p.flag = flipped ? 1 : 0; p.sq = ctx->sq;
+    c128 *work = flipped ? (c128 *)((char *)ctx->gate_ws.ptr + lf_bytes) : (c128 *)dD;
+    p.out = work;
+    p.r1 = std::hypot(are, aim);                                        // r = np.abs(alpha)
+    p.r2 = std::atan2(aim, are);                                        // phi = np.angle(alpha)
+    p.r0 = p.r1 * p.r1;                                                 // r ** 2.0
+    g_launches += 2;
+    CK(mmh_launch_displacement(p, (const double *)ctx->gate_ws.ptr, st));
+    if (flipped) { g_launches++; CK(mmh_launch_transpose(work, (c128 *)dD, N, M, st)); }
+    return MMH_OK;
+}
+static int disp_derivs_impl(int kind, int64_t M, int64_t N, const void *dD, double a0, double a1, void *o1, void *o2, cudaStream_t st) {
+    const int64_t shape[2] = { M, N };
+    int mx; long long total; int rc;
+    if ((rc = check_dims(shape, 2, &mx, &total))) return rc;
+    if (!dD || !o1 || !o2) return MMH_ERR_NULL_POINTER;
+    DeviceCtx *ctx;
+    if ((rc = gate_ctx(&ctx, st, mx))) return rc;
+    GateParams p; memset(&p, 0, sizeof(p));
+    p.shape[0] = (int)M; p.shape[1] = (int)N; p.sq = ctx->sq;
+    if (kind == 0) p.z0 = make_double2(a0, a1);                         // alpha
+    else {                                                              // (r, phi)
+        p.r1 = a0; p.r0 = std::cos(a1); p.r2 = std::sin(a1);
+        p.z0 = make_double2(a0 * p.r0, a0 * p.r2);                      // alpha = r * exp(1j * phi)
+    }
+    g_launches++;
+    CK(mmh_launch_disp_derivs(p, (const c128 *)dD, (c128 *)o1, (c128 *)o2, kind, st));
+    return MMH_OK;
+}
+// out: [ndim * ndim] un-symmetrised upper-triangular sums U | [ndim] dLdb | [1] sum(G * dLdG over the support)
+static int gate_vjp_impl(int kind, int ndim, const int64_t *shape, const void *dG, const void *dg, void *dout, cudaStream_t st) {
+    const int want = kind == 0 ? 4 : (kind == 1 ? 2 : 1);
+    if (kind < 0 || kind > 2 || ndim != want) return MMH_ERR_BAD_NDIM;
+    int mx; long long total; int rc;
+    if ((rc = check_dims(shape, ndim, &mx, &total))) return rc;
+    if (!dG || !dg || !dout) return MMH_ERR_NULL_POINTER;
+    DeviceCtx *ctx;
+    if ((rc = gate_ctx(&ctx, st, mx))) return rc;
+    const int nout = ndim * ndim + ndim + 1;
+    const size_t head = (sizeof(c128) * (size_t)(nout + 1) + 255) / 256 * 256;
+    if ((rc = ensure_scratch(ctx->gate_ws, head + sizeof(c128) * (size_t)total))) return rc;
+    c128 *sym = (c128 *)ctx->gate_ws.ptr, *one = sym + nout, *gm = (c128 *)((char *)ctx->gate_ws.ptr + head);
+    g_launches += 3;
+    CK(mmh_launch_fill_ones(one, 1, st));
+    CK(mmh_launch_gate_mask((const c128 *)dg, gm, total, kind, (int)shape[ndim > 1 ? 1 : 0], ndim > 2 ? (int)shape[2] : 1,
+                            ndim > 3 ? (int)shape[3] : 1, st));
+    if ((rc = vjp_impl(1, ndim, shape, dG, one, gm, sym, sym + ndim * ndim, sym + ndim * ndim + ndim, st))) return rc;
+    CK(mmh_launch_gate_unsym(sym, (c128 *)dout, ndim, st));
+    CK(cudaMemcpyAsync((c128 *)dout + ndim * ndim, sym + ndim * ndim, sizeof(c128) * (size_t)(ndim + 1), cudaMemcpyDeviceToDevice, st));
+    return MMH_OK;
+}
+
+extern "C" {
+int mmh_squeezer(int64_t M, int64_t N, double r, double theta, void *dS, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return squeezer_impl(M, N, r, theta, dS, (cudaStream_t)stream);
+}
+int mmh_squeezed(int64_t cutoff, double r, double theta, void *dS, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return squeezed_impl(cutoff, r, theta, dS, (cudaStream_t)stream);
+}
+int mmh_beamsplitter(const int64_t *shape, double theta, double phi, int stable, void *dG, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return beamsplitter_impl(shape, theta, phi, stable, dG, (cudaStream_t)stream);
+}
+int mmh_displacement(int64_t c0, int64_t c1, double alpha_re, double alpha_im, void *dD, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return displacement_impl(c0, c1, alpha_re, alpha_im, dD, (cudaStream_t)stream);
+}
+int mmh_displacement_jacobian(int64_t M, int64_t N, const void *dD, double alpha_re, double alpha_im, void *d_jac_alpha,
+                              void *d_jac_alphac, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return disp_derivs_impl(0, M, N, dD, alpha_re, alpha_im, d_jac_alpha, d_jac_alphac, (cudaStream_t)stream);
+}
+int mmh_displacement_grad(int64_t cutoff, const void *dT, double r, double phi, void *d_grad_r, void *d_grad_phi, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return disp_derivs_impl(1, cutoff, cutoff, dT, r, phi, d_grad_r, d_grad_phi, (cudaStream_t)stream);
+}
+int mmh_gate_vjp(int kind, int ndim, const int64_t *shape, const void *dG, const void *ddLdG, void *dout, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return gate_vjp_impl(kind, ndim, shape, dG, ddLdG, dout, (cudaStream_t)stream);
+}
+
+// host-pointer variants (numpy drop-in): what = 0 squeezer(M, N, r, theta), 1 squeezed(M, r, theta), 2 beamsplitter(shape4, theta, phi),
+// 3 stable_beamsplitter, 4 displacement(c0, c1, alpha)
+int mmh_gate_host(int what, const int64_t *shape, double a0, double a1, void *out) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (!shape || !out) return MMH_ERR_NULL_POINTER;
+    const int nd = what == 1 ? 1 : ((what == 2 || what == 3) ? 4 : 2);
+    if (what < 0 || what > 4) return MMH_ERR_UNSUPPORTED;
+    int mx; long long total; int rc;
+    if ((rc = check_dims(shape, nd, &mx, &total))) return rc;
+    DeviceCtx *ctx;
+    if ((rc = get_ctx(&ctx))) return rc;
+    void *dout;
+    if ((rc = stage_in(*ctx, 3, nullptr, sizeof(c128) * (size_t)total, &dout))) return rc;
+    switch (what) {
+        case 0: rc = squeezer_impl(shape[0], shape[1], a0, a1, dout, 0); break;
+        case 1: rc = squeezed_impl(shape[0], a0, a1, dout, 0); break;
+        case 2: rc = beamsplitter_impl(shape, a0, a1, 0, dout, 0); break;
+        case 3: rc = beamsplitter_impl(shape, a0, a1, 1, dout, 0); break;
+        default: rc = displacement_impl(shape[0], shape[1], a0, a1, dout, 0); break;
+    }
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, dout, sizeof(c128) * (size_t)total, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    return end_host_call(ctx);
+}
+// what = 0 jacobian_displacement(D[M, N], alpha) -> (jac_alpha, jac_alphac); 1 grad_displacement(T[c, c], r, phi) -> (grad_r, grad_phi)
+int mmh_displacement_derivs_host(int what, int64_t M, int64_t N, const void *D, double a0, double a1, void *o1, void *o2) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (!D || !o1 || !o2) return MMH_ERR_NULL_POINTER;
+    if (what < 0 || what > 1) return MMH_ERR_UNSUPPORTED;
+    const int64_t shape[2] = { M, N };
+    int mx; long long total; int rc;
+    if ((rc = check_dims(shape, 2, &mx, &total))) return rc;
+    DeviceCtx *ctx;
+    if ((rc = get_ctx(&ctx))) return rc;
+    void *dD, *d1, *d2;
+    const size_t bytes = sizeof(c128) * (size_t)total;
+    if ((rc = stage_in(*ctx, 0, D, bytes, &dD))) return rc;
+    if ((rc = stage_in(*ctx, 4, nullptr, bytes, &d1))) return rc;
+    if ((rc = stage_in(*ctx, 5, nullptr, bytes, &d2))) return rc;
+    if ((rc = disp_derivs_impl(what, M, N, dD, a0, a1, d1, d2, 0))) return rc;
+    CK(cudaMemcpyAsync(o1, d1, bytes, cudaMemcpyDeviceToHost, 0));
+    CK(cudaMemcpyAsync(o2, d2, bytes, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    return end_host_call(ctx);
+}
+int mmh_gate_vjp_host(int kind, int ndim, const int64_t *shape, const void *G, const void *dLdG, void *out) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (!G || !dLdG || !out) return MMH_ERR_NULL_POINTER;
+    int mx; long long total; int rc;
+    if (ndim < 1 || ndim > 4) return MMH_ERR_BAD_NDIM;
+    if ((rc = check_dims(shape, ndim, &mx, &total))) return rc;
+    DeviceCtx *ctx;
+    if ((rc = get_ctx(&ctx))) return rc;
+    void *dG, *dg, *dout;
+    const size_t bytes = sizeof(c128) * (size_t)total, obytes = sizeof(c128) * (size_t)(ndim * ndim + ndim + 1);
+    if ((rc = stage_in(*ctx, 0, G, bytes, &dG))) return rc;
+    if ((rc = stage_in(*ctx, 1, dLdG, bytes, &dg))) return rc;
+    if ((rc = stage_in(*ctx, 4, nullptr, obytes, &dout))) return rc;
+    if ((rc = gate_vjp_impl(kind, ndim, shape, dG, dg, dout, 0))) return rc;
+    CK(cudaMemcpyAsync(out, dout, obytes, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    return end_host_call(ctx);
+}
+}  // extern "C"

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(128) k_march_lanes(StageParams p, int ln, int 
     const int cpitch = n1 | 1;
     pdl_launch_dependents_l();
     for (int n = threadIdx.x; n < ntab; n += blockDim.x) sqt[n] = make_double2(p.sq[n], p.rsq[n]);
+    pdl_wait();   // the caller's buffers (A, b, c, G) are touched from here on
     __syncthreads();
     if (FUSE) {
         const long long cl = (long long)blockIdx.x * nw * Lw + threadIdx.x;   // this thread's chain
@@ -185,12 +186,18 @@ bool mmh_plan_march_lanes(int n1, int *R_out, int *ln_out, int *Lw_out) {
     return best > 0.0;
 }
 
-cudaError_t mmh_launch_march_lanes(const StageParams &p, int R, int ln, int Lw, cudaStream_t st) {
-    const int block = 128, nw = block / 32;
+cudaError_t mmh_launch_march_lanes(const StageParams &p, int R, int ln, int Lw, int sm_count, cudaStream_t st) {
+    // 4 warps per CTA; 2 when the batch leaves the device less than ~8 CTAs per SM (sharded sweeps: 8,192 triples per GPU are
+    // 512 four-warp CTAs = 3.46 per SM, i.e. the SMs holding 4 set the time: +16%; 1,024 two-warp CTAs balance to 1%)
+    int block = 128;
+    if ((p.batch + 4LL * Lw - 1) / (4LL * Lw) < 8LL * sm_count) block = 64;
+    if (const char *e = getenv("MMH_LANES_BLOCK")) block = atoi(e) == 64 ? 64 : (atoi(e) == 32 ? 32 : 128);
+    const int nw = block / 32;
     const long long grid = (p.batch + (long long)nw * Lw - 1) / ((long long)nw * Lw);
     if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
     const int S = p.d.shape[p.d.D - 2], n1 = p.d.shape[p.d.D - 1];
     const bool fuse = p.fuse_chain != 0;
+    const bool pdl = !getenv("MMH_NO_PDL");
     const size_t ntab = (fuse && n1 > S) ? n1 : S;
 #define MMH_LAUNCH(N, F)                                                                                               \
     {                                                                                                                  \
@@ -201,8 +208,7 @@ cudaError_t mmh_launch_march_lanes(const StageParams &p, int R, int ln, int Lw, 
             cudaError_t e = cudaFuncSetAttribute(k_march_lanes<N, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return e;                                                                            \
         }                                                                                                              \
-        k_march_lanes<N, F><<<(unsigned)grid, block, smem, st>>>(p, ln, Lw);                                           \
-        return cudaGetLastError();                                                                                     \
+        return mmh_launch_ex(k_march_lanes<N, F>, dim3((unsigned)grid), dim3(block), smem, st, pdl, p, ln, Lw);        \
     }
 #define MMH_CASE(N) case N: if (fuse) MMH_LAUNCH(N, true) else MMH_LAUNCH(N, false)
     switch (R) {

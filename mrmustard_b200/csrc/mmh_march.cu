@@ -22,7 +22,6 @@
 // Programmatic dependent launch (sm_90+): a kernel may let its successor in the stream start its prologue early
 // (launch_dependents) and the successor blocks at `wait` until the predecessor grid has completed and flushed.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // Divide all R numerators by sqrt(s) in place.  The IEEE slow path (inf/nan/subnormal-range numerators) is a
 // single warp-level branch for the whole step, so the common path stays branch-free and v's registers are reused.

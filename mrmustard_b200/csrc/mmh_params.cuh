@@ -95,8 +95,8 @@ bool mmh_plan_march_box(const LatticeDesc &d, int stage, BoxParams *bp, int *T_o
 cudaError_t mmh_launch_march_box(const BoxParams &p, int sm_count, int T, size_t smem, cudaStream_t st);
 bool mmh_plan_march_lanes(int n1, int *R_out, int *ln_out, int *Lw_out);
 int mmh_vjp_blocks_per_sm(const VjpParams &p, int block);
-cudaError_t mmh_launch_vjp_lanes(const VjpParams &p, int R, int ln, int Lw, cudaStream_t st);
-cudaError_t mmh_launch_march_lanes(const StageParams &p, int R, int ln, int Lw, cudaStream_t st);
+cudaError_t mmh_launch_vjp_lanes(const VjpParams &p, int R, int ln, int Lw, int sm_count, cudaStream_t st);
+cudaError_t mmh_launch_march_lanes(const StageParams &p, int R, int ln, int Lw, int sm_count, cudaStream_t st);
 cudaError_t mmh_launch_contract_last(const c128 *G, const c128 *cp, c128 *out, long long nout, long long ncore, int nd, cudaStream_t st);
 cudaError_t mmh_launch_fill_sentinel(c128 *p, long long n, bool pdl, cudaStream_t st);
 cudaError_t mmh_launch_fill_ones(c128 *p, long long n, cudaStream_t st);
@@ -135,3 +135,22 @@ struct DiagTanParams {
 };
 cudaError_t mmh_launch_diagonal_tangent(DiagTanParams tp, int nlevels, long long *launches, cudaStream_t st);
 cudaError_t mmh_launch_diagonal(DiagParams q, const c128 *G0, int nlevels, long long *launches, cudaStream_t st);
+
+// gate-specific strategies (mmh_gates.cu)
+struct GateParams {
+    int shape[4];
+    int flag;            // displacement: 1 when the host swapped the cutoffs (flipped)
+    const double *sq;    // sqrt table
+    c128 *out;
+    c128 z0;             // squeezer: e^{i theta} tanh r; squeezed: e^{i theta} (-tanh r); beamsplitter: st = sin(theta) e^{i phi};
+                         // displacement derivatives: alpha
+    double r0, r1, r2;   // squeezer: sech r, sqrt(sech r); beamsplitter: cos(theta); displacement: |alpha|^2, |alpha|, arg(alpha)
+};
+cudaError_t mmh_launch_squeezer(const GateParams &p, cudaStream_t st);
+cudaError_t mmh_launch_squeezed(const GateParams &p, cudaStream_t st);
+cudaError_t mmh_launch_beamsplitter(const GateParams &p, bool stable, long long *launches, cudaStream_t st);
+cudaError_t mmh_launch_displacement(const GateParams &p, const double *logfac, cudaStream_t st);
+cudaError_t mmh_launch_transpose(const c128 *in, c128 *out, int rows, int cols, cudaStream_t st);
+cudaError_t mmh_launch_disp_derivs(const GateParams &p, const c128 *D, c128 *o1, c128 *o2, int kind, cudaStream_t st);
+cudaError_t mmh_launch_gate_mask(const c128 *g, c128 *out, long long n_total, int kind, int s1, int s2, int s3, cudaStream_t st);
+cudaError_t mmh_launch_gate_unsym(const c128 *sym, c128 *out, int D, cudaStream_t st);

@@ -226,6 +226,8 @@ __global__ void __launch_bounds__(128) k_vjp_lanes(VjpParams p, int ln, int Lw) 
     const int n1 = d.shape[1], S = d.shape[0];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const long long wl0 = ((long long)blockIdx.x * nw + warp) * Lw;
+    pdl_trigger();
+    pdl_wait();   // G is normally the output of the kernel right before this one
     if (wl0 >= p.batch) return;
     const int nlat = (int)(p.batch - wl0 < Lw ? p.batch - wl0 : Lw);
     const double *__restrict__ sq = p.sq;
@@ -306,21 +308,25 @@ __global__ void __launch_bounds__(128) k_vjp_lanes(VjpParams p, int ln, int Lw) 
     }
 }
 
-cudaError_t mmh_launch_vjp_lanes(const VjpParams &p, int R, int ln, int Lw, cudaStream_t st) {
-    const int block = 128, nw = block / 32;
+cudaError_t mmh_launch_vjp_lanes(const VjpParams &p, int R, int ln, int Lw, int sm_count, cudaStream_t st) {
+    int block = 128;   // 2 warps per CTA when the batch leaves less than ~8 CTAs per SM (see mmh_launch_march_lanes)
+    if ((p.batch + 4LL * Lw - 1) / (4LL * Lw) < 8LL * sm_count) block = 64;
+    if (const char *e = getenv("MMH_LANES_BLOCK")) block = atoi(e) == 64 ? 64 : (atoi(e) == 32 ? 32 : 128);
+    const int nw = block / 32;
     const long long grid = (p.batch + (long long)nw * Lw - 1) / ((long long)nw * Lw);
     if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
+    const bool pdl = !getenv("MMH_NO_PDL");
+    const dim3 g((unsigned)grid), b(block);
     switch (R) {
-        case 2: k_vjp_lanes<2><<<(unsigned)grid, block, 0, st>>>(p, ln, Lw); break;
-        case 3: k_vjp_lanes<3><<<(unsigned)grid, block, 0, st>>>(p, ln, Lw); break;
-        case 4: k_vjp_lanes<4><<<(unsigned)grid, block, 0, st>>>(p, ln, Lw); break;
-        case 5: k_vjp_lanes<5><<<(unsigned)grid, block, 0, st>>>(p, ln, Lw); break;
-        case 6: k_vjp_lanes<6><<<(unsigned)grid, block, 0, st>>>(p, ln, Lw); break;
-        case 7: k_vjp_lanes<7><<<(unsigned)grid, block, 0, st>>>(p, ln, Lw); break;
-        case 8: k_vjp_lanes<8><<<(unsigned)grid, block, 0, st>>>(p, ln, Lw); break;
+        case 2: return mmh_launch_ex(k_vjp_lanes<2>, g, b, 0, st, pdl, p, ln, Lw);
+        case 3: return mmh_launch_ex(k_vjp_lanes<3>, g, b, 0, st, pdl, p, ln, Lw);
+        case 4: return mmh_launch_ex(k_vjp_lanes<4>, g, b, 0, st, pdl, p, ln, Lw);
+        case 5: return mmh_launch_ex(k_vjp_lanes<5>, g, b, 0, st, pdl, p, ln, Lw);
+        case 6: return mmh_launch_ex(k_vjp_lanes<6>, g, b, 0, st, pdl, p, ln, Lw);
+        case 7: return mmh_launch_ex(k_vjp_lanes<7>, g, b, 0, st, pdl, p, ln, Lw);
+        case 8: return mmh_launch_ex(k_vjp_lanes<8>, g, b, 0, st, pdl, p, ln, Lw);
         default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
 }
 
 template <typename IT>

@@ -13,7 +13,11 @@ from . import backend, strategies
 _saved: dict = {}
 
 _STRATEGY_NAMES = ["vanilla_numba", "stable_numba", "vanilla_batch_numba", "vanilla_vjp_numba",
-                   "vanilla_batch_vjp_numba", "binomial", "fast_diagonal"]
+                   "vanilla_batch_vjp_numba", "binomial", "fast_diagonal",
+                   # gate-specific strategies (BackendNumpy.displacement / beamsplitter / squeezed / squeezer look them up by name,
+                   # backend_numpy.py:452-475; beamsplitter_schwinger stays the reference's numpy eigendecomposition)
+                   "squeezer", "squeezed", "beamsplitter", "stable_beamsplitter", "displacement", "jacobian_displacement",
+                   "grad_displacement", "beamsplitter_vjp", "squeezer_vjp", "squeezed_vjp"]
 
 
 def install() -> None:

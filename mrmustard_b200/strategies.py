@@ -22,6 +22,8 @@ __all__ = [
     "hermite_multidimensional_diagonal", "hermite_multidimensional_1leftoverMode", "fast_diagonal",
     "grad_hermite_multidimensional_diagonal", "hermite_renormalized_diagonal_vjp",
     "grad_hermite_multidimensional_1leftoverMode", "vanilla_contract_numba",
+    "squeezer", "squeezed", "beamsplitter", "stable_beamsplitter", "displacement", "jacobian_displacement", "grad_displacement",
+    "beamsplitter_vjp", "squeezer_vjp", "squeezed_vjp",
 ]
 
 
@@ -326,3 +328,118 @@ def vanilla_contract_numba(shape, shape_derived, A, b, c_poly, stable=False) -> 
     check(lib.mmh_forward_contract_host(B, D, shape_array(full), len(shape), _p(A), _p(b), _p(c_poly), _p(out),
                                         int(bool(stable))))
     return out if batched else out.reshape(shape)
+
+
+# ---- gate-specific strategies -------------------------------------------------------------
+def _gate(what: int, shape, a0: float, a1: float) -> np.ndarray:
+    shape = _check_shape(shape)
+    out = _lib.pinned_empty(shape)
+    check(lib.mmh_gate_host(what, shape_array(shape), float(a0), float(a1), _p(out)))
+    return out
+
+
+def squeezer(shape, r, theta, dtype=np.complex128) -> np.ndarray:
+    """Fock matrix of the squeezing gate, S[out, in] (strategies/squeezer.py:29-66).  Bit-identical to the numba strategy."""
+    if len(tuple(shape)) != 2:
+        raise ValueError("squeezer expects shape = (M, N)")
+    return _gate(0, shape, r, theta)
+
+
+def squeezed(cutoff, r, theta, dtype=np.complex128) -> np.ndarray:
+    """Fock amplitudes of the single-mode squeezed vacuum (strategies/squeezer.py:127-147)."""
+    return _gate(1, (int(cutoff),), r, theta)
+
+
+def beamsplitter(shape, theta, phi, dtype=np.complex128) -> np.ndarray:
+    """Fock tensor G[out0, out1, in0, in1] of the beamsplitter (strategies/beamsplitter.py:37-91), including the reference's
+    `for n in range(N - m)` bound of the q = 0 face (:67), which leaves the face entries with out0 + out1 >= N zero."""
+    if len(tuple(shape)) != 4:
+        raise ValueError("beamsplitter expects shape = (M, N, P, Q)")
+    return _gate(2, shape, theta, phi)
+
+
+def stable_beamsplitter(shape, theta, phi) -> np.ndarray:
+    """All-pivot average of the beamsplitter recurrence (strategies/beamsplitter.py:94-172)."""
+    if len(tuple(shape)) != 4:
+        raise ValueError("stable_beamsplitter expects shape = (M, N, P, Q)")
+    return _gate(3, shape, theta, phi)
+
+
+def displacement(cutoffs, alpha, dtype=np.complex128) -> np.ndarray:
+    """Fock matrix D[out, in] of the displacement gate from the log-domain Laguerre form (strategies/displacement.py:24-65)."""
+    cutoffs = tuple(int(c) for c in cutoffs)
+    if len(cutoffs) != 2:
+        raise ValueError("displacement expects cutoffs = (N, M)")
+    alpha = complex(alpha)
+    return _gate(4, cutoffs, alpha.real, alpha.imag)
+
+
+def _disp_derivs(what: int, D, a0: float, a1: float):
+    D = _c128(D)
+    if D.ndim != 2:
+        raise ValueError("expected a 2-dimensional gate array")
+    o1 = np.empty(D.shape, np.complex128)
+    o2 = np.empty(D.shape, np.complex128)
+    check(lib.mmh_displacement_derivs_host(what, D.shape[0], D.shape[1], _p(D), float(a0), float(a1), _p(o1), _p(o2)))
+    return o1, o2
+
+
+def jacobian_displacement(D, alpha):
+    """(dD/dalpha, dD/dconj(alpha)) of the displacement gate (strategies/displacement.py:117-139)."""
+    alpha = complex(alpha)
+    return _disp_derivs(0, D, alpha.real, alpha.imag)
+
+
+def grad_displacement(T, r, phi):
+    """(dT/dr, dT/dphi) of the displacement gate (strategies/displacement.py:85-114); T square."""
+    T = _c128(T)
+    if T.ndim != 2 or T.shape[0] != T.shape[1]:
+        raise ValueError("grad_displacement expects a square gate array")
+    return _disp_derivs(1, T, r, phi)
+
+
+def _gate_vjp(kind: int, G, dLdG):
+    """Sums over the gate's support of dLdG[k] * vanilla_step_grad(G, k) (lattice/steps.py:145-171):
+    (dLdA upper-triangular [D, D], dLdb [D], sum(G * dLdG))."""
+    G = _c128(G)
+    dLdG = _c128(dLdG)
+    if dLdG.shape != G.shape:
+        raise ValueError(f"dLdG.shape={dLdG.shape} must equal G.shape={G.shape}")
+    D = G.ndim
+    out = np.empty(D * D + D + 1, np.complex128)
+    check(lib.mmh_gate_vjp_host(kind, D, shape_array(G.shape), _p(G), _p(dLdG), _p(out)))
+    return out[: D * D].reshape(D, D), out[D * D: D * D + D], complex(out[-1])
+
+
+def beamsplitter_vjp(G, dLdG, theta, phi):
+    """(dL/dtheta, dL/dphi) (strategies/beamsplitter.py:175-243): lattice reduction on the GPU, then the chain rule through
+    dV/dtheta, dV/dphi of the 2x2 beamsplitter unitary (:232-241)."""
+    dLdA, _, _ = _gate_vjp(0, G, dLdG)
+    st, ct = np.sin(theta), np.cos(theta)
+    e, em = np.exp(1j * phi), np.exp(-1j * phi)
+    dLdtheta = 2 * np.real(-st * dLdA[0, 2] - ct * em * dLdA[0, 3] + ct * e * dLdA[1, 2] - st * dLdA[1, 3])
+    dLdphi = 2 * np.real(1j * st * em * dLdA[0, 3] + 1j * st * e * dLdA[1, 2])
+    return dLdtheta, dLdphi
+
+
+def squeezer_vjp(G, dLdG, r, phi):
+    """(dL/dr, dL/dphi) of the squeezing gate (strategies/squeezer.py:69-124)."""
+    dLdA, _, dLdC = _gate_vjp(1, G, dLdG)
+    d_sech = -np.tanh(r) / np.cosh(r)
+    d_tanh = 1.0 / np.cosh(r) ** 2
+    tanh = np.tanh(r)
+    e, ec = np.exp(1j * phi), np.exp(-1j * phi)
+    dLdr = 2 * np.real(-dLdA[0, 0] * e * d_tanh + dLdA[0, 1] * d_sech + dLdA[1, 1] * ec * d_tanh - np.conj(dLdC) * 0.5 * tanh)
+    dLdphi = 2 * np.real(-dLdA[0, 0] * 1j * e * tanh - dLdA[1, 1] * 1j * ec * tanh)
+    return dLdr, dLdphi
+
+
+def squeezed_vjp(G, dLdG, r, phi):
+    """(dL/dr, dL/dphi) of the squeezed vacuum ket (strategies/squeezer.py:150-191)."""
+    dLdA, _, dLdC = _gate_vjp(2, G, dLdG)
+    tanh = np.tanh(r)
+    d_tanh = 1.0 / np.cosh(r) ** 2
+    e = np.exp(1j * phi)
+    dLdr = 2 * np.real(-dLdA[0, 0] * e * d_tanh - np.conj(dLdC) * 0.5 * tanh)
+    dLdphi = 2 * np.real(-dLdA[0, 0] * 1j * e * tanh)
+    return dLdr, dLdphi

@@ -115,3 +115,20 @@ def test_compactfock_entry_points(ref):
         math.hermite_renormalized_1leftoverMode(A, b, c, output_cutoff=3, pnr_cutoffs=(2, 3))))
     assert launches > 0 and got.shape == want.shape
     assert np.allclose(got, want, rtol=1e-9, atol=1e-12)
+
+
+def test_gate_fock_arrays_on_cuda_path(ref):
+    """Dgate / Sgate / BSgate / SqueezedVacuum.fock_array reach strategies.displacement / squeezer / beamsplitter / squeezed by name
+    (lab/transformations/{dgate,sgate,bsgate}.py, lab/states/squeezed_vacuum.py -> backend_numpy.py:452-475)."""
+    mm, dropin, _lib = ref
+    from mrmustard.lab import BSgate, Dgate, Sgate, SqueezedVacuum
+    want, got, launches = _both(dropin, _lib, lambda: np.asarray(Sgate(0, r=0.6, phi=0.9).fock_array((30, 30))))
+    assert launches > 0 and np.array_equal(got + 0.0, want + 0.0)
+    want, got, launches = _both(dropin, _lib, lambda: np.asarray(SqueezedVacuum(0, r=0.5, phi=0.3).fock_array((40,))))
+    assert launches > 0 and np.array_equal(got + 0.0, want + 0.0)
+    for method in ("vanilla", "stable"):
+        want, got, launches = _both(dropin, _lib, lambda: np.asarray(BSgate((0, 1), theta=0.7, phi=1.3).fock_array((9, 8, 9, 8), method=method)))
+        assert launches > 0 and np.array_equal(got + 0.0, want + 0.0), method
+    want, got, launches = _both(dropin, _lib, lambda: np.asarray(Dgate(0, alpha=0.4 - 0.3j).fock_array((25, 25))))
+    assert launches > 0
+    assert_parity(np.ascontiguousarray(got), np.ascontiguousarray(want), "Dgate")

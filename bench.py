@@ -798,6 +798,16 @@ def extras(ctx, skip):
         Adm = np.zeros((16, 16), complex); Adm[:8, :8] = np.conj(A8k); Adm[8:, 8:] = A8k
         bdm = np.concatenate([np.conj(b8k), b8k])
         out["cfg4_diagonal_M8_cutoff6_ms"] = wall(lambda: mm.hermite_renormalized_diagonal(Adm, bdm, abs(c8k) ** 2, (6,) * 8), 2)
+        # cfg4 AS WRITTEN: the 8-mode ket through the diagonal strategy at cutoff 12 (A 16x16, 430 M diagonal amplitudes), device
+        # resident, rolling weight-level buffers (mmh_diagonal_rolling.cu); the reference cannot run this config (0.94 TB of aux arrays)
+        A2, b2 = (np.ascontiguousarray(x) for x in mm.backend.reorder_AB_bargmann(Adm, bdm))
+        dA2, db2, dG0 = (torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.complex128))).to(dev) for x in (A2, b2, np.array([abs(c8k) ** 2])))
+        cut = (12,) * 8
+        dO = torch.empty((12 ** 8,), dtype=torch.complex128, device=dev)
+        ms = timeit(lambda: check(lib.mmh_diagonal(8, _lib.shape_array(cut), dA2.data_ptr(), db2.data_ptr(), 0, dG0.data_ptr(), dO.data_ptr(), sptr)), 2, False)
+        out["cfg4_diagonal_M8_cutoff12"] = {"ms": ms, "diagonal_amps_per_s": 12 ** 8 / (ms * 1e-3), "launches_per_call": 90,
+                                            "note": "BASELINE config 4 as written; equals |vanilla (12,)^8|^2 within 1e-10 (tests/test_gpu_diagonal.py)"}
+        del dO
 
     todo = {"cfg2": cfg2, "cfg5": cfg5, "cfg3": cfg3, "batches": batches, "stable": stable, "misc": misc, "cfg4": cfg4}
     for name, fn in todo.items():

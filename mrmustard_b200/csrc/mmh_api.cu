@@ -754,7 +754,23 @@ static int diagonal_impl(int M, const int64_t *cutoffs, int L0, const void *dA, 
     if ((rc = ensure_tables(*ctx, mx + 3))) return rc;
     const long long naux = 2LL * Md + Md + 2LL * Md * (Md > 1 ? Md - 1 : 1);
     const size_t bytes = sizeof(c128) * (size_t)naux * (size_t)q.E;
-    if (bytes > (size_t)160 << 30) return MMH_ERR_TOO_LARGE;   // reference layout; rolling level buffers are future work
+    // Large sweeps of the pure diagonal case: rolling weight-level buffers (mmh_diagonal_rolling.cu) -- the reference layout of the
+    // auxiliary arrays is 0.94 TB for the 8-mode, cutoff-12 config; two level buffers are 18 GB.  MMH_DIAG_ROLLING=0/1 forces a path.
+    {
+        const char *er = getenv("MMH_DIAG_ROLLING");
+        const bool rolling = !L0 && (er ? atoi(er) != 0 : bytes > ((size_t)1 << 30));
+        if (rolling) {
+            const size_t ws = mmh_diagonal_rolling_workspace(Md, q.cut, q.nb);
+            if (ws > (size_t)150 << 30) return MMH_ERR_TOO_LARGE;
+            if ((rc = ensure_scratch(ctx->diag_ws, ws))) return rc;
+            long long launches = 0;
+            CK(mmh_launch_diagonal_rolling(Md, q.cut, q.nb, (const c128 *)dA, (const c128 *)dB, (const c128 *)dG0, (c128 *)dout,
+                                           ctx->sq, ctx->diag_ws.ptr, &launches, st));
+            g_launches += launches;
+            return MMH_OK;
+        }
+    }
+    if (bytes > (size_t)160 << 30) return MMH_ERR_TOO_LARGE;
     if ((rc = ensure_scratch(ctx->diag_ws, bytes))) return rc;
     CK(cudaMemsetAsync(ctx->diag_ws.ptr, 0, bytes, st));
     c128 *w = (c128 *)ctx->diag_ws.ptr;

@@ -154,3 +154,8 @@ cudaError_t mmh_launch_transpose(const c128 *in, c128 *out, int rows, int cols, 
 cudaError_t mmh_launch_disp_derivs(const GateParams &p, const c128 *D, c128 *o1, c128 *o2, int kind, cudaStream_t st);
 cudaError_t mmh_launch_gate_mask(const c128 *g, c128 *out, long long n_total, int kind, int s1, int s2, int s3, cudaStream_t st);
 cudaError_t mmh_launch_gate_unsym(const c128 *sym, c128 *out, int D, cudaStream_t st);
+
+// compactFock diagonal sweep with rolling weight-level buffers (mmh_diagonal_rolling.cu)
+size_t mmh_diagonal_rolling_workspace(int M, const int *cut, int nb);
+cudaError_t mmh_launch_diagonal_rolling(int M, const int *cut, int nb, const c128 *A, const c128 *B, const c128 *G0, c128 *arr0,
+                                        const double *sq, void *workspace, long long *launches, cudaStream_t st);

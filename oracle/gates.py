@@ -5,8 +5,10 @@ numpy restatements (level-synchronous, vectorised over the independent points of
   squeezer / squeezer_vjp / squeezed / squeezed_vjp                       (strategies/squeezer.py:29-191)
   beamsplitter / stable_beamsplitter / beamsplitter_vjp                   (strategies/beamsplitter.py:37-243)
 Parity status: pinned against golden vectors generated from the unmodified reference
-(tests/golden/gen_golden_gates.py -> tests/golden/gates_golden.npz) by tests/test_oracle_gates.py at 1e-10 rel / 1e-14 abs;
-the transcendental parameters (exp, tanh, cosh, log) go through libm on both sides, so the last bits are not pinned.
+(tests/golden/gen_golden_gates.py -> tests/golden/gates_golden.npz) by tests/test_oracle_gates.py: squeezer / squeezed /
+beamsplitter / stable_beamsplitter BIT-IDENTICAL to the numba strategies (same IEEE operations in the same order, scalar
+transcendentals through libm like numba's lowering, complex / real as a component-wise division), displacement and all
+derivatives at 1e-10 rel / 1e-14 abs (per-element log / exp).
 """
 from __future__ import annotations
 
@@ -159,6 +161,13 @@ def squeezed_vjp(G, dLdG, r, phi):
 
 
 # ---- beamsplitter (beamsplitter.py:37-91, :94-172, :175-243) ---------------------------------------------------
+def _cdiv(z, s):
+    """complex / real as numba lowers it (component-wise true division); numpy's scalar complex division multiplies by the
+    reciprocal of the denominator instead, which differs in the last bit."""
+    z = complex(z)
+    return complex(z.real / s, z.imag / s)
+
+
 def beamsplitter(shape, theta, phi):
     """Photon-number conserving fill: first the q = 0 face G[m, n, m+n, 0] level by level in m + n, then for every p the
     entries q = m + n - p >= 1 level by level in m + n (each level reads the previous one only)."""
@@ -175,7 +184,7 @@ def beamsplitter(shape, theta, phi):
             if m > 0:
                 v = v + ct * SQRT[m] / SQRT[p] * G[m - 1, n, p - 1, 0]
             if n > 0:
-                v = v + st * SQRT[n] / SQRT[p] * G[m, n - 1, p - 1, 0]
+                v = v + _cdiv(st * SQRT[n], SQRT[p]) * G[m, n - 1, p - 1, 0]
             G[m, n, p, 0] = v
     for L in range(1, M + N - 1):
         for m in range(max(0, L - N + 1), min(M, L + 1)):
@@ -184,7 +193,7 @@ def beamsplitter(shape, theta, phi):
                 q = L - p
                 v = 0.0
                 if m > 0:
-                    v = v + -stc * SQRT[m] / SQRT[q] * G[m - 1, n, p, q - 1]
+                    v = v + _cdiv(-stc * SQRT[m], SQRT[q]) * G[m - 1, n, p, q - 1]
                 if n > 0:
                     v = v + ct * SQRT[n] / SQRT[q] * G[m, n - 1, p, q - 1]
                 G[m, n, p, q] = v
@@ -213,18 +222,18 @@ def stable_beamsplitter(shape, theta, phi):
                     if m > 0:
                         val += ct * SQRT[p] / SQRT[m] * g(m - 1, n, p - 1, 0); piv += 1
                     if n > 0:
-                        val += st * SQRT[p] / SQRT[n] * g(m, n - 1, p - 1, 0); piv += 1
+                        val += _cdiv(st * SQRT[p], SQRT[n]) * g(m, n - 1, p - 1, 0); piv += 1
                     if p > 0:
-                        val += ct * SQRT[m] / SQRT[p] * g(m - 1, n, p - 1, 0) + st * SQRT[n] / SQRT[p] * g(m, n - 1, p - 1, 0); piv += 1
+                        val += ct * SQRT[m] / SQRT[p] * g(m - 1, n, p - 1, 0) + _cdiv(st * SQRT[n], SQRT[p]) * g(m, n - 1, p - 1, 0); piv += 1
                 else:
                     if m > 0:
-                        val += ct * SQRT[p] / SQRT[m] * g(m - 1, n, p - 1, q) - stc * SQRT[q] / SQRT[m] * g(m - 1, n, p, q - 1); piv += 1
+                        val += ct * SQRT[p] / SQRT[m] * g(m - 1, n, p - 1, q) - _cdiv(stc * SQRT[q], SQRT[m]) * g(m - 1, n, p, q - 1); piv += 1
                     if n > 0:
-                        val += st * SQRT[p] / SQRT[n] * g(m, n - 1, p - 1, q) + ct * SQRT[q] / SQRT[n] * g(m, n - 1, p, q - 1); piv += 1
+                        val += _cdiv(st * SQRT[p], SQRT[n]) * g(m, n - 1, p - 1, q) + ct * SQRT[q] / SQRT[n] * g(m, n - 1, p, q - 1); piv += 1
                     if p > 0:
-                        val += ct * SQRT[m] / SQRT[p] * g(m - 1, n, p - 1, q) + st * SQRT[n] / SQRT[p] * g(m, n - 1, p - 1, q); piv += 1
-                    val += -stc * SQRT[m] / SQRT[q] * g(m - 1, n, p, q - 1) + ct * SQRT[n] / SQRT[q] * g(m, n - 1, p, q - 1); piv += 1
-                G[m, n, p, q] = val / piv
+                        val += ct * SQRT[m] / SQRT[p] * g(m - 1, n, p - 1, q) + _cdiv(st * SQRT[n], SQRT[p]) * g(m, n - 1, p - 1, q); piv += 1
+                    val += _cdiv(-stc * SQRT[m], SQRT[q]) * g(m - 1, n, p, q - 1) + ct * SQRT[n] / SQRT[q] * g(m, n - 1, p, q - 1); piv += 1
+                G[m, n, p, q] = _cdiv(val, piv)
     return G
 
 

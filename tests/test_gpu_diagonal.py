@@ -175,3 +175,65 @@ def test_eight_mode_ket_diagonal_vs_vanilla_lattice(mm, golden):
         want = np.abs(psi) ** 2
         assert got.shape == cut
         assert np.all(np.abs(got - want) <= 1e-14 + 1e-10 * np.abs(want)), cut
+
+
+def test_rolling_level_buffers_same_results(mm, gd, monkeypatch):
+    """The rolling-level-buffer sweep (mmh_diagonal_rolling.cu; default for large sweeps) against the reference goldens and against
+    the full-layout sweep on every golden diagonal case, b-batched included."""
+    for name in list(gd["diag_cases"]) + ["db"]:
+        A, b, c = gd[f"{name}_A"], gd[f"{name}_b"], complex(gd[f"{name}_c"])
+        cut = tuple(int(x) for x in gd[f"{name}_cut"])
+        monkeypatch.setenv("MMH_DIAG_ROLLING", "0")
+        full = mm.hermite_renormalized_diagonal(A, b, c, cut)
+        monkeypatch.setenv("MMH_DIAG_ROLLING", "1")
+        roll = mm.hermite_renormalized_diagonal(A, b, c, cut)
+        assert roll.shape == full.shape
+        assert_parity(np.ascontiguousarray(roll), np.ascontiguousarray(gd[f"{name}_G"]), name + " rolling vs reference")
+        assert np.allclose(roll, full, rtol=1e-13, atol=1e-16), name
+
+
+def test_rolling_eight_modes_small_cutoffs(mm, golden, monkeypatch):
+    A, b, c = golden["cfg4_A"], golden["cfg4_b"], complex(golden["cfg4_c"])
+    Adm = np.zeros((16, 16), complex); Adm[:8, :8] = np.conj(A); Adm[8:, 8:] = A
+    bdm = np.concatenate([np.conj(b), b]); cdm = abs(c) ** 2
+    monkeypatch.setenv("MMH_DIAG_ROLLING", "1")
+    for cut in [(3, 2, 3, 2, 2, 3, 2, 3), (4,) * 8, (1, 5, 1, 4, 2, 1, 3, 2)]:
+        got = mm.hermite_renormalized_diagonal(Adm, bdm, cdm, cut)
+        want = np.abs(mm.strategies.vanilla_numba(cut, A, b, c)) ** 2
+        assert np.all(np.abs(got - want) <= 1e-14 + 1e-10 * np.abs(want)), cut
+
+
+def test_cfg4_as_written_eight_modes_cutoff_12(golden):
+    """BASELINE config 4 as written: the 8-mode Gaussian ket through the diagonal strategy at cutoff 12 (A 16x16, 430 M diagonal
+    amplitudes).  The reference cannot run it (its auxiliary arrays would take 0.94 TB); here it must equal the squared moduli of the
+    (12,)^8 vanilla lattice of the same ket within 1e-10 relative / 1e-14 absolute.  Everything stays on the device (6.9 GB per array)."""
+    import ctypes
+    import torch
+    from mrmustard_b200 import _lib as L
+    free, _ = torch.cuda.mem_get_info()
+    if free < (60 << 30):
+        pytest.skip("needs ~45 GB of device memory")
+    dev = torch.device("cuda:0")
+    A, b, c = golden["cfg4_A"], golden["cfg4_b"], complex(golden["cfg4_c"])
+    Adm = np.zeros((16, 16), complex); Adm[:8, :8] = np.conj(A); Adm[8:, 8:] = A
+    bdm = np.concatenate([np.conj(b), b])
+    import mrmustard_b200 as mm
+    A2, b2 = (np.ascontiguousarray(x) for x in mm.backend.reorder_AB_bargmann(Adm, bdm))
+    to = lambda x: torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.complex128))).to(dev)
+    dA2, db2, dG0 = to(A2), to(b2), to(np.array([abs(c) ** 2]))
+    cut = (12,) * 8
+    n = 12 ** 8
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    out = torch.empty(n, dtype=torch.complex128, device=dev)
+    L.check(L.lib.mmh_diagonal(8, L.shape_array(cut), dA2.data_ptr(), db2.data_ptr(), 0, dG0.data_ptr(), out.data_ptr(), st))
+    dA, db, dc = to(A), to(b), to(np.array([c]))
+    psi = torch.empty(n, dtype=torch.complex128, device=dev)
+    L.check(L.lib.mmh_forward(8, L.shape_array(cut), dA.data_ptr(), db.data_ptr(), dc.data_ptr(), psi.data_ptr(), 0, st))
+    torch.cuda.synchronize()
+    want = psi.real ** 2 + psi.imag ** 2
+    del psi
+    err = (out.real - want).abs()
+    tol = 1e-14 + 1e-10 * want
+    assert bool(torch.all(err <= tol)), f"max err {float(err.max())}, max |want| {float(want.max())}"
+    assert float(out.imag.abs().max()) <= 1e-14
+    assert abs(float(want.sum()) - float(out.real.sum())) <= 1e-9 * float(want.sum())

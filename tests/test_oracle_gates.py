@@ -38,7 +38,7 @@ def test_squeezer_and_vjp(gg):
         if big:
             continue    # (200, 200): GPU only
         G = og.squeezer(shape, r, th)
-        assert_parity(G, gg[f"{tag}_G"], tag)
+        assert np.array_equal(G + 0.0, gg[f"{tag}_G"] + 0.0), tag      # bit-identical to the numba strategy
         k = int(gg[f"{tag}_gseed"])
         g = np.random.RandomState(k).standard_normal(shape) + 1j * np.random.RandomState(k + 1000).standard_normal(shape)
         dr, dphi = og.squeezer_vjp(G, g, r, th)
@@ -50,7 +50,7 @@ def test_squeezed_and_vjp(gg):
     for tag in gg["sqz_cases"]:
         cut = int(gg[f"{tag}_cut"]); r = float(gg[f"{tag}_r"]); th = float(gg[f"{tag}_theta"])
         G = og.squeezed(cut, r, th)
-        assert_parity(G, gg[f"{tag}_G"], tag)
+        assert np.array_equal(G + 0.0, gg[f"{tag}_G"] + 0.0), tag
         dr, dphi = og.squeezed_vjp(G, gg[f"{tag}_g"], r, th)
         assert_parity(np.float64(dr), np.float64(gg[f"{tag}_dr"]), tag + " dr")
         assert_parity(np.float64(dphi), np.float64(gg[f"{tag}_dphi"]), tag + " dphi")
@@ -62,9 +62,9 @@ def test_beamsplitter_and_vjp(gg):
         if f"{tag}_G" not in gg.files:
             continue    # large cases: GPU only
         G = og.beamsplitter(shape, th, ph)
-        assert_parity(G, gg[f"{tag}_G"], tag)
+        assert np.array_equal(G + 0.0, gg[f"{tag}_G"] + 0.0), tag
         if int(np.prod(shape)) <= 5000:
-            assert_parity(og.stable_beamsplitter(shape, th, ph), gg[f"{tag}_Gs"], tag + " stable")
+            assert np.array_equal(og.stable_beamsplitter(shape, th, ph) + 0.0, gg[f"{tag}_Gs"] + 0.0), tag + " stable"
             dth, dph = og.beamsplitter_vjp(G, gg[f"{tag}_g"], th, ph)
             assert_parity(np.float64(dth), np.float64(gg[f"{tag}_dtheta"]), tag + " dtheta")
             assert_parity(np.float64(dph), np.float64(gg[f"{tag}_dphi"]), tag + " dphi")

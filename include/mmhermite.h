@@ -203,6 +203,32 @@ int mmh_displacement_derivs_host(int what, int64_t M, int64_t N, const void *D, 
 int mmh_gate_vjp(int kind, int ndim, const int64_t *shape, const void *dG, const void *ddLdG, void *dout, void *stream);
 int mmh_gate_vjp_host(int kind, int ndim, const int64_t *shape, const void *G, const void *dLdG, void *out);
 
+/* Fock-shape estimate of a Gaussian density matrix -------------------------------------------
+ * replaces: autoshape_numba(A, b, c, max_prob, max_shape, min_shape)   (mrmustard/math/lattice/autoshape.py:24-154), called by
+ *           State.auto_shape (lab/states/base.py:383-444) to choose the shapes of fock_array / to_fock.
+ * A[2M,2M], b[2M] in bargmann order [m0.. | m0..], c[1]  ->  shape_out[M] (int64): for every mode the number of diagonal entries
+ * of its single-mode marginal needed to capture max_prob of the trace, clipped to [min_shape, max_shape].  M <= 32.            */
+int mmh_autoshape(int M, const void *dA, const void *db, const void *dc, double max_prob, int64_t max_shape, int64_t min_shape,
+                  int64_t *dshape_out, void *stream);
+int mmh_autoshape_host(int M, const void *A, const void *b, const void *c, double max_prob, int64_t max_shape, int64_t min_shape,
+                       int64_t *shape_out);
+
+/* Fock-space consumers of the lattice ---------------------------------------------------------
+ * replaces: ArrayAnsatz.contract(other, idx1, idx2, idx_out)   (mrmustard/physics/ansatz/array_ansatz.py:159-225): the einsum of
+ *           two Fock arrays by labels, with every label shared by both operands running over the common minimum of its two dims
+ *           (:209-218) -- the contraction CircuitComponent.contract performs on `to_fock` outputs
+ *           (lab/circuit_components.py:446-458, physics/mm_einsum.py:51-165).
+ * labels are small non-negative integers (< 128), one per axis, no label twice inside one operand.  Labels missing from labelsOut
+ * are summed.  C is written C-contiguous in the order of labelsOut; out_shape (HOST pointer, nOut entries, may be NULL) receives
+ * its shape.  The call synchronises `stream` once (it stages its index tables).                                              */
+int mmh_fock_contract(int nA, const int64_t *shapeA, const int *labelsA, int nB, const int64_t *shapeB, const int *labelsB, int nOut,
+                      const int *labelsOut, const void *dA, const void *dB, void *dC, int64_t *out_shape, void *stream);
+int mmh_fock_contract_host(int nA, const int64_t *shapeA, const int *labelsA, int nB, const int64_t *shapeB, const int *labelsB, int nOut,
+                           const int *labelsOut, const void *A, const void *B, void *C);
+/* replaces: ArrayAnsatz.reduce(shape) (array_ansatz.py:227-267; mm_einsum.to_fock, physics/mm_einsum.py:272-292): every axis is
+ *           sliced to out_shape[d] or zero-padded up to it (batch axes are passed with equal in/out extents).                */
+int mmh_fock_reduce(int ndim, const int64_t *in_shape, const int64_t *out_shape, const void *din, void *dout, void *stream);
+
 /* debug aid, not part of the reference interface: 4 (lattice index mod 4) x 16 x 4 %globaltimer stamps (entry, dependency wait passed, first step,
  * exit of CTA 0) of the last single-lattice forward's kernels; synchronises the device.                          */
 int mmh_debug_timeline(unsigned long long *out64);

@@ -50,6 +50,7 @@ struct DeviceCtx {
     Scratch timeline;             // 16 x 4 debug stamps of the last forward launches
     Scratch lattice_ws;           // lattice kept on the device by mmh_forward_contract
     Scratch ones;                 // vacuum amplitudes c = 1 of mmh_forward_contract
+    Scratch ein_ws;               // offset tables of the Fock-space contraction
     Scratch gate_ws;              // gate strategies: log-factorial table, transposition buffer, masked cotangent
     Scratch host_slots[8];        // staging for the *_host entry points
     int *err_host = nullptr;      // mapped page-locked word the watchdogs of the polling kernels set when they give up
@@ -1487,5 +1488,186 @@ int mmh_gate_vjp_host(int kind, int ndim, const int64_t *shape, const void *G, c
     CK(cudaMemcpyAsync(out, dout, obytes, cudaMemcpyDeviceToHost, 0));
     CK(cudaStreamSynchronize(0));
     return end_host_call(ctx);
+}
+}  // extern "C"
+
+// ---- autoshape (mmh_autoshape.cu) ------------------------------------------------------------
+static int autoshape_impl(int M, const void *dA, const void *db, const void *dc, double max_prob, long long max_shape,
+                          long long min_shape, void *dshape, cudaStream_t st) {
+    if (M < 1 || M > 32) return MMH_ERR_BAD_NDIM;
+    if (max_shape < 0 || max_shape > (1 << 20)) return MMH_ERR_BAD_SHAPE;
+    if (!dA || !db || !dc || !dshape) return MMH_ERR_NULL_POINTER;
+    DeviceCtx *ctx;
+    int rc;
+    if ((rc = gate_ctx(&ctx, st, (int)max_shape + 2))) return rc;
+    g_launches++;
+    CK(mmh_launch_autoshape(M, (const c128 *)dA, (const c128 *)db, (const c128 *)dc, max_prob, max_shape, min_shape,
+                            (long long *)dshape, ctx->sq, st));
+    return MMH_OK;
+}
+extern "C" int mmh_autoshape(int M, const void *dA, const void *db, const void *dc, double max_prob, int64_t max_shape,
+                             int64_t min_shape, int64_t *dshape_out, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return autoshape_impl(M, dA, db, dc, max_prob, max_shape, min_shape, dshape_out, (cudaStream_t)stream);
+}
+extern "C" int mmh_autoshape_host(int M, const void *A, const void *b, const void *c, double max_prob, int64_t max_shape,
+                                  int64_t min_shape, int64_t *shape_out) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (M < 1 || M > 32) return MMH_ERR_BAD_NDIM;
+    if (!A || !b || !c || !shape_out) return MMH_ERR_NULL_POINTER;
+    DeviceCtx *ctx;
+    int rc;
+    if ((rc = get_ctx(&ctx))) return rc;
+    void *dA, *db, *dc, *dsh;
+    const size_t n2 = 2 * (size_t)M;
+    if ((rc = stage_in(*ctx, 0, A, sizeof(c128) * n2 * n2, &dA))) return rc;
+    if ((rc = stage_in(*ctx, 1, b, sizeof(c128) * n2, &db))) return rc;
+    if ((rc = stage_in(*ctx, 2, c, sizeof(c128), &dc))) return rc;
+    if ((rc = stage_in(*ctx, 4, nullptr, sizeof(int64_t) * (size_t)M, &dsh))) return rc;
+    if ((rc = autoshape_impl(M, dA, db, dc, max_prob, max_shape, min_shape, dsh, 0))) return rc;
+    CK(cudaMemcpyAsync(shape_out, dsh, sizeof(int64_t) * (size_t)M, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    return end_host_call(ctx);
+}
+
+// ---- Fock-space contraction / reduce (mmh_einsum.cu) -------------------------------------------
+static int fock_contract_impl(int nA, const int64_t *shapeA, const int *labA, int nB, const int64_t *shapeB, const int *labB, int nO,
+                              const int *labO, const void *dA, const void *dB, void *dC, int64_t *out_shape, cudaStream_t st) {
+    if (nA < 0 || nA > MMH_MAX_DIM || nB < 0 || nB > MMH_MAX_DIM || nO < 0 || nO > 2 * MMH_MAX_DIM) return MMH_ERR_BAD_NDIM;
+    if ((nA && (!shapeA || !labA)) || (nB && (!shapeB || !labB)) || (nO && !labO)) return MMH_ERR_NULL_POINTER;
+    if (!dA || !dB || !dC) return MMH_ERR_NULL_POINTER;
+    const int NL = 128;
+    long long dimA[NL], dimB[NL], strA[NL], strB[NL], strC[NL], dim[NL];
+    bool inA[NL] = { false }, inB[NL] = { false }, inO[NL] = { false };
+    for (int l = 0; l < NL; l++) { dimA[l] = dimB[l] = dim[l] = 0; strA[l] = strB[l] = strC[l] = 0; }
+    long long s = 1;
+    for (int i = nA - 1; i >= 0; i--) {
+        const int l = labA[i];
+        if (l < 0 || l >= NL || inA[l]) return MMH_ERR_UNSUPPORTED;   // repeated label inside one operand (a trace): not handled here
+        if (shapeA[i] < 1) return MMH_ERR_BAD_SHAPE;
+        inA[l] = true; dimA[l] = shapeA[i]; strA[l] = s; s *= shapeA[i];
+    }
+    s = 1;
+    for (int i = nB - 1; i >= 0; i--) {
+        const int l = labB[i];
+        if (l < 0 || l >= NL || inB[l]) return MMH_ERR_UNSUPPORTED;
+        if (shapeB[i] < 1) return MMH_ERR_BAD_SHAPE;
+        inB[l] = true; dimB[l] = shapeB[i]; strB[l] = s; s *= shapeB[i];
+    }
+    for (int l = 0; l < NL; l++)   // shared labels run over the common minimum (array_ansatz.py:209-218)
+        dim[l] = (inA[l] && inB[l]) ? (dimA[l] < dimB[l] ? dimA[l] : dimB[l]) : (inA[l] ? dimA[l] : dimB[l]);
+    s = 1;
+    for (int i = nO - 1; i >= 0; i--) {
+        const int l = labO[i];
+        if (l < 0 || l >= NL || inO[l] || !(inA[l] || inB[l])) return MMH_ERR_BAD_SHAPE;
+        inO[l] = true; strC[l] = s; s *= dim[l];
+        if (out_shape) out_shape[i] = dim[l];
+    }
+    // groups, in label order: batch (A, B, O), M (A, O), N (B, O), K (not O)
+    std::vector<int> gb, gm, gn, gk;
+    for (int l = 0; l < NL; l++) {
+        if (!inA[l] && !inB[l]) continue;
+        if (inO[l]) (inA[l] && inB[l] ? gb : (inA[l] ? gm : gn)).push_back(l);
+        else gk.push_back(l);
+    }
+    auto count = [&](const std::vector<int> &g) { long long n = 1; for (int l : g) n *= dim[l]; return n; };
+    const long long nb = count(gb), M = count(gm), N = count(gn), K = count(gk);
+    if (nb > 65535 || M > (1LL << 26) || N > (1LL << 26) || K > (1LL << 26)) return MMH_ERR_TOO_LARGE;
+    auto table = [&](const std::vector<int> &g, long long n, const long long *stride, std::vector<long long> &out) {
+        const size_t base = out.size();
+        out.resize(base + (size_t)n);
+        for (long long f = 0; f < n; f++) {
+            long long rem = f, off = 0;
+            for (int t = (int)g.size() - 1; t >= 0; t--) { const int l = g[t]; off += (rem % dim[l]) * stride[l]; rem /= dim[l]; }
+            out[base + (size_t)f] = off;
+        }
+        return base;
+    };
+    std::vector<long long> tab;
+    const size_t oAb = table(gb, nb, strA, tab), oBb = table(gb, nb, strB, tab), oCb = table(gb, nb, strC, tab);
+    const size_t oAm = table(gm, M, strA, tab), oCm = table(gm, M, strC, tab);
+    const size_t oBn = table(gn, N, strB, tab), oCn = table(gn, N, strC, tab);
+    const size_t oAk = table(gk, K, strA, tab), oBk = table(gk, K, strB, tab);
+    DeviceCtx *ctx;
+    int rc;
+    if ((rc = get_ctx(&ctx))) return rc;
+    if ((rc = begin_call(ctx, st))) return rc;
+    if ((rc = ensure_scratch(ctx->ein_ws, sizeof(long long) * tab.size()))) return rc;
+    CK(cudaMemcpyAsync(ctx->ein_ws.ptr, tab.data(), sizeof(long long) * tab.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));   // tab is a local
+    const long long *d = (const long long *)ctx->ein_ws.ptr;
+    EinsumParams p;
+    p.A = (const c128 *)dA; p.B = (const c128 *)dB; p.C = (c128 *)dC;
+    p.M = M; p.N = N; p.K = K; p.nbatch = nb;
+    p.offA_b = d + oAb; p.offB_b = d + oBb; p.offC_b = d + oCb;
+    p.offA_m = d + oAm; p.offC_m = d + oCm; p.offB_n = d + oBn; p.offC_n = d + oCn; p.offA_k = d + oAk; p.offB_k = d + oBk;
+    g_launches++;
+    CK(mmh_launch_einsum(p, st));
+    return MMH_OK;
+}
+
+static int fock_reduce_impl(int ndim, const int64_t *in_shape, const int64_t *out_shape, const void *din, void *dout, cudaStream_t st) {
+    if (ndim < 0 || ndim > MMH_MAX_DIM) return MMH_ERR_BAD_NDIM;
+    if (ndim && (!in_shape || !out_shape)) return MMH_ERR_NULL_POINTER;
+    if (!din || !dout) return MMH_ERR_NULL_POINTER;
+    ReduceParams p;
+    memset(&p, 0, sizeof(p));
+    p.ndim = ndim; p.in = (const c128 *)din; p.out = (c128 *)dout;
+    long long s = 1, n = 1;
+    for (int d = ndim - 1; d >= 0; d--) {
+        if (in_shape[d] < 1 || out_shape[d] < 1) return MMH_ERR_BAD_SHAPE;
+        p.in_shape[d] = in_shape[d]; p.out_shape[d] = out_shape[d]; p.in_stride[d] = s;
+        s *= in_shape[d];
+        if (n > (1LL << 40) / out_shape[d]) return MMH_ERR_TOO_LARGE;
+        n *= out_shape[d];
+    }
+    p.n_out = n;
+    DeviceCtx *ctx;
+    int rc;
+    if ((rc = get_ctx(&ctx))) return rc;
+    if ((rc = begin_call(ctx, st))) return rc;
+    g_launches++;
+    CK(mmh_launch_fock_reduce(p, st));
+    return MMH_OK;
+}
+
+extern "C" {
+int mmh_fock_contract(int nA, const int64_t *shapeA, const int *labelsA, int nB, const int64_t *shapeB, const int *labelsB, int nOut,
+                      const int *labelsOut, const void *dA, const void *dB, void *dC, int64_t *out_shape, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return fock_contract_impl(nA, shapeA, labelsA, nB, shapeB, labelsB, nOut, labelsOut, dA, dB, dC, out_shape, (cudaStream_t)stream);
+}
+int mmh_fock_contract_host(int nA, const int64_t *shapeA, const int *labelsA, int nB, const int64_t *shapeB, const int *labelsB, int nOut,
+                           const int *labelsOut, const void *A, const void *B, void *C) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (!A || !B || !C) return MMH_ERR_NULL_POINTER;
+    if (nA < 0 || nA > MMH_MAX_DIM || nB < 0 || nB > MMH_MAX_DIM || nOut < 0 || nOut > 2 * MMH_MAX_DIM) return MMH_ERR_BAD_NDIM;
+    size_t na = 1, nbb = 1;
+    for (int i = 0; i < nA; i++) { if (!shapeA || shapeA[i] < 1) return MMH_ERR_BAD_SHAPE; na *= (size_t)shapeA[i]; }
+    for (int i = 0; i < nB; i++) { if (!shapeB || shapeB[i] < 1) return MMH_ERR_BAD_SHAPE; nbb *= (size_t)shapeB[i]; }
+    // output size: product over the output labels of the (common-minimum) dims
+    size_t nc = 1;
+    for (int i = 0; i < nOut; i++) {
+        long long d = 0;
+        for (int j = 0; j < nA; j++) if (labelsA[j] == labelsOut[i]) d = shapeA[j];
+        for (int j = 0; j < nB; j++) if (labelsB[j] == labelsOut[i]) d = (d == 0 || shapeB[j] < d) ? shapeB[j] : d;
+        if (d < 1) return MMH_ERR_BAD_SHAPE;
+        nc *= (size_t)d;
+    }
+    DeviceCtx *ctx;
+    int rc;
+    if ((rc = get_ctx(&ctx))) return rc;
+    void *dA, *dB, *dC;
+    if ((rc = stage_in(*ctx, 0, A, sizeof(c128) * na, &dA))) return rc;
+    if ((rc = stage_in(*ctx, 1, B, sizeof(c128) * nbb, &dB))) return rc;
+    if ((rc = stage_in(*ctx, 3, nullptr, sizeof(c128) * nc, &dC))) return rc;
+    if ((rc = fock_contract_impl(nA, shapeA, labelsA, nB, shapeB, labelsB, nOut, labelsOut, dA, dB, dC, nullptr, 0))) return rc;
+    CK(cudaMemcpyAsync(C, dC, sizeof(c128) * nc, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    return end_host_call(ctx);
+}
+int mmh_fock_reduce(int ndim, const int64_t *in_shape, const int64_t *out_shape, const void *din, void *dout, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return fock_reduce_impl(ndim, in_shape, out_shape, din, dout, (cudaStream_t)stream);
 }
 }  // extern "C"

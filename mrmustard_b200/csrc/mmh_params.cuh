@@ -159,3 +159,27 @@ cudaError_t mmh_launch_gate_unsym(const c128 *sym, c128 *out, int D, cudaStream_
 size_t mmh_diagonal_rolling_workspace(int M, const int *cut, int nb);
 cudaError_t mmh_launch_diagonal_rolling(int M, const int *cut, int nb, const c128 *A, const c128 *B, const c128 *G0, c128 *arr0,
                                         const double *sq, void *workspace, long long *launches, cudaStream_t st);
+
+// autoshape (mmh_autoshape.cu)
+cudaError_t mmh_launch_autoshape(int M, const c128 *A, const c128 *b, const c128 *c, double max_prob, long long max_shape,
+                                 long long min_shape, long long *shape_out, const double *sq, cudaStream_t st);
+
+// Fock-space contraction / reduce (mmh_einsum.cu)
+struct EinsumParams {
+    const c128 *A, *B;
+    c128 *C;
+    long long M, N, K, nbatch;
+    const long long *offA_b, *offB_b, *offC_b;   // [nbatch]
+    const long long *offA_m, *offC_m;            // [M]
+    const long long *offB_n, *offC_n;            // [N]
+    const long long *offA_k, *offB_k;            // [K]
+};
+struct ReduceParams {
+    int ndim;
+    long long in_shape[MMH_MAX_DIM], out_shape[MMH_MAX_DIM], in_stride[MMH_MAX_DIM];
+    long long n_out;
+    const c128 *in;
+    c128 *out;
+};
+cudaError_t mmh_launch_einsum(const EinsumParams &p, cudaStream_t st);
+cudaError_t mmh_launch_fock_reduce(const ReduceParams &p, cudaStream_t st);

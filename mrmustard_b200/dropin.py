@@ -20,7 +20,7 @@ _STRATEGY_NAMES = ["vanilla_numba", "stable_numba", "vanilla_batch_numba", "vani
                    "grad_displacement", "beamsplitter_vjp", "squeezer_vjp", "squeezed_vjp"]
 
 
-def install() -> None:
+def install(fock: bool = False) -> None:
     # (`import mrmustard.math.lattice.strategies as x` fails: `mrmustard.math` is the BackendManager instance, math/__init__.py:34)
     from mrmustard.math.lattice import strategies as ref_strategies
     from mrmustard.math.backend_numpy import BackendNumpy
@@ -44,6 +44,23 @@ def install() -> None:
     }.items():
         _saved[("b", name)] = getattr(BackendNumpy, name)
         setattr(BackendNumpy, name, fn)
+    # autoshape_numba is imported by name into the modules that call it (lab/states/base.py:383-444): rebind it wherever it lives
+    import sys
+    for modname in ("mrmustard.math.lattice.autoshape", "mrmustard.lab.states.base"):
+        mod = sys.modules.get(modname)
+        if mod is not None and hasattr(mod, "autoshape_numba"):
+            _saved[("m", modname)] = mod.autoshape_numba
+            mod.autoshape_numba = strategies.autoshape_numba
+    if fock:   # the Fock-space contraction of `to_fock` outputs on the GPU as well
+        from mrmustard.physics.ansatz.array_ansatz import ArrayAnsatz
+        from . import fock as _fock
+
+        def contract(self, other, idx1, idx2, idx_out):
+            result = _fock.contract(self.array, list(idx1), other.array, list(idx2), list(idx_out))
+            return ArrayAnsatz(result, batch_dims=sum(1 for label in idx_out if isinstance(label, str)))
+
+        _saved[("a", "contract")] = ArrayAnsatz.contract
+        ArrayAnsatz.contract = contract
     backend._installed = True
 
 
@@ -52,7 +69,16 @@ def uninstall() -> None:
     from mrmustard.math.lattice import strategies as ref_strategies
     from mrmustard.math.backend_numpy import BackendNumpy
 
+    import sys
     for (kind, name), fn in _saved.items():
+        if kind == "m":
+            if name in sys.modules:
+                sys.modules[name].autoshape_numba = fn
+            continue
+        if kind == "a":
+            from mrmustard.physics.ansatz.array_ansatz import ArrayAnsatz
+            setattr(ArrayAnsatz, name, fn)
+            continue
         setattr(ref_strategies if kind == "s" else BackendNumpy, name, fn)
     _saved.clear()
     backend._installed = False

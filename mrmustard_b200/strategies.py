@@ -23,7 +23,7 @@ __all__ = [
     "grad_hermite_multidimensional_diagonal", "hermite_renormalized_diagonal_vjp",
     "grad_hermite_multidimensional_1leftoverMode", "vanilla_contract_numba",
     "squeezer", "squeezed", "beamsplitter", "stable_beamsplitter", "displacement", "jacobian_displacement", "grad_displacement",
-    "beamsplitter_vjp", "squeezer_vjp", "squeezed_vjp",
+    "beamsplitter_vjp", "squeezer_vjp", "squeezed_vjp", "autoshape_numba",
 ]
 
 
@@ -443,3 +443,19 @@ def squeezed_vjp(G, dLdG, r, phi):
     dLdr = 2 * np.real(-dLdA[0, 0] * e * d_tanh - np.conj(dLdC) * 0.5 * tanh)
     dLdphi = 2 * np.real(-dLdA[0, 0] * 1j * e * tanh)
     return dLdr, dLdphi
+
+
+# ---- autoshape -------------------------------------------------------------------------------
+def autoshape_numba(A, b, c, max_prob, max_shape, min_shape) -> np.ndarray:
+    """Fock shape of a Gaussian density matrix such that every single-mode marginal keeps max_prob of its trace
+    (math/lattice/autoshape.py:24-154): A[2M,2M], b[2M] in bargmann order, c scalar -> int64[M] clipped to [min_shape, max_shape]."""
+    b = _c128(b)
+    if b.ndim != 1 or b.shape[0] % 2:
+        raise ValueError("b must be a vector of even length 2M")
+    M = b.shape[0] // 2
+    A = _c128(A, (2 * M, 2 * M))
+    c = _c128(c, (1,))
+    out = np.empty(M, np.int64)
+    check(lib.mmh_autoshape_host(M, _p(A), _p(b), _p(c), float(max_prob), int(max_shape), int(min_shape),
+                                 out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))))
+    return out

@@ -714,9 +714,17 @@ def extras(ctx, skip):
         a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         train_step(); torch.cuda.synchronize()
         a.record(stream); train_step(); bb.record(stream); torch.cuda.synchronize()
-        rec["train_step_e2e"] = {"wall_ms": ms_e2e, "device_ms": a.elapsed_time(bb), "kernel_ms_forward_plus_vjp": rec["forward"]["ms"] + rec["vjp"]["ms"],
-                                 "h2d_bytes": 336, "d2h_bytes": 22 * 16,
-                                 "api": "mrmustard_b200.device.hermite_renormalized (torch.autograd.Function over mmh_forward / mmh_vjp); loss in torch ops"}
+        rec["train_step_autograd_e2e"] = {"wall_ms": ms_e2e, "device_ms": a.elapsed_time(bb), "h2d_bytes": 336, "d2h_bytes": 22 * 16,
+                                          "api": "mrmustard_b200.device.hermite_renormalized (torch.autograd.Function over mmh_forward / mmh_vjp); loss written in torch ops"}
+        # the same step through the fused device path: packed H2D (336 B) -> mmh_forward -> mmh_overlap -> mmh_vjp (constant
+        # cotangent conj(target)) -> D2H of 22 complex numbers; host inputs, host outputs, everything inside the timed region
+        step = dv.FidelityStep(shape, t)
+        hAn, hbn, hcn = np.ascontiguousarray(A), np.ascontiguousarray(b), complex(c[0])
+        ms_fused = wall(lambda: step(hAn, hbn, hcn), 20)
+        kern = rec["forward"]["ms"] + rec["vjp"]["ms"]
+        rec["train_step_e2e"] = {"wall_ms": ms_fused, "kernel_ms_forward_plus_vjp": kern, "ratio_to_kernels": ms_fused / kern,
+                                 "steps_per_s": 1e3 / ms_fused, "h2d_bytes": 336, "d2h_bytes": 22 * 16,
+                                 "api": "mrmustard_b200.device.FidelityStep(shape, target)(A, b, c) -> (loss, dLdA, dLdb, dLdc); numpy in, numpy out"}
         ms_np = wall(lambda: mm.strategies.vanilla_vjp_numba(mm.strategies.vanilla_numba(shape, A, b, complex(c[0])), complex(c[0]), np.ones(shape, complex)), 3)
         rec["train_step_numpy_api_wall_ms"] = ms_np
         if not ctx["args"].no_cpu:

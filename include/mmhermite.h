@@ -229,6 +229,12 @@ int mmh_fock_contract_host(int nA, const int64_t *shapeA, const int *labelsA, in
  *           sliced to out_shape[d] or zero-padded up to it (batch axes are passed with equal in/out extents).                */
 int mmh_fock_reduce(int ndim, const int64_t *in_shape, const int64_t *out_shape, const void *din, void *dout, void *stream);
 
+/* Bilinear overlap of two device lattices: out[0] = sum_k x[k] * y[k] (no conjugation; pass conj(target) for <target|G>).
+ * The scalar a fidelity cost takes from the lattice (BASELINE config 5: 1 - |<target|psi>|^2 inside Optimizer.minimize,
+ * mrmustard/training/optimizer.py:82-105; physics/fock_utils fidelity), reduced on the device so that a training step reads
+ * back a handful of numbers instead of the lattice.  Deterministic (fixed-order reduction).                                  */
+int mmh_overlap(int64_t n, const void *dx, const void *dy, void *dout, void *stream);
+
 /* debug aid, not part of the reference interface: 4 (lattice index mod 4) x 16 x 4 %globaltimer stamps (entry, dependency wait passed, first step,
  * exit of CTA 0) of the last single-lattice forward's kernels; synchronises the device.                          */
 int mmh_debug_timeline(unsigned long long *out64);

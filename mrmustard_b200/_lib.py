@@ -32,7 +32,7 @@ SYMBOLS = [
     "mmh_forward_contract", "mmh_forward_contract_host", "mmh_debug_timeline", "mmh_debug_plan",
     "mmh_squeezer", "mmh_squeezed", "mmh_beamsplitter", "mmh_displacement", "mmh_gate_host",
     "mmh_displacement_jacobian", "mmh_displacement_grad", "mmh_displacement_derivs_host", "mmh_gate_vjp", "mmh_gate_vjp_host",
-    "mmh_autoshape", "mmh_autoshape_host", "mmh_fock_contract", "mmh_fock_contract_host", "mmh_fock_reduce",
+    "mmh_autoshape", "mmh_autoshape_host", "mmh_fock_contract", "mmh_fock_contract_host", "mmh_fock_reduce", "mmh_overlap",
 ]
 
 
@@ -97,6 +97,7 @@ def _load() -> ctypes.CDLL:
         "mmh_fock_contract": ([ci, p64, ctypes.POINTER(ci), ci, p64, ctypes.POINTER(ci), ci, ctypes.POINTER(ci), vp, vp, vp, p64, vp], ci),
         "mmh_fock_contract_host": ([ci, p64, ctypes.POINTER(ci), ci, p64, ctypes.POINTER(ci), ci, ctypes.POINTER(ci), vp, vp, vp], ci),
         "mmh_fock_reduce": ([ci, p64, p64, vp, vp, vp], ci),
+        "mmh_overlap": ([i64, vp, vp, vp, vp], ci),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)

@@ -51,6 +51,7 @@ struct DeviceCtx {
     Scratch lattice_ws;           // lattice kept on the device by mmh_forward_contract
     Scratch ones;                 // vacuum amplitudes c = 1 of mmh_forward_contract
     Scratch ein_ws;               // offset tables of the Fock-space contraction
+    Scratch dot_ws;               // per-CTA partials of mmh_overlap
     Scratch gate_ws;              // gate strategies: log-factorial table, transposition buffer, masked cotangent
     Scratch host_slots[8];        // staging for the *_host entry points
     int *err_host = nullptr;      // mapped page-locked word the watchdogs of the polling kernels set when they give up
@@ -1671,3 +1672,22 @@ int mmh_fock_reduce(int ndim, const int64_t *in_shape, const int64_t *out_shape,
     return fock_reduce_impl(ndim, in_shape, out_shape, din, dout, (cudaStream_t)stream);
 }
 }  // extern "C"
+
+// ---- bilinear overlap of two lattices (mmh_vjp.cu k_dot_*) ----------------------------------------------------------------
+extern "C" int mmh_overlap(int64_t n, const void *dx, const void *dy, void *dout, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (n < 0) return MMH_ERR_BAD_SHAPE;
+    if (!dx || !dy || !dout) return MMH_ERR_NULL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    DeviceCtx *ctx;
+    int rc;
+    if ((rc = get_ctx(&ctx))) return rc;
+    if ((rc = begin_call(ctx, st))) return rc;
+    long long want = (n + 256 * 8 - 1) / (256 * 8);
+    const long long cap = 4LL * ctx->sm_count;
+    int nblk = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    if ((rc = ensure_scratch(ctx->dot_ws, sizeof(c128) * (size_t)nblk))) return rc;
+    g_launches += 2;
+    CK(mmh_launch_dot((const c128 *)dx, (const c128 *)dy, n, (c128 *)ctx->dot_ws.ptr, nblk, (c128 *)dout, st));
+    return MMH_OK;
+}

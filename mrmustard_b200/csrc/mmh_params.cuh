@@ -183,3 +183,4 @@ struct ReduceParams {
 };
 cudaError_t mmh_launch_einsum(const EinsumParams &p, cudaStream_t st);
 cudaError_t mmh_launch_fock_reduce(const ReduceParams &p, cudaStream_t st);
+cudaError_t mmh_launch_dot(const c128 *x, const c128 *y, long long n, c128 *partial, int nblk, c128 *out, cudaStream_t st);

@@ -392,3 +392,34 @@ cudaError_t mmh_launch_vjp(const VjpParams &p_in, int grid_y, int block, cudaStr
     k_vjp_finish<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, st>>>(p);
     return cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Bilinear overlap  s = sum_k x_k y_k  of two lattices (no conjugation: the caller passes conj(target)) -- the scalar a fidelity
+// cost needs from the lattice (cfg5: 1 - |<target|G>|^2), reduced on the device so that a training step reads back 22 numbers
+// instead of the lattice.  Deterministic: fixed grid, fixed-order tree per CTA, partials summed in index order by one CTA.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dot_partial(const c128 *__restrict__ x, const c128 *__restrict__ y, long long n, c128 *partial) {
+    __shared__ double red[8][2];
+    c128 acc = c_make(0.0, 0.0);
+    for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += (long long)gridDim.x * blockDim.x) c_fma(acc, x[f], y[f]);
+    acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[warp][0] = acc.x; red[warp][1] = acc.y; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        c128 s = c_make(0.0, 0.0);
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { s.x += red[w][0]; s.y += red[w][1]; }
+        partial[blockIdx.x] = s;
+    }
+}
+__global__ void __launch_bounds__(32) k_dot_finish(const c128 *partial, int nblk, c128 *out) {
+    c128 s = c_make(0.0, 0.0);
+    for (int b = threadIdx.x; b < nblk; b += 32) { s.x += partial[b].x; s.y += partial[b].y; }
+    s.x = warp_sum(s.x); s.y = warp_sum(s.y);
+    if (threadIdx.x == 0) out[0] = s;
+}
+cudaError_t mmh_launch_dot(const c128 *x, const c128 *y, long long n, c128 *partial, int nblk, c128 *out, cudaStream_t st) {
+    k_dot_partial<<<nblk, 256, 0, st>>>(x, y, n, partial);
+    k_dot_finish<<<1, 32, 0, st>>>(partial, nblk, out);
+    return cudaGetLastError();
+}

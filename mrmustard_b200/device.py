@@ -28,7 +28,7 @@ from . import _lib
 from ._lib import check, lib, shape_array
 
 __all__ = ["hermite_renormalized", "hermite_renormalized_batched", "vanilla_vjp", "vanilla_batch_vjp",
-           "HermiteRenormalized", "HermiteRenormalizedBatched"]
+           "HermiteRenormalized", "HermiteRenormalizedBatched", "FidelityStep"]
 
 _C128 = torch.complex128
 
@@ -197,3 +197,68 @@ def hermite_renormalized(A, b, c, shape, stable=False, out=None):
         _forward_raw(A, b, c.reshape(1), shape, stable, out)
         return out.view(shape)
     return HermiteRenormalized.apply(A, b, c, shape, bool(stable))
+
+
+class FidelityStep:
+    """One optimisation step's worth of device work for a fidelity cost, BASELINE config 5: L(A, b, c) = 1 - |<target|G(A, b, c)>|^2
+    and its gradient, the quantity `Optimizer.minimize` needs per iteration (mrmustard/training/optimizer.py:82-105 with the
+    custom_vjp of math/jax_vjps/hermite.py:47-102).
+
+        step = FidelityStep(shape, target)            # target: lattice-shaped array (numpy or CUDA tensor), kept on the device
+        loss, dLdA, dLdb, dLdc = step(A, b, c)        # host (numpy) or device triples
+
+    Per call: ONE 21-number H2D copy of the packed triple (host inputs), the forward lattice (mmh_forward), the overlap
+    s = <target|G> (mmh_overlap), the reverse recurrence with the constant cotangent conj(target) (mmh_vjp; the VJP is linear in
+    its cotangent and the fidelity's cotangent is the rank-one -conj(s) conj(target), so the scalar factor is applied to the 21
+    results instead of to the lattice), and ONE D2H copy of 22 numbers.  The lattice never leaves the device and no lattice-sized
+    temporary is formed.  Gradients are returned in the reference's convention (the plain sums dL/dtheta = sum_k (dL/dG_k)
+    dG_k/dtheta that the jax bwd returns and the optimizer then conjugates, optimizer.py:104); dLdA is symmetrised like
+    vanilla_vjp_numba's (gradients.py:79)."""
+
+    def __init__(self, shape, target, device_index=None):
+        self.shape = _shape(shape)
+        self.D = len(self.shape)
+        dev = torch.device("cuda", torch.cuda.current_device() if device_index is None else device_index)
+        self.dev = dev
+        t = target if isinstance(target, torch.Tensor) else torch.from_numpy(__import__("numpy").ascontiguousarray(target))
+        t = t.to(device=dev, dtype=_C128).reshape(self.shape)
+        self.tconj = t.conj().resolve_conj().contiguous()
+        D = self.D
+        self.n_in = D * D + D + 1
+        self.h_in = torch.empty(self.n_in, dtype=_C128).pin_memory()
+        self.d_in = torch.empty(self.n_in, dtype=_C128, device=dev)
+        self.d_out = torch.empty(self.n_in + 1, dtype=_C128, device=dev)          # [s | dA (D*D) | db (D) | dc]
+        self.h_out = torch.empty(self.n_in + 1, dtype=_C128).pin_memory()
+        self.G = torch.empty(self.shape, dtype=_C128, device=dev)
+        self._sh = shape_array(self.shape)
+        self._n = int(self.G.numel())
+
+    def __call__(self, A, b, c):
+        import numpy as np
+        D, dev = self.D, self.dev
+        with torch.cuda.device(dev):
+            st = _stream()
+            if isinstance(A, torch.Tensor) and A.is_cuda:
+                self.d_in[: D * D] = A.reshape(-1)
+                self.d_in[D * D: D * D + D] = b.reshape(-1)
+                self.d_in[D * D + D:] = c.reshape(-1)
+            else:
+                h = self.h_in.numpy()
+                h[: D * D] = np.asarray(A, dtype=np.complex128).reshape(-1)
+                h[D * D: D * D + D] = np.asarray(b, dtype=np.complex128).reshape(-1)
+                h[D * D + D] = complex(np.asarray(c).reshape(()))
+                self.d_in.copy_(self.h_in, non_blocking=True)
+            pA = self.d_in.data_ptr()
+            pb, pc = pA + 16 * D * D, pA + 16 * (D * D + D)
+            po = self.d_out.data_ptr()
+            check(lib.mmh_forward(D, self._sh, pA, pb, pc, self.G.data_ptr(), 0, st))
+            check(lib.mmh_overlap(self._n, self.tconj.data_ptr(), self.G.data_ptr(), po, st))
+            check(lib.mmh_vjp(D, self._sh, self.G.data_ptr(), pc, self.tconj.data_ptr(), po + 16, po + 16 * (1 + D * D),
+                              po + 16 * (1 + D * D + D), st))
+            self.h_out.copy_(self.d_out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        o = self.h_out.numpy()
+        s = complex(o[0])
+        k = -np.conj(s)                                   # dL/dG_k = -conj(s) conj(t_k)
+        loss = 1.0 - (s.real * s.real + s.imag * s.imag)
+        return loss, (k * o[1: 1 + D * D]).reshape(D, D), k * o[1 + D * D: 1 + D * D + D], complex(k * o[1 + D * D + D])

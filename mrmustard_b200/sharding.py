@@ -118,10 +118,11 @@ class CudaPanelOps:
     def sublattice(self, G, shape, A, b, c):
         L = self._lib
         D = len(shape)
-        dA, db, dc = self.to_dev(np.asarray(A)[1:, 1:]), self.to_dev(np.asarray(b)[1:]), self.to_dev(np.asarray(c).reshape(1))
+        if getattr(self, "_keep", None) is None:   # device copies of the sub-triple, made once per plan
+            self._keep = (self.to_dev(np.asarray(A)[1:, 1:]), self.to_dev(np.asarray(b)[1:]), self.to_dev(np.asarray(c).reshape(1)))
+        dA, db, dc = self._keep
         L.check(L.lib.mmh_forward(D - 1, L.shape_array(shape[1:]), dA.data_ptr(), db.data_ptr(), dc.data_ptr(),
                                   G.data_ptr(), 0, self._stream()))
-        self._keep = (dA, db, dc)
 
     def prepare(self, shape, A, b):
         self._A, self._b = self.to_dev(A), self.to_dev(b)
@@ -166,15 +167,38 @@ class SingleLatticePlan:
         self.ops.prepare(self.shape, A, b)
 
     def run(self):
+        """Fill this rank's part of the lattice.  Per panel step the rank first computes the LAST H offsets of its range -- the
+        amplitudes the ranks above it wait for -- hands them to the communication stream (NCCL send / recv over NVLink) and computes
+        the rest of its range while they travel; the next step waits for the received halo only (CUDA events, no host block)."""
         import torch
         dist, ops, G, P = self.dist, self.ops, self.G, self.P
         ops.sublattice(G, self.shape, self.A, self.b, self.c)                 # panel 0, redundantly on every rank
         Gr = torch.view_as_real(G)                                            # NCCL/gloo p2p on the (re, im) view
+        cuda = G.is_cuda
+        split = self.f_hi - min(self.H, self.f_hi - self.f_lo)                # [split, f_hi) is what the ranks above need
+        if cuda and self.sched:
+            if not hasattr(self, "_comm"):
+                self._comm = torch.cuda.Stream(device=G.device)
+            comm, main = self._comm, torch.cuda.current_stream(G.device)
         for s in range(1, self.S0):
-            ops.panel_range(G, self.shape, s, self.f_lo, self.f_hi)
-            if self.sched and s < self.S0 - 1:
-                reqs = [dist.P2POp(dist.isend if snd else dist.irecv, Gr[s * P + lo: s * P + hi], peer)
-                        for peer, lo, hi, snd in self.sched]
+            exchange = bool(self.sched) and s < self.S0 - 1
+            if not exchange:
+                ops.panel_range(G, self.shape, s, self.f_lo, self.f_hi)
+                continue
+            ops.panel_range(G, self.shape, s, split, self.f_hi)                # boundary first
+            reqs = [dist.P2POp(dist.isend if snd else dist.irecv, Gr[s * P + lo: s * P + hi], peer)
+                    for peer, lo, hi, snd in self.sched]
+            if cuda:
+                ready = torch.cuda.Event(); ready.record(main)
+                with torch.cuda.stream(comm):
+                    comm.wait_event(ready)
+                    for w in dist.batch_isend_irecv(reqs):
+                        w.wait()
+                    done = torch.cuda.Event(); done.record(comm)
+                ops.panel_range(G, self.shape, s, self.f_lo, split)            # the rest overlaps the transfer
+                main.wait_event(done)
+            else:
+                ops.panel_range(G, self.shape, s, self.f_lo, split)
                 for w in dist.batch_isend_irecv(reqs):
                     w.wait()
         return G

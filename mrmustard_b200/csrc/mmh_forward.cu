@@ -39,7 +39,7 @@ __device__ void cta_fill_vanilla(const LatticeDesc &d, const c128 *sA, const c12
 // Level-wavefront fill for the stable rule: level n = |k|; threads enumerate the prefix (k_0..k_{D-2})
 // and derive k_{D-1} = n - sum(prefix).
 __device__ void cta_fill_stable(const LatticeDesc &d, const c128 *sA, const c128 *sb, c128 *G,
-                                const double *sq) {
+                                const double *sq, const double *rsq) {
     const int D = d.D;
     const int last = d.shape[D - 1];
     const long long Q = d.N / last;  // number of prefixes
@@ -59,7 +59,7 @@ __device__ void cta_fill_stable(const LatticeDesc &d, const c128 *sA, const c128
             if (kl < 0 || kl >= last) continue;
             k[D - 1] = kl;
             const long long flat = q * last + kl;
-            G[flat] = stable_point(d, sA, sb, G, sq, k, flat);
+            G[flat] = stable_point(d, sA, sb, G, sq, rsq, k, flat);
         }
         __syncthreads();
     }
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) k_fwd_cta(FwdParams p) {
         c128 *G = p.G + l * p.d.N;
         if (threadIdx.x == 0) G[0] = p.c[l];
         __syncthreads();
-        if (STABLE) cta_fill_stable(p.d, sA, sb, G, p.sq);
+        if (STABLE) cta_fill_stable(p.d, sA, sb, G, p.sq, p.rsq);
         else cta_fill_vanilla(p.d, sA, sb, G, p.sq, p.rsq, p.d.D - 1, 0);
     }
 }
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256) k_stable_coop(FwdParams p) {
                 for (int j = 0; j < D - 1; j++) k[j] = kk[o][j];
                 k[D - 1] = kl;
                 const long long flat = kbase[o] + kl;
-                G[flat] = stable_point(d, sA, sb, G, p.sq, k, flat);
+                G[flat] = stable_point(d, sA, sb, G, p.sq, p.rsq, k, flat);
             }
         }
         return;
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256) k_stable_coop(FwdParams p) {
             if (kl < 0 || kl >= last) continue;
             k[D - 1] = kl;
             const long long flat = q * last + kl;
-            G[flat] = stable_point(d, sA, sb, G, p.sq, k, flat);
+            G[flat] = stable_point(d, sA, sb, G, p.sq, p.rsq, k, flat);
         }
     }
 }
@@ -353,8 +353,11 @@ __global__ void __launch_bounds__(256) k_panel_step_walk(FwdParams p, int stage,
         // all loads of the point first, unconditionally (an absent neighbour re-reads the pivot and is not used): with a branch
         // around each of them they issue one L2/DRAM latency after the other, and this kernel is latency bound
         // (ncu: long-scoreboard stall 9.8 cycles per issue, L2 24 %, FP64 29 %)
+        // cache policy: panel s-2 and the output are touched once (streaming, evict-first); panel s-1 is re-read up to NPD times
+        // at distances up to strides[stage+1] behind the sweep -- with the streams kept out of its way L2 retains that window
+        // ((12,)^8: 48 MB), so every amplitude of panel s-1 is fetched from HBM once
         const c128 pv = Gp[f];
-        const c128 pp = Gpp[s >= 2 ? f : 0];
+        const c128 pp = __ldcs(Gpp + (s >= 2 ? f : 0));
         c128 nb[NPD];
 #pragma unroll
         for (int jj = 0; jj < NPD; jj++) nb[jj] = Gp[k[jj] > 0 ? f - st[jj] : f];
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(256) k_panel_step_walk(FwdParams p, int stage,
 #pragma unroll
         for (int jj = 0; jj < NPD; jj++)
             if (k[jj] > 0) val = c_add(val, c_mul(c_scale(sA[stage * D + stage + 1 + jj], sq[k[jj]]), nb[jj]));
-        Gc[f] = c_div_table(val, sqs, rsqs);
+        __stcs(Gc + f, c_div_table(val, sqs, rsqs));
         int carry = 0;
 #pragma unroll
         for (int jj = NPD - 1; jj >= 0; jj--) {
@@ -379,6 +382,24 @@ cudaError_t mmh_launch_panel_step(const FwdParams &p, int stage, int s, long lon
                                   size_t smem, cudaStream_t st) {
     const int npd = p.d.D - 1 - stage;
     if (p.d.N < 0x7fffffffLL && npd >= 1 && npd <= 8) {
+        // a grid-stride sweep wants exactly one resident wave: 8 CTAs per SM were asked for, 6 fit (40 registers), and the
+        // 1.33 waves ran as two
+        {
+            static int per_sm[9] = { 0 }, sms = 0;
+            if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+            if (!per_sm[npd]) {
+                int n = 0;
+                switch (npd) {
+#define MMH_OCC(N) case N: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_panel_step_walk<N>, 256, smem); break;
+                    MMH_OCC(1) MMH_OCC(2) MMH_OCC(3) MMH_OCC(4) MMH_OCC(5) MMH_OCC(6) MMH_OCC(7) MMH_OCC(8)
+#undef MMH_OCC
+                }
+                per_sm[npd] = n > 0 ? n : 1;
+            }
+            const long long need = (f_hi - f_lo + 255) / 256, cap = (long long)per_sm[npd] * sms;
+            grid = (int)(need < cap ? need : cap);
+            if (grid < 1) grid = 1;
+        }
         PanelWalk w;
         long long sd = (long long)grid * 256;
         for (int jj = npd - 1; jj >= 0; jj--) {

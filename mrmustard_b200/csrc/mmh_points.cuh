@@ -45,10 +45,20 @@ __device__ __forceinline__ c128 vanilla_point32(const LatticeDesc &d, const c128
 // All neighbour amplitudes (k - e_i, and k - e_i - e_j once per unordered pair) are fetched FIRST, in one batch of
 // independent loads, and the arithmetic then runs on registers in the reference's order: fetched one by one inside the sum
 // they are D(D+1) dependent-looking L2 round trips per point (the level wavefront is L2-latency bound).
+// x / np for the number of pivots np: powers of two are exact scalings (RN(x / 2^m) == RN(x * 2^-m), also in the subnormal
+// range: both round the same exact quotient), everything else takes the IEEE division
+__device__ __forceinline__ c128 c_div_count(c128 v, int np) {
+    if (np == 1) return v;
+    if (np == 2) return make_double2(__dmul_rn(v.x, 0.5), __dmul_rn(v.y, 0.5));
+    if (np == 4) return make_double2(__dmul_rn(v.x, 0.25), __dmul_rn(v.y, 0.25));
+    if (np == 8) return make_double2(__dmul_rn(v.x, 0.125), __dmul_rn(v.y, 0.125));
+    return c_div_real(v, (double)np);
+}
+
 template <int DMAX>
 static __device__ __forceinline__ c128 stable_point_batched(const LatticeDesc &d, const c128 *sA, const c128 *sb,
-                                                            const c128 *G, const double *__restrict__ sq, const int *k,
-                                                            long long flat) {
+                                                            const c128 *G, const double *__restrict__ sq,
+                                                            const double *__restrict__ rsq, const int *k, long long flat) {
     const int D = d.D;
     c128 p1[DMAX], p2[DMAX][DMAX];   // p1[i] = G[k - e_i], p2[i][j] (i <= j) = G[k - e_i - e_j]
 #pragma unroll
@@ -75,13 +85,13 @@ static __device__ __forceinline__ c128 stable_point_batched(const LatticeDesc &d
             if (j == i) { if (k[i] > 1) val = c_add(val, c_mul(c_scale(sA[i * D + i], sq[k[i] - 1]), p2[i][i])); }
             else if (k[j] > 0) val = c_add(val, c_mul(c_scale(sA[i * D + j], sq[k[j]]), j < i ? p2[j][i] : p2[i][j]));
         }
-        vals = c_add(vals, c_div_real(val, sq[k[i]]));
+        vals = c_add(vals, c_div_table(val, sq[k[i]], rsq[k[i]]));   // == the IEEE quotient bit for bit (mmh_common.cuh), 5 ops instead of ~25
     }
-    return c_div_real(vals, (double)np);
+    return c_div_count(vals, np);
 }
 
 static __device__ c128 stable_point_generic(const LatticeDesc &d, const c128 *sA, const c128 *sb,
-                             const c128 *G, const double *__restrict__ sq, const int *k,
+                             const c128 *G, const double *__restrict__ sq, const double *__restrict__ rsq, const int *k,
                              long long flat) {
     const int D = d.D;
     c128 vals = c_make(0.0, 0.0);
@@ -96,16 +106,16 @@ static __device__ c128 stable_point_generic(const LatticeDesc &d, const c128 *sA
         if (k[i] > 1) val = c_add(val, c_mul(c_scale(sA[i * D + i], sq[k[i] - 1]), G[pivot - d.strides[i]]));
         for (int j = i + 1; j < D; j++)
             if (k[j] > 0) val = c_add(val, c_mul(c_scale(sA[i * D + j], sq[k[j]]), G[pivot - d.strides[j]]));
-        vals = c_add(vals, c_div_real(val, sq[k[i]]));
+        vals = c_add(vals, c_div_table(val, sq[k[i]], rsq[k[i]]));
     }
-    return c_div_real(vals, (double)np);
+    return c_div_count(vals, np);
 }
 
 static __device__ c128 stable_point(const LatticeDesc &d, const c128 *sA, const c128 *sb,
-                             const c128 *G, const double *__restrict__ sq, const int *k,
+                             const c128 *G, const double *__restrict__ sq, const double *__restrict__ rsq, const int *k,
                              long long flat) {
-    if (d.D <= 2) return stable_point_batched<2>(d, sA, sb, G, sq, k, flat);
-    if (d.D <= 4) return stable_point_batched<4>(d, sA, sb, G, sq, k, flat);
-    return stable_point_generic(d, sA, sb, G, sq, k, flat);
+    if (d.D <= 2) return stable_point_batched<2>(d, sA, sb, G, sq, rsq, k, flat);
+    if (d.D <= 4) return stable_point_batched<4>(d, sA, sb, G, sq, rsq, k, flat);
+    return stable_point_generic(d, sA, sb, G, sq, rsq, k, flat);
 }
 

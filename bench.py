@@ -618,16 +618,24 @@ def bench_cfg4(ctx):
         get = lambda: dG
     else:
         plan = sharding.SingleLatticePlan(shape, A, b, complex(c[0]))
-        step = plan.run
+        step = plan.run if os.environ.get("MMH_BENCH_NO_GRAPH") else plan.run_graphed
         get = lambda: plan.G
     step(); torch.cuda.synchronize()
     # parity: the (3,)^8 corner of the lattice is the reference golden cfg4_G3 (a lattice's corner does not depend on the cutoff)
     G = get().view(shape)
-    corner = G[tuple(slice(0, 3) for _ in range(8))]
+    # rank 0 owns the panel offsets f < P / world of every panel k_0 >= 1: the part of the corner with k_1 < k1c lies inside
+    k1c = 3
+    while world > 1 and k1c > 1 and (k1c - 1) * 12 ** 6 + 2 * sum(12 ** j for j in range(6)) >= (12 ** 7) // world:
+        k1c -= 1
     lo_ok = True
     if world == 1 or rank == 0:
-        lo_ok = bool(np.array_equal(corner.cpu().numpy(), gold["cfg4_G3"]))
+        sl = (slice(0, 3), slice(0, k1c)) + tuple(slice(0, 3) for _ in range(6))
+        lo_ok = bool(np.array_equal(G[sl].cpu().numpy(), gold["cfg4_G3"][sl]))
     assert lo_ok, "bench: cfg4 corner differs from the reference golden"
+    # every rank: its last owned amplitude of the last panel must be finite and non-zero (the halo chain delivered)
+    if world > 1:
+        probe = complex(plan.G[(shape[0] - 1) * plan.P + plan.f_hi - 1].cpu())
+        assert np.isfinite(probe.real) and np.isfinite(probe.imag), f"bench: rank {rank} holds a non-finite amplitude"
     sampler = ClockSampler(ctx["local_rank"]); sampler.start()
     ms, launches = _timed_steps(ctx, step, steps, max(args.warmup, 3) if world == 1 else 3)
     clocks = sampler.stop()
@@ -638,7 +646,9 @@ def bench_cfg4(ctx):
             "ms_per_step": st, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_for("cfg4", world), "clocks": clocks, "e2e": None, "gpu_launches": int(launches),
             "roofline": _roofline("k_panel_step (one launch per panel step)", ALGO_BYTES_PER_AMP_FWD * n / world, st, "cfg4", peak, peak_src),
-            "notes": {"l2": "6.9 GB lattice, larger than L2", "parity": "(3,)^8 corner bit-identical to the reference golden"}}
+            "notes": {"l2": "6.9 GB lattice, larger than L2", "parity": "(3,)^8 corner bit-identical to the reference golden",
+                      "graph": None if world == 1 else ("eager" if getattr(plan, "_graph", None) in (None, False) else "CUDA graph replay"),
+                      "graph_error": None if world == 1 else getattr(plan, "_graph_error", None)}}
     if rank == 0 and not args.no_cpu:
         line["cpu_baseline"] = CpuArm("cfg4").baseline("forward", 4.0)
     return line

@@ -166,6 +166,36 @@ class SingleLatticePlan:
                     self.sched.append((r, lo, hi, False))
         self.ops.prepare(self.shape, A, b)
 
+    def run_graphed(self):
+        """run() replayed from a CUDA graph: the per-step host work of the eager loop (two kernel launches, a NCCL group call,
+        four event operations -- ~0.4 ms per step against 0.15 ms of device work at 4 GPUs) is paid once at capture.  NCCL
+        send / recv and the library's launches are all stream-ordered, so the whole march is capturable.  Falls back to the eager
+        loop if capture is not possible (CPU ops, an old NCCL)."""
+        import torch
+        if not self.G.is_cuda:
+            return self.run()
+        if getattr(self, "_graph", None) is None:
+            side = torch.cuda.Stream(device=self.G.device)
+            side.wait_stream(torch.cuda.current_stream(self.G.device))
+            with torch.cuda.stream(side):            # warm-up on the capture stream: scratch, tables, NCCL channels
+                self.run()
+                self.run()
+            torch.cuda.current_stream(self.G.device).wait_stream(side)
+            torch.cuda.synchronize(self.G.device)
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    self.run()
+                self._graph = g
+            except Exception as e:   # pragma: no cover - capture support depends on the NCCL / driver combination
+                self._graph = False
+                self._graph_error = repr(e)
+                torch.cuda.synchronize(self.G.device)
+        if self._graph is False:
+            return self.run()
+        self._graph.replay()
+        return self.G
+
     def run(self):
         """Fill this rank's part of the lattice.  Per panel step the rank first computes the LAST H offsets of its range -- the
         amplitudes the ranks above it wait for -- hands them to the communication stream (NCCL send / recv over NVLink) and computes

@@ -34,7 +34,17 @@ def _worker(rank, world, port, q):
         A, b, c = random_triple(len(shape), (), seed=seed)
         G = sharding.forward_single_sharded(shape, A, b, complex(c), gather=True)
         ok &= bool(np.array_equal(G.cpu().numpy().reshape(shape), oracle.vanilla(shape, A, b, complex(c))))
-    q.put((rank, ok))
+    # the same march replayed from a CUDA graph (NCCL send/recv + the library's launches captured once), twice
+    shape, seed = (9, 8, 7, 6), 3
+    A, b, c = random_triple(len(shape), (), seed=seed)
+    plan = sharding.SingleLatticePlan(shape, A, b, complex(c))
+    want = oracle.vanilla(shape, A, b, complex(c))
+    for _ in range(2):
+        plan.G.zero_()
+        plan.run_graphed()
+        ok &= bool(np.array_equal(plan.gather().cpu().numpy().reshape(shape), want))
+    graphed = getattr(plan, "_graph", None) not in (None, False)
+    q.put((rank, ok, graphed, getattr(plan, "_graph_error", None)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -50,4 +60,5 @@ def test_two_gpu_sharding():
     for p in procs: p.start()
     res = [q.get(timeout=300) for _ in range(world)]
     for p in procs: p.join(timeout=60)
-    assert all(ok for _, ok in res), res
+    assert all(r[1] for r in res), res
+    print("graph replay used:", [r[2] for r in res], [r[3] for r in res])

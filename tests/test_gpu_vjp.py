@@ -122,3 +122,25 @@ def test_linearity_in_cotangent(S):
     a12 = S.vanilla_vjp_numba(G, complex(c), 2.0 * g1 - 3.0 * g2)
     for x1, x2, x12 in zip(a1, a2, a12):
         assert np.allclose(2.0 * np.asarray(x1) - 3.0 * np.asarray(x2), np.asarray(x12), rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("shape,batch", [((40, 40, 40), 1), ((9, 10, 33, 41), 1), ((5, 4, 6, 7, 37), 2), ((3, 2, 3, 2, 20, 70), 1),
+                                         ((33, 33, 5, 4), 3), ((12, 12, 12, 12), 1), ((2, 1, 130, 129), 1)])
+def test_more_shapes_vs_oracle(shape, batch):
+    """Lattices with three to six indices, ragged last dims, small batches: the VJP against the oracle."""
+    import oracle
+    from mrmustard_b200 import strategies as S
+    D = len(shape)
+    rng = np.random.RandomState(D * 7 + batch)
+    if batch == 1:
+        A, b, c = random_triple(D, (), seed=50 + D)
+        G = oracle.vanilla(shape, A * 0.6, b * 0.7, complex(c))
+        g = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+        got, want = S.vanilla_vjp_numba(G, complex(c), g), oracle.vanilla_vjp(G, complex(c), g)
+    else:
+        A, b, c = random_triple(D, (batch,), seed=60 + D)
+        G = oracle.vanilla_batch(shape, A * 0.6, b * 0.7, c)
+        g = rng.standard_normal(G.shape) + 1j * rng.standard_normal(G.shape)
+        got, want = S.vanilla_batch_vjp_numba(G, c, g), oracle.vanilla_batch_vjp(G, c, g)
+    for x, y, nm in zip(got, want, ("dLdA", "dLdb", "dLdc")):
+        assert_parity(np.asarray(x, dtype=np.complex128), np.asarray(y, dtype=np.complex128), f"{shape} {nm} vs oracle")

@@ -47,7 +47,9 @@ def _load() -> ctypes.CDLL:
             raise ImportError(
                 f"mrmustard_b200: CUDA library {SO_PATH} is missing and could not be built ({e}). "
                 "Run `python -m mrmustard_b200.build`; there is no CPU fallback.") from e
-    lib = ctypes.CDLL(SO_PATH)
+    # MMH_LIBRARY: load another build of the same sources (debug hook: scripts/build_racecheck_variant.sh builds the variant whose
+    # tile hand-off uses named barriers so that compute-sanitizer's racecheck can follow it)
+    lib = ctypes.CDLL(os.environ.get("MMH_LIBRARY") or SO_PATH)
     vp, i64, ci, dbl = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double
     p64 = ctypes.POINTER(ctypes.c_int64)
     sig = {

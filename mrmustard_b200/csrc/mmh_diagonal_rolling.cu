@@ -46,11 +46,14 @@ __device__ __forceinline__ long long pre_at(const DiagRollParams &q, int j, int 
     return __ldg(q.Pre + ((long long)j * q.W1 + s) * q.cm1 + v);
 }
 
-// value = (piv * B[i] + sum_{l >= l_lo} A[i, l] G_in[l]) / K
-__device__ __forceinline__ c128 roll_value(const DiagRollParams &q, const c128 *sA, int i, c128 piv, const c128 *G_in, int l_lo, int t, double K) {
-    const int n2 = 2 * q.M;
+// value = (piv * B[i] + sum_l A[i, l] G_in[l]) / K.  The sum always runs over all 2M entries, fully unrolled: the entries below the
+// pivot's first index are exact zeros, and a compile-time trip count keeps G_in in registers (a run-time lower bound put the array
+// in local memory: 162 LDL per thread in the SASS)
+template <int N2>
+__device__ __forceinline__ c128 roll_value(const DiagRollParams &q, const c128 *sA, int i, c128 piv, const c128 (&G_in)[N2], int t, double K) {
     c128 v = r_cmul(piv, q.B[(long long)i * q.nb + t]);
-    for (int l = l_lo; l < n2; l++) v = r_cadd(v, r_cmul(sA[i * n2 + l], G_in[l]));
+#pragma unroll
+    for (int l = 0; l < N2; l++) v = r_cadd(v, r_cmul(sA[i * N2 + l], G_in[l]));
     return make_double2(v.x / K, v.y / K);
 }
 
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(128) k_diag_roll(DiagRollParams q) {
         for (int i = 0; i < n2; i++) {
             const int j = i >> 1;
             if (params[j] + 1 < q.cut[j] && (i != 1 || params[0] + 2 < q.cut[0])) {
-                const c128 v = roll_value(q, sA, i, a0, G_in, 0, t, sq[params[j] + 1]);
+                const c128 v = roll_value<n2>(q, sA, i, a0, G_in, t, sq[params[j] + 1]);
                 q.cur[((long long)i * q.n0_cur + r) * nb + t] = v;
                 if ((i & 1) == 0) a1even[j] = v;
             }
@@ -151,14 +154,14 @@ __global__ void __launch_bounds__(128) k_diag_roll(DiagRollParams q) {
             const c128 piv = a1even[d];
             c128 *cv = q.cur + q.baseD_cur[d] * nb;
             const long long nC = q.nD_cur[d];
-            q.arr0[(flat + q.pst[d]) * nb + t] = roll_value(q, sA, 2 * d + 1, piv, G_in, 2 * d, t, sq[params[d] + 1]);
-            if (params[d] + 2 < q.cut[d]) cv[r * nb + t] = roll_value(q, sA, 2 * d, piv, G_in, 2 * d, t, sq[params[d] + 2]);   // arr2[d]
+            q.arr0[(flat + q.pst[d]) * nb + t] = roll_value<n2>(q, sA, 2 * d + 1, piv, G_in, t, sq[params[d] + 1]);
+            if (params[d] + 2 < q.cut[d]) cv[r * nb + t] = roll_value<n2>(q, sA, 2 * d, piv, G_in, t, sq[params[d] + 2]);   // arr2[d]
 #pragma unroll
             for (int i = d + 1; i < M; i++) {
                 if (params[i] + 1 < q.cut[i]) {
                     const int a = 1 + 2 * (i - d - 1);
-                    cv[((long long)a * nC + r) * nb + t] = roll_value(q, sA, 2 * i, piv, G_in, 2 * d, t, sq[params[i] + 1]);            // arr1010
-                    cv[((long long)(a + 1) * nC + r) * nb + t] = roll_value(q, sA, 2 * i + 1, piv, G_in, 2 * d, t, sq[params[i] + 1]);  // arr1001
+                    cv[((long long)a * nC + r) * nb + t] = roll_value<n2>(q, sA, 2 * i, piv, G_in, t, sq[params[i] + 1]);            // arr1010
+                    cv[((long long)(a + 1) * nC + r) * nb + t] = roll_value<n2>(q, sA, 2 * i + 1, piv, G_in, t, sq[params[i] + 1]);  // arr1001
                 }
             }
         }

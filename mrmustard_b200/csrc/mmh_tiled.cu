@@ -33,6 +33,12 @@
 #ifndef MMH_T2_PRE_EARLY
 #define MMH_T2_PRE_EARLY 1   // 1: the register-only part of step s+1 is issued before the barrier of step s; 0: after its loads
 #endif
+#ifndef MMH_T2_HANDOFF_BAR
+#define MMH_T2_HANDOFF_BAR 0   // 1: debug build for compute-sanitizer racecheck -- the step hand-off ("every compute thread has stored
+                               //    panel s and its halo has arrived") goes through named barriers (bar.sync / bar.arrive), which the tool
+                               //    models, instead of the mbarrier split arrive / wait, which it reports as unsynchronised
+#endif
+#define MMH_T2_BAR_FULL 1    // + k (debug hand-off only): panel buffer k is complete
 #define MMH_T2_NHW 4     // halo warps
 #define MMH_SENTINEL 0xFFFFFFFFFFFFFFFFull
 
@@ -339,7 +345,11 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
             }
             if (p.trace && lane == 0) p.trace[((size_t)tile * S + u) * 8 + 4] = gtimer_ns();
             __syncwarp();            // the lanes' shared-memory stores are ordered before lane 0's (release) arrive
+#if MMH_T2_HANDOFF_BAR
+            bar_arrive(MMH_T2_BAR_FULL + hw, TC + 32);
+#else
             if (lane == 0) mbar_arrive(sync_base + 8u * (unsigned)hw);
+#endif
             if (p.trace && lane == 0) p.trace[((size_t)tile * S + u) * 8 + 3] = gtimer_ns();
             // self-cleaning, off the critical path: put the sentinel back for the next launch
             for (int c = lane; c < HC; c += 32) stg_relaxed_v2(src + c, MMH_SENTINEL, MMH_SENTINEL);
@@ -391,7 +401,7 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
                     }                                                                                 \
         }                                                                                             \
         _Pragma("unroll") for (int r = 0; r < R; r++) sts_c128(bcur + loco[r], v[r]);                 \
-        if (xch) mbar_arrive(sync_base + 8u * (unsigned)(s_ & (NB - 1)));   /* my part of panel s is in shared memory */ \
+        if (xch && !MMH_T2_HANDOFF_BAR) mbar_arrive(sync_base + 8u * (unsigned)(s_ & (NB - 1)));   /* my part of panel s is in shared memory */ \
         _Pragma("unroll") for (int r = 0; r < R; r++) {                                               \
             P2[r] = v[r];                                                                             \
             if (flags[r] & 1u) gpan[gofs[r]] = v[r];                                                  \
@@ -401,7 +411,10 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
         if (p.trace && tidc == 0) p.trace[((size_t)tile * S + s_) * 8 + 2] = gtimer_ns();             \
         /* hand-off to step s+1: every compute warp has written panel s, and the halo of panel s has arrived */ \
         if (have_halo && s_ + 3 <= S - 2) bar_arrive(MMH_T2_BAR_FREE + ((s_ - 1) & (NB - 1)), TC + 32); \
-        if (xch) mbar_wait(sync_base + 8u * (unsigned)(s_ & (NB - 1)), (unsigned)((s_ - 1) >> 2) & 1u); \
+        if (xch) {                                                                                    \
+            if (MMH_T2_HANDOFF_BAR) bar_sync(MMH_T2_BAR_FULL + (s_ & (NB - 1)), TC + (have_halo ? 32 : 0)); \
+            else mbar_wait(sync_base + 8u * (unsigned)(s_ & (NB - 1)), (unsigned)((s_ - 1) >> 2) & 1u); \
+        }                                                                                             \
         if (p.trace && tidc == 0) p.trace[((size_t)tile * S + s_) * 8 + 1] = gtimer_ns();             \
     }
 

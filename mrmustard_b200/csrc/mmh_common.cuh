@@ -86,6 +86,14 @@ __device__ __forceinline__ c128 c_div_table(c128 v, double s, double r) {
     if (!(div_needs_slow(v.x) | div_needs_slow(v.y))) return make_double2(div_fast(v.x, s, r), div_fast(v.y, s, r));
     return make_double2(div_by_table(v.x, s, r), div_by_table(v.y, s, r));
 }
+// the same quotient for the latency-bound 1-D chains: the fast sequence is issued unconditionally and the range test resolves
+// beside it (the test sits in front of the 5-level chain in c_div_table: ~15 cycles on a ~100-cycle dependent step); the rare
+// out-of-range value redoes the division afterwards.  Bit-identical to c_div_table.
+__device__ __forceinline__ c128 c_div_table_spec(c128 v, double s, double r) {
+    c128 q = make_double2(div_fast(v.x, s, r), div_fast(v.y, s, r));
+    if (div_needs_slow(v.x) | div_needs_slow(v.y)) q = make_double2(div_by_table(v.x, s, r), div_by_table(v.y, s, r));
+    return q;
+}
 __device__ __forceinline__ c128 c_div_real(c128 v, double s) {
     return make_double2(__ddiv_rn(v.x, s), __ddiv_rn(v.y, s));
 }

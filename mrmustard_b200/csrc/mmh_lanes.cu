@@ -65,16 +65,17 @@ __global__ void __launch_bounds__(128) k_march_lanes(StageParams p, int ln, int 
         if ((int)threadIdx.x < nw * Lw && cl < p.batch) {
             const c128 Ac = p.A[cl * D * D + (D - 1) * D + (D - 1)], bc = p.b[cl * D + (D - 1)];
             c128 *row = chain + (size_t)threadIdx.x * cpitch;
-            c128 p1 = p.c[cl], p2 = c_make(0.0, 0.0);
+            c128 p1 = p.c[cl], aterm = c_make(0.0, 0.0);   // pipelined as in k_fwd_chain (mmh_march.cu): same operations, same order
             row[0] = p1;
-            double sqm = 0.0;
+            double2 t = sqt[n1 > 1 ? 1 : 0];
             for (int s = 1; s < n1; s++) {
-                const double2 t = sqt[s];
+                const double2 tn = sqt[s + 1 < n1 ? s + 1 : s];
                 c128 v = c_mul(bc, p1);
-                if (s >= 2) v = c_add(v, c_mul(c_scale(Ac, sqm), p2));
-                v = c_div_table(v, t.x, t.y);
+                if (s >= 2) v = c_add(v, aterm);
+                aterm = c_mul(c_scale(Ac, t.x), p1);
+                v = c_div_table_spec(v, t.x, t.y);
                 row[s] = v;
-                p2 = p1; p1 = v; sqm = t.x;
+                p1 = v; t = tn;
             }
         }
         __syncthreads();

@@ -191,17 +191,24 @@ __global__ void __launch_bounds__(128) k_fwd_chain(FwdParams p, int tab) {
     if (l >= p.batch) return;
     const c128 A = p.A[l * D * D + i * D + i], b = p.b[l * D + i];
     c128 *g = p.G + l * p.d.N;
-    c128 p1 = p.c[l], p2 = c_make(0.0, 0.0);
+    // software pipelined like the chain of k_warp_tail: the A-term of step s+1, (A sqrt(s)) G[s-1], and the table entry of step
+    // s+1 are issued beside the quotient of step s, and the quotient's range test resolves beside its fast sequence -- the
+    // dependent chain of a step is b G (2 levels), one add and the 5-level quotient (cfg1: 134 -> ~60 ns per step).
+    // Same operations in the same order as the plain loop: bit-identical.
+#define MMH_CHAIN_TAB(n) (tab ? sqt_chain[(n)] : make_double2(p.sq[(n)], p.rsq[(n)]))
+    c128 p1 = p.c[l], aterm = c_make(0.0, 0.0);
     g[0] = p1;
-    double sqm = 0.0;
+    double2 t = MMH_CHAIN_TAB(S > 1 ? 1 : 0);
     for (int s = 1; s < S; s++) {
-        const double2 t = tab ? sqt_chain[s] : make_double2(p.sq[s], p.rsq[s]);
+        const double2 tn = MMH_CHAIN_TAB(s + 1 < S ? s + 1 : s);
         c128 v = c_mul(b, p1);
-        if (s >= 2) v = c_add(v, c_mul(c_scale(A, sqm), p2));
-        v = c_div_table(v, t.x, t.y);
+        if (s >= 2) v = c_add(v, aterm);
+        aterm = c_mul(c_scale(A, t.x), p1);
+        v = c_div_table_spec(v, t.x, t.y);
         g[s] = v;
-        p2 = p1; p1 = v; sqm = t.x;
+        p1 = v; t = tn;
     }
+#undef MMH_CHAIN_TAB
 }
 
 // The same chain for a batch, staged in shared memory: a thread that stores its own amplitude every step writes 16 bytes a
@@ -226,19 +233,19 @@ __global__ void __launch_bounds__(128) k_fwd_chain_rows(FwdParams p) {
     const int nlat = (int)(p.batch - lat0 < T ? p.batch - lat0 : T);
     const long long lc = act ? l : lat0;
     const c128 A = p.A[lc * D * D + i * D + i], b = p.b[lc * D + i];
-    c128 p1 = p.c[lc], p2 = c_make(0.0, 0.0);
-    double sqm = 0.0;
+    c128 p1 = p.c[lc], aterm = c_make(0.0, 0.0);
     for (int c0 = 0, buf = 0; c0 < S; c0 += CH, buf ^= 1) {
         const int cw = S - c0 < CH ? S - c0 : CH;
         c128 *mine = tile + ((size_t)buf * T + threadIdx.x) * PITCH;
         for (int j = 0; j < cw; j++) {
             const int s = c0 + j;
-            if (s > 0) {
+            if (s > 0) {   // pipelined as in k_fwd_chain: aterm = (A sqrt(s-1)) G[s-2] was formed one step earlier
                 const double2 t = sqt_rows[s];
                 c128 v = c_mul(b, p1);
-                if (s >= 2) v = c_add(v, c_mul(c_scale(A, sqm), p2));
-                v = c_div_table(v, t.x, t.y);
-                p2 = p1; p1 = v; sqm = t.x;
+                if (s >= 2) v = c_add(v, aterm);
+                aterm = c_mul(c_scale(A, t.x), p1);
+                v = c_div_table_spec(v, t.x, t.y);
+                p1 = v;
             }
             mine[j] = p1;
         }
@@ -276,6 +283,10 @@ __device__ __forceinline__ c128 shfl_up_c128(c128 v, int delta) {
 }
 __device__ __forceinline__ c128 shfl_c128(c128 v, int src) {
     return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+
+__device__ __forceinline__ void stg_strong(c128 *p, c128 v) {
+    asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 
 __global__ void __launch_bounds__(32) k_warp_tail(StageParams p) {
@@ -327,7 +338,7 @@ __global__ void __launch_bounds__(32) k_warp_tail(StageParams p) {
             c128 v = c_mul(bc, p1);
             if (s >= 2) v = c_add(v, aterm);
             aterm = c_mul(c_scale(Ac, t.x), p1);
-            v = c_div_table(v, t.x, t.y);
+            v = c_div_table_spec(v, t.x, t.y);
             chain[s] = v;
             p1 = v; t = tn;
         }
@@ -345,7 +356,7 @@ __global__ void __launch_bounds__(32) k_warp_tail(StageParams p) {
         aterm[r] = c_make(0.0, 0.0);
         coef[r] = (act[r] && k > 0) ? c_scale(Arow, sqt[k].x) : c_make(0.0, 0.0);
         g[r] = p.G + k;
-        if (act[r]) *g[r] = P1[r];
+        if (act[r]) stg_strong(g[r], P1[r]);   // stage i1 may validate these amplitudes by polling (stage overlap): strong stores
     }
     if (lane == 0) timeline_stamp(p.timeline, 8, 2);   // chain done
     if (S2 < 2) return;
@@ -378,7 +389,7 @@ __global__ void __launch_bounds__(32) k_warp_tail(StageParams p) {
         for (int r = 0; r < 2; r++) {
             P1[r] = v[r];
             g[r] += P;
-            if (act[r]) *g[r] = v[r];
+            if (act[r]) stg_strong(g[r], v[r]);
         }
         t = tn;
     }

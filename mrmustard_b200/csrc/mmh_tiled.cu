@@ -55,6 +55,11 @@ __device__ __forceinline__ void ldg_relaxed_v2(const void *p, unsigned long long
 __device__ __forceinline__ void stg_relaxed_v2(void *p, unsigned long long a, unsigned long long b) {
     asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
+// amplitudes another CTA / kernel validates by polling (halo exports, and the lattice itself under stage overlap) are written with
+// strong stores: the PTX memory model only orders a polling ld.relaxed.gpu against stores that are themselves strong
+__device__ __forceinline__ void stg_relaxed_c128(c128 *p, c128 v) {
+    asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
 // panel-0 amplitude that may not have been written yet (stage overlap): poll until both words differ from the sentinel
 __device__ __forceinline__ c128 poll_c128(const c128 *p, unsigned long long t_giveup, int *err) {
     unsigned long long a, b;
@@ -397,14 +402,14 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
                     if (m < NPD && (flags[r] & (2u << m))) {                                          \
                         unsigned xo_;                                                                 \
                         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(xo_) : "r"(xo_base + 4u * (unsigned)(m * R * TC + r * TC + tidc)) : "memory"); \
-                        __stcg(xpan + xo_, v[r]);                                                     \
+                        stg_relaxed_c128(xpan + xo_, v[r]);   /* polled by the consumer: a strong (relaxed.gpu) store */ \
                     }                                                                                 \
         }                                                                                             \
         _Pragma("unroll") for (int r = 0; r < R; r++) sts_c128(bcur + loco[r], v[r]);                 \
         if (xch && !MMH_T2_HANDOFF_BAR) mbar_arrive(sync_base + 8u * (unsigned)(s_ & (NB - 1)));   /* my part of panel s is in shared memory */ \
         _Pragma("unroll") for (int r = 0; r < R; r++) {                                               \
             P2[r] = v[r];                                                                             \
-            if (flags[r] & 1u) gpan[gofs[r]] = v[r];                                                  \
+            if (flags[r] & 1u) stg_relaxed_c128(gpan + gofs[r], v[r]);   /* the next stage may poll it (poll0) */ \
             if (MMH_T2_PRE_EARLY) pre[r] = c_add(c_mul(b0, v[r]), c_mul(a00s, P1[r]));                \
         }                                                                                             \
         gpan += P; xpan += p.hc_max; sqm = st_.x;                                                     \

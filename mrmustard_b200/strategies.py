@@ -233,9 +233,11 @@ def hermite_multidimensional_1leftoverMode(A, B, G0, cutoffs, rtol=1e-05, atol=1
 def fast_diagonal(A, b, c, output_cutoff, pnr_cutoffs, stable=False):
     """Conditional density matrices, output [*(pnr+1), out+1, out+1]; A, b in bargmann order [m0.. | m0..]
     (strategies/fast_diagonal.py:32-77).  `stable` only changed the rounding of the reference's seed block and is
-    accepted for call compatibility.  For output_cutoff < 2 the reference's weight loop (fast_diagonal.py:68) stops
-    one level early and leaves the top-weight entries wrong; this implementation returns the correct amplitudes
-    (equal to the compactFock path and to the diagonal of the full vanilla lattice)."""
+    accepted for call compatibility.
+    Deviation from the reference (stated by tests/test_gpu_diagonal.py::test_fast_diagonal_deviation): its weight loop
+    `range(1, 2*output_cutoff + 2*sum(pnr_cutoffs) - L)` (fast_diagonal.py:68, L = number of modes) ends before the top weight
+    2*sum(pnr_cutoffs) whenever 2*output_cutoff - L < 1 and leaves the highest-weight conditional density matrices ZERO; this
+    implementation returns the true amplitudes there (equal to the compactFock path and to the diagonal of the vanilla lattice)."""
     pnr_cutoffs = tuple(int(p) for p in pnr_cutoffs)
     L = len(pnr_cutoffs) + 1
     perm = [i for m in range(L) for i in (m, m + L)]

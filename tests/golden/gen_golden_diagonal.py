@@ -81,21 +81,18 @@ def main():
                     f"{name}_G": np.asarray(Gl), f"{name}_Gfast": np.asarray(Gf), f"{name}_Gcompact": np.asarray(Gc)})
         lnames.append(name)
     out["leftover_cases"] = np.array(lnames)
-    # The reference's grad_hermite_multidimensional_1leftoverMode (singleLeftoverMode_grad.py) does not compile under the
-    # numba 0.65 of this image (numba interpreter assertion in peep_hole_list_to_tuple), and its only test is disabled in the
-    # reference (tests/test_math/test_compactFock.py:100) -> no golden vectors can be produced for the leftover Jacobians;
-    # they are pinned by finite differences in tests/test_gpu_diagonal.py.
-    try:
-        from mrmustard.math.lattice.strategies.compactFock.inputValidation import grad_hermite_multidimensional_1leftoverMode
-        A, b, c = out["l2_A"], out["l2_b"], complex(out["l2_c"])
-        A2, b2 = (np.asarray(x) for x in math.backend.reorder_AB_bargmann(A, b))
-        arrs = hermite_multidimensional_1leftoverMode(A2, b2, c, (4, 5))
-        dG0, dA, dB = grad_hermite_multidimensional_1leftoverMode(A2, b2, c, *arrs)
-        out.update(l2_dG0=dG0, l2_dA=dA, l2_dB=dB)
-        out["leftover_grad_reference_runs"] = np.array(True)
-    except Exception as e:  # noqa: BLE001
-        print("reference leftover Jacobians unavailable:", type(e).__name__)
-        out["leftover_grad_reference_runs"] = np.array(False)
+    # The reference's fast_diagonal quirk: its weight loop `range(1, 2*oc + 2*sum(pnr) - L)` (fast_diagonal.py:68) ends before the top
+    # weight 2*sum(pnr) whenever 2*output_cutoff - L < 1, leaving the highest-weight conditional density matrices zero; the compactFock
+    # strategy (and the diagonal of the vanilla lattice) hold the true values.  One such case, both reference outputs stored.
+    A, b, c = triple([0, 1, 2], 17)
+    oc, pnr = 1, (2, 2)
+    Gf = S.fast_diagonal(A, b, c, oc, pnr, False)
+    A2, b2 = math.backend.reorder_AB_bargmann(A, b)
+    Gc = hermite_multidimensional_1leftoverMode(np.asarray(A2), np.asarray(b2), c, (oc + 1,) + tuple(p + 1 for p in pnr))[0]
+    out.update(lq_A=A, lq_b=b, lq_c=np.asarray(c), lq_oc=np.array(oc), lq_pnr=np.array(pnr), lq_Gfast=np.asarray(Gf), lq_Gcompact=np.asarray(Gc))
+    # (The Jacobians of the one-leftover-mode path are generated by tests/golden/gen_golden_leftover_grad.py: the reference's
+    #  grad_hermite_multidimensional_1leftoverMode does not compile under the numba 0.65 of this image, so that generator runs the
+    #  unmodified source with the JIT disabled.)
     path = os.path.join(HERE, "diagonal_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) / 1e6, "MB")

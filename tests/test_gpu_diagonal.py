@@ -237,3 +237,20 @@ def test_cfg4_as_written_eight_modes_cutoff_12(golden):
     assert bool(torch.all(err <= tol)), f"max err {float(err.max())}, max |want| {float(want.max())}"
     assert float(out.imag.abs().max()) <= 1e-14
     assert abs(float(want.sum()) - float(out.real.sum())) <= 1e-9 * float(want.sum())
+
+
+def test_fast_diagonal_deviation(mm, gd):
+    """The one place where this implementation deliberately differs from the reference: for 2*output_cutoff - L < 1 the reference's
+    fast_diagonal weight loop (fast_diagonal.py:68) stops before the top weight and leaves those conditional density matrices zero
+    (golden `lq_Gfast`), while its own compactFock strategy holds the true values (golden `lq_Gcompact`).  Ours equals the
+    compactFock values everywhere and the reference's fast_diagonal wherever that one is filled."""
+    A, b, c = gd["lq_A"], gd["lq_b"], complex(gd["lq_c"])
+    oc, pnr = int(gd["lq_oc"]), tuple(int(x) for x in gd["lq_pnr"])
+    assert 2 * oc - (len(pnr) + 1) < 1
+    F = np.ascontiguousarray(mm.strategies.fast_diagonal(A, b, c, oc, pnr))
+    ref_fast, ref_compact = gd["lq_Gfast"], gd["lq_Gcompact"].transpose(2, 3, 0, 1)
+    assert F.shape == ref_fast.shape
+    assert np.allclose(F, ref_compact, rtol=1e-9, atol=1e-13)
+    missing = np.abs(ref_fast).max(axis=(-2, -1)) == 0.0            # partitions the reference never filled
+    assert missing.any() and missing[pnr] and np.abs(F[pnr]).max() > 1e-6
+    assert np.allclose(F[~missing], ref_fast[~missing], rtol=1e-9, atol=1e-13)

@@ -732,7 +732,10 @@ def extras(ctx, skip):
         hAn, hbn, hcn = np.ascontiguousarray(A), np.ascontiguousarray(b), complex(c[0])
         ms_fused = wall(lambda: step(hAn, hbn, hcn), 20)
         kern = rec["forward"]["ms"] + rec["vjp"]["ms"]
-        rec["train_step_e2e"] = {"wall_ms": ms_fused, "kernel_ms_forward_plus_vjp": kern, "ratio_to_kernels": ms_fused / kern,
+        step_eager = dv.FidelityStep(shape, t, use_graph=False)
+        ms_eager = wall(lambda: step_eager(hAn, hbn, hcn), 20)
+        rec["train_step_e2e"] = {"wall_ms": ms_fused, "wall_ms_without_cuda_graph": ms_eager, "cuda_graph": bool(getattr(step, "_graph", None)),
+                                 "kernel_ms_forward_plus_vjp": kern, "ratio_to_kernels": ms_fused / kern,
                                  "steps_per_s": 1e3 / ms_fused, "h2d_bytes": 336, "d2h_bytes": 22 * 16,
                                  "api": "mrmustard_b200.device.FidelityStep(shape, target)(A, b, c) -> (loss, dLdA, dLdb, dLdc); numpy in, numpy out"}
         ms_np = wall(lambda: mm.strategies.vanilla_vjp_numba(mm.strategies.vanilla_numba(shape, A, b, complex(c[0])), complex(c[0]), np.ones(shape, complex)), 3)

@@ -215,7 +215,8 @@ class FidelityStep:
     dG_k/dtheta that the jax bwd returns and the optimizer then conjugates, optimizer.py:104); dLdA is symmetrised like
     vanilla_vjp_numba's (gradients.py:79)."""
 
-    def __init__(self, shape, target, device_index=None):
+    def __init__(self, shape, target, device_index=None, use_graph=True):
+        self.use_graph = bool(use_graph)
         self.shape = _shape(shape)
         self.D = len(self.shape)
         dev = torch.device("cuda", torch.cuda.current_device() if device_index is None else device_index)
@@ -233,30 +234,64 @@ class FidelityStep:
         self._sh = shape_array(self.shape)
         self._n = int(self.G.numel())
 
+    def _enqueue(self, host_inputs: bool):
+        """H2D of the packed triple (host inputs), forward, overlap, VJP, D2H of the 22 results -- all on the current stream."""
+        D = self.D
+        st = _stream()
+        if host_inputs:
+            self.d_in.copy_(self.h_in, non_blocking=True)
+        pA = self.d_in.data_ptr()
+        pb, pc = pA + 16 * D * D, pA + 16 * (D * D + D)
+        po = self.d_out.data_ptr()
+        check(lib.mmh_forward(D, self._sh, pA, pb, pc, self.G.data_ptr(), 0, st))
+        check(lib.mmh_overlap(self._n, self.tconj.data_ptr(), self.G.data_ptr(), po, st))
+        check(lib.mmh_vjp(D, self._sh, self.G.data_ptr(), pc, self.tconj.data_ptr(), po + 16, po + 16 * (1 + D * D),
+                          po + 16 * (1 + D * D + D), st))
+        self.h_out.copy_(self.d_out, non_blocking=True)
+
+    def _capture(self):
+        """The step as a CUDA graph (two copies + seven kernels with fixed addresses): replaying it removes the per-launch host
+        work of an optimisation loop.  Falls back to eager launches if the capture is refused."""
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        try:
+            with torch.cuda.stream(side):
+                self._enqueue(True)          # warm-up on the capture stream (scratch, tables, plans)
+                self._enqueue(True)
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                self._enqueue(True)
+            self._graph = g
+        except Exception as e:               # pragma: no cover
+            self._graph = False
+            self._graph_error = repr(e)
+            torch.cuda.synchronize(self.dev)
+
     def __call__(self, A, b, c):
         import numpy as np
         D, dev = self.D, self.dev
         with torch.cuda.device(dev):
-            st = _stream()
-            if isinstance(A, torch.Tensor) and A.is_cuda:
-                self.d_in[: D * D] = A.reshape(-1)
-                self.d_in[D * D: D * D + D] = b.reshape(-1)
-                self.d_in[D * D + D:] = c.reshape(-1)
-            else:
+            host = not (isinstance(A, torch.Tensor) and A.is_cuda)
+            if host:
                 h = self.h_in.numpy()
                 h[: D * D] = np.asarray(A, dtype=np.complex128).reshape(-1)
                 h[D * D: D * D + D] = np.asarray(b, dtype=np.complex128).reshape(-1)
                 h[D * D + D] = complex(np.asarray(c).reshape(()))
-                self.d_in.copy_(self.h_in, non_blocking=True)
-            pA = self.d_in.data_ptr()
-            pb, pc = pA + 16 * D * D, pA + 16 * (D * D + D)
-            po = self.d_out.data_ptr()
-            check(lib.mmh_forward(D, self._sh, pA, pb, pc, self.G.data_ptr(), 0, st))
-            check(lib.mmh_overlap(self._n, self.tconj.data_ptr(), self.G.data_ptr(), po, st))
-            check(lib.mmh_vjp(D, self._sh, self.G.data_ptr(), pc, self.tconj.data_ptr(), po + 16, po + 16 * (1 + D * D),
-                              po + 16 * (1 + D * D + D), st))
-            self.h_out.copy_(self.d_out, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+                if getattr(self, "_graph", None) is None and self.use_graph:
+                    self._capture()
+                if getattr(self, "_graph", None):
+                    self._graph.replay()
+                    torch.cuda.synchronize(dev)
+                else:
+                    self._enqueue(True)
+                    torch.cuda.current_stream().synchronize()
+            else:
+                self.d_in[: D * D] = A.reshape(-1)
+                self.d_in[D * D: D * D + D] = b.reshape(-1)
+                self.d_in[D * D + D:] = c.reshape(-1)
+                self._enqueue(False)
+                torch.cuda.current_stream().synchronize()
         o = self.h_out.numpy()
         s = complex(o[0])
         k = -np.conj(s)                                   # dL/dG_k = -conj(s) conj(t_k)

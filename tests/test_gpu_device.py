@@ -121,6 +121,11 @@ def test_fused_fidelity_step_matches_autograd_and_reference(T, dv, golden):
     t /= np.linalg.norm(t)
     step = dv.FidelityStep(shape, t)
     loss, dA, db, dc = step(A, b, c)
+    eager = dv.FidelityStep(shape, t, use_graph=False)(A, b, c)           # graph replay and eager launches give the same bits
+    assert eager[0] == loss and np.array_equal(eager[1], dA) and np.array_equal(eager[2], db) and eager[3] == dc
+    l3, dA3, _, _ = step(A * 0.5, b, c)                                     # the replayed graph reads the NEW inputs
+    assert l3 != loss and not np.array_equal(dA3, dA)
+    assert step(A, b, c)[0] == loss
     G = mm.strategies.vanilla_numba(shape, A, b, complex(c))
     s = np.sum(np.conj(t) * G)
     assert np.isclose(loss, 1.0 - abs(s) ** 2, rtol=1e-12, atol=1e-14)

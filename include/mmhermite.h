@@ -17,6 +17,11 @@
  *   - return value: 0 = OK; negative = invalid-argument class (the Python shim re-raises the
  *     reference's exception type, see mmh_error_string); positive = cudaError_t of the failing call.
  *   - there is NO CPU fallback: without a CUDA device every compute entry point returns an error.
+ *   - streams: calls on one stream are ordered by the stream.  The library keeps ONE set of per-device scratch buffers, so a call on
+ *     a different stream than the previous call first waits (on the device) for the work enqueued so far on the previous stream.
+ *     Entry points that stage a host-built table synchronise `stream` once before returning: mmh_binomial (returns the norm),
+ *     mmh_displacement, mmh_fock_contract, and mmh_diagonal when it takes the rolling-level path; they cannot be captured into a
+ *     CUDA graph, all the others can.
  */
 #ifndef MMHERMITE_H
 #define MMHERMITE_H

@@ -21,7 +21,8 @@
  *     a different stream than the previous call first waits (on the device) for the work enqueued so far on the previous stream.
  *     Entry points that stage a host-built table synchronise `stream` once before returning: mmh_binomial (returns the norm),
  *     mmh_displacement, mmh_fock_contract, and mmh_diagonal when it takes the rolling-level path; they cannot be captured into a
- *     CUDA graph, all the others can.
+ *     CUDA graph, all the others can -- after one un-captured call with the same arguments (scratch buffers, tables and launch
+ *     plans are created on first use; nothing is allocated afterwards).  During capture the cross-stream wait is skipped.
  */
 #ifndef MMHERMITE_H
 #define MMHERMITE_H

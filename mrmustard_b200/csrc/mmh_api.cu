@@ -125,6 +125,12 @@ static int get_ctx(DeviceCtx **out) {
 // previous one first waits (on the device, no host block) for everything enqueued so far on the previous stream, so two streams
 // never run library kernels on the same scratch concurrently.  Single-stream callers pay nothing.  Callers hold g_mutex.
 static int enter_stream(DeviceCtx *ctx, cudaStream_t st) {
+    {   // a stream that is being captured into a CUDA graph must not wait on an event recorded outside the capture (that would
+        // invalidate the capture); the graph's owner orders the replay against other work
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) return MMH_OK;
+        cudaGetLastError();
+    }
     if (ctx->have_last && ctx->last_stream != st) {
         cudaError_t e = cudaEventRecord(ctx->xstream_ev, ctx->last_stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ctx->xstream_ev, 0);

@@ -22,6 +22,10 @@
 #include "mmh_params.cuh"
 
 #define MMH_ROLL_MAXM 8
+#ifndef MMH_ROLL_MINB
+#define MMH_ROLL_MINB 4   // resident CTAs per SM asked of ptxas (128 registers, 48 B spilled): the gathers are latency bound and want the
+                          // occupancy -- 8-mode cutoff 12: 369 ms at 2 CTAs per SM, 271 at 3, 254 at 4
+#endif
 
 __device__ __forceinline__ c128 r_cmul(c128 x, c128 y) { return make_double2(x.x * y.x - x.y * y.y, x.x * y.y + x.y * y.x); }
 __device__ __forceinline__ c128 r_cadd(c128 x, c128 y) { return make_double2(x.x + y.x, x.y + y.y); }
@@ -53,12 +57,12 @@ template <int N2>
 __device__ __forceinline__ c128 roll_value(const DiagRollParams &q, const c128 *sA, int i, c128 piv, const c128 (&G_in)[N2], int t, double K) {
     c128 v = r_cmul(piv, q.B[(long long)i * q.nb + t]);
 #pragma unroll
-    for (int l = 0; l < N2; l++) v = r_cadd(v, r_cmul(sA[i * N2 + l], G_in[l]));
+    for (int l = 0; l < N2; l++) c_fma(v, sA[i * N2 + l], G_in[l]);   // fused multiply-adds: this path is tolerance-gated (1e-10), not bit-exact
     return make_double2(v.x / K, v.y / K);
 }
 
 template <int MT>
-__global__ void __launch_bounds__(128) k_diag_roll(DiagRollParams q) {
+__global__ void __launch_bounds__(128, MMH_ROLL_MINB) k_diag_roll(DiagRollParams q) {
     extern __shared__ c128 sA[];
     constexpr int M = MT, n2 = 2 * MT;
     for (int e = threadIdx.x; e < n2 * n2; e += blockDim.x) sA[e] = q.A[e];
@@ -112,9 +116,8 @@ __global__ void __launch_bounds__(128) k_diag_roll(DiagRollParams q) {
     const c128 a0 = q.arr0[flat * nb + t];
 
     // ---- diagonal pivot [a,a,b,b,...] (diagonal_amps.py:98-141) ----
-    c128 a1even[M];   // arr1[2d, params]: the pivots of the off-diagonal steps below
-#pragma unroll
-    for (int d = 0; d < M; d++) a1even[d] = make_double2(0.0, 0.0);
+    c128 a1_0 = make_double2(0.0, 0.0);   // arr1[0, params]: the pivot of the off-diagonal step d = 0 (the pivots d >= 1, used only where
+                                          // params[:d] == 0, are re-read from the level buffer this thread has just written)
     c128 G_in[n2];
     if (q.cut[0] == 1 || params[0] < q.cut[0] - 1) {
 #pragma unroll
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(128) k_diag_roll(DiagRollParams q) {
             if (params[j] + 1 < q.cut[j] && (i != 1 || params[0] + 2 < q.cut[0])) {
                 const c128 v = roll_value<n2>(q, sA, i, a0, G_in, t, sq[params[j] + 1]);
                 q.cur[((long long)i * q.n0_cur + r) * nb + t] = v;
-                if ((i & 1) == 0) a1even[j] = v;
+                if (i == 0) a1_0 = v;
             }
         }
     }
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(128) k_diag_roll(DiagRollParams q) {
                     G_in[2 * i + 1] = r_cscale(pv[((long long)a * nP + nbr[i]) * nb + t], sq[params[i]]);            // arr1010[d, i]
                 }
             }
-            const c128 piv = a1even[d];
+            const c128 piv = d == 0 ? a1_0 : q.cur[((long long)(2 * d) * q.n0_cur + r) * nb + t];
             c128 *cv = q.cur + q.baseD_cur[d] * nb;
             const long long nC = q.nD_cur[d];
             q.arr0[(flat + q.pst[d]) * nb + t] = roll_value<n2>(q, sA, 2 * d + 1, piv, G_in, t, sq[params[d] + 1]);

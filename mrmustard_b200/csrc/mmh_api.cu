@@ -278,9 +278,71 @@ static int forward_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st, b
     return MMH_OK;
 }
 
+// K1r plan (mmh_rows.cu k_march_rows) for a given box grid over the panel dims of `stage` (all of them: npd = 2 or 3, so that the
+// last panel dim is contiguous): lanes own R consecutive cells of a row.  R = 2 (16 compute warps, four per scheduler) measured
+// best on cfg2 (121 us against 127 us at R = 5 and 131 us for k_march_tiled2); larger R only where R = 2 needs more than 512 lanes.
+static bool plan_rows_for_grid(const LatticeDesc &d, int stage, const int *gin, int forcedR, TiledParams *tp, int *ntiles_out,
+                               size_t *smem_out) {
+    const int npd = d.D - 1 - stage;
+    if (npd < 2 || npd > 3) return false;
+    if (d.strides[stage] >= (1LL << 31)) return false;
+    const int S = d.shape[stage];
+    const int off = 3 - npd;
+    int shp[3] = { 1, 1, 1 }, g[3] = { 1, 1, 1 }, em[3];
+    for (int m = off; m < 3; m++) { shp[m] = d.shape[stage + 1 + m - off]; g[m] = gin[m - off]; }
+    for (int m = 0; m < 3; m++) {
+        if (g[m] < 1 || g[m] > shp[m]) return false;
+        em[m] = (shp[m] + g[m] - 1) / g[m];
+    }
+    const long long HC = (long long)(g[0] > 1) * em[1] * em[2] + (long long)(g[1] > 1) * em[0] * em[2] + (long long)(g[2] > 1) * em[0] * em[1];
+    const long long HCs = HC > 0 ? HC : 1;
+    if ((double)g[0] * g[1] * g[2] * (double)S * (double)HCs >= 2147483648.0) return false;   // 32-bit export offsets
+    for (int R = 2; R <= 6; R++) {
+        if (forcedR && R != forcedR) continue;
+        const int C = (em[2] + R - 1) / R;
+        const long long lanes = (long long)em[0] * em[1] * C;
+        if (lanes > mmh_rows_max_threads(R)) continue;
+        const int TC = round_up32(lanes);
+        // shared-memory row stride (16-byte cells): the one with the fewest bank conflicts of a quarter-warp's LDS.128
+        int RS = C * R, bestc = 1 << 30;
+        for (int cand = C * R; cand <= C * R + 3; cand++) {
+            int conf = 0;
+            for (int q0 = 0; q0 < 32; q0 += 8) {
+                int cnt[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+                for (int q = q0; q < q0 + 8; q++) cnt[((q / C) * cand + (q % C) * R) & 7]++;
+                for (int b = 0; b < 8; b++) if (cnt[b] > 1) conf += cnt[b] - 1;
+            }
+            if (conf < bestc) { bestc = conf; RS = cand; }
+        }
+        const long long next = (long long)(em[0] + 1) * (em[1] + 1);
+        const long long LS = next * (RS + 1) + RS + 1;   // rows | dim-2 halo cells | zero row
+        const int cells_max = em[0] * em[1] * em[2];
+        const size_t smem = mmh_rows_smem((int)LS, (int)HCs, S, C * R, cells_max, 0);
+        if (smem > 200 * 1024) continue;
+        memset(tp, 0, sizeof(*tp));
+        tp->d = d; tp->stage = stage; tp->nt = npd;
+        for (int m = off; m < 3; m++) tp->g[m - off] = g[m];
+        for (int m = npd; m < 3; m++) tp->g[m] = 1;
+        tp->tc = TC; tp->ls_max = (int)LS; tp->hc_max = (int)HCs;
+        tp->rows_R = R; tp->rows_C = C; tp->rs = RS; tp->cells_max = cells_max; tp->xc_max = 0;
+        *ntiles_out = g[0] * g[1] * g[2];
+        *smem_out = smem;
+        return true;
+    }
+    return false;
+}
+
 // K1 plan: tile grid over the first nt panel dims of `stage` (mmh_march.cu k_march_tiled)
 static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, TiledParams *tp, int *R_out,
                              int *ntiles_out, size_t *smem_out, double *cost_out = nullptr) {
+    // test / tuning hook: MMH_ROWS_G="g0,g1,g2" forces k_march_rows with that box grid (MMH_ROWS_R: cells per lane)
+    const int rows_forcedR = getenv("MMH_ROWS_R") ? atoi(getenv("MMH_ROWS_R")) : 0;
+    if (const char *eg = getenv("MMH_ROWS_G"))
+        if (!getenv("MMH_NO_ROWS") && (!getenv("MMH_TILE_STAGE") || atoi(getenv("MMH_TILE_STAGE")) == stage)) {
+            int fg[3] = { 1, 1, 1 };
+            sscanf(eg, "%d,%d,%d", &fg[0], &fg[1], &fg[2]);
+            if (plan_rows_for_grid(d, stage, fg, rows_forcedR, tp, ntiles_out, smem_out)) { *R_out = tp->rows_R; return true; }
+        }
     const int npd = d.D - 1 - stage;
     if (npd < 1 || npd > 7) return false;
     const long long P = d.strides[stage];
@@ -340,6 +402,18 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
                 }
             }
     if (best > 1e299) return false;
+    // Boxes with enough arithmetic per step run on the row-lane kernel (mmh_rows.cu) with the same grid: its compute warps do
+    // nothing but the recurrence (service warps import, export and drain).  Small boxes stay on k_march_tiled2, whose step is
+    // bound by the hand-off latency either way (measured: (40,)^4 in 8x8x8 boxes 84 vs 80 us, (50,)^4 in 10x10x10 boxes 121 vs 131 us).
+    if (npd == 3 && inner == 1 && !getenv("MMH_NO_ROWS") && !forced[0]) {
+        const long long min_cells = getenv("MMH_ROWS_MIN_CELLS") ? atoll(getenv("MMH_ROWS_MIN_CELLS")) : 700;
+        long long cells = 1;
+        for (int m = 0; m < 3; m++) cells *= (shp[m] + bg[m] - 1) / bg[m];
+        if (cells >= min_cells && plan_rows_for_grid(d, stage, bg, rows_forcedR, tp, ntiles_out, smem_out)) {
+            *R_out = tp->rows_R;
+            return true;
+        }
+    }
     memset(tp, 0, sizeof(*tp));
     tp->d = d; tp->stage = stage; tp->nt = nt;
     for (int m = 0; m < 3; m++) tp->g[m] = bg[m];
@@ -358,7 +432,7 @@ static bool plan_march_tiled_cached(const LatticeDesc &d, int stage, int sm_coun
     static std::map<std::string, TiledPlan> cache;
     std::string key((const char *)d.shape, sizeof(int) * (size_t)d.D);
     key.push_back((char)stage); key.push_back((char)d.D); key.append(std::to_string(sm_count));
-    for (const char *name : { "MMH_TILE_G", "MMH_TILE_STAGE", "MMH_TILE_R" }) {
+    for (const char *name : { "MMH_TILE_G", "MMH_TILE_STAGE", "MMH_TILE_R", "MMH_NO_ROWS", "MMH_ROWS_G", "MMH_ROWS_R", "MMH_ROWS_MIN_CELLS" }) {
         const char *v = getenv(name);
         key.push_back('|');
         if (v) key.append(v);
@@ -385,6 +459,7 @@ static bool plan_march_tiled_cached(const LatticeDesc &d, int stage, int sm_coun
 // fill of its tile pipeline run on the SMs that lattice seq's tile pipeline has already vacated.  Every kMaxInFlight-th lattice
 // is launched in plain stream order (full wait), which makes the reuse of an exchange-buffer slot (seq % kMaxInFlight) safe.
 static const int kMaxInFlight = 4;
+struct PendingTrace { unsigned long long *dev; size_t words; int stage; int hdr[8]; };
 static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st, long long seq) {
     const LatticeDesc &d = p.d;
     const int D = d.D;
@@ -400,6 +475,14 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
     }
     bool chain_done = false, first = true;
     int rc;
+    std::vector<PendingTrace> traces;   // MMH_TRACE_FILE: per-stage debug timelines, read back at the end
+    const size_t kTraceArenaWords = 4u << 20;   // one arena, allocated and cleared before the first launch (no sync between stages)
+    unsigned long long *trace_arena = nullptr;
+    size_t trace_used = 0;
+    if (getenv("MMH_TRACE_FILE")) {
+        CK(cudaMalloc(&trace_arena, kTraceArenaWords * 8));
+        CK(cudaMemsetAsync(trace_arena, 0, kTraceArenaWords * 8, st));
+    }
     // Stage overlap: when the last two marched stages are both tiled, the last one does not wait for its predecessor's
     // kernel but for the amplitudes themselves (TiledParams::poll0).  Its panel 0 -- the first strides[i0] amplitudes of
     // G -- is pre-filled with the sentinel before anything runs, and the two kernels get disjoint exchange buffers.
@@ -412,7 +495,7 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
     bool pipelined = false;          // this lattice's first kernels are chained behind the previous lattice's (see kMaxInFlight)
     size_t xbase = 0;                // exchange-buffer slot of this lattice
     size_t xoff1 = 0;                // exchange-buffer offset (bytes) of stage i0 when it overlaps stage i1
-    if (use_pdl && i1 >= 0 && !getenv("MMH_TRACE_FILE") && !getenv("MMH_NO_OVERLAP")) {
+    if (use_pdl && i1 >= 0 && (!getenv("MMH_TRACE_FILE") || getenv("MMH_TRACE_OVERLAP")) && !getenv("MMH_NO_OVERLAP")) {
         int L_, R_, T_, n0 = 0, n1 = 0;
         size_t sm_;
         TiledParams t0, t1;
@@ -496,6 +579,9 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
             tp.pdl = (use_pdl && !first) ? 1 : 0;
             first = false;
             tp.poll0 = ((overlap && i == i0) || (overlap1 && i == i1)) ? 1 : 0;
+            tp.strong_g = (overlap && i == i1) ? 1 : 0;   // only a stage that a later stage polls needs strong lattice stores
+            tp.dbg = getenv("MMH_ROWS_DBG") ? atoi(getenv("MMH_ROWS_DBG")) : 0;
+            if (tp.dbg & 2) tp.strong_g = 1;
             {   // exchange buffer: grow-only scratch, (re)filled with the sentinel whenever it is (re)allocated
                 const size_t xoff = xbase + ((overlap && i == i0) ? xoff1 : 0);
                 const size_t xbytes = xoff + sizeof(c128) * (size_t)ntiles * d.shape[i] * tp.hc_max;
@@ -508,24 +594,19 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
             const char *trace_file = getenv("MMH_TRACE_FILE");   // debug timeline of the tile pipeline
             const size_t trace_words = (size_t)ntiles * d.shape[i] * 8;
             if (trace_file) {
-                CK(cudaMalloc(&tp.trace, trace_words * 8));
-                CK(cudaMemset(tp.trace, 0, trace_words * 8));
+                if (trace_used + trace_words > kTraceArenaWords) return MMH_ERR_TOO_LARGE;
+                tp.trace = trace_arena + trace_used;
+                trace_used += trace_words;
             }
             g_launches++;
-            CK(mmh_launch_march_tiled2(tp, R, ntiles, sm, st));
-            if (trace_file) {
-                std::vector<unsigned long long> h(trace_words);
-                CK(cudaStreamSynchronize(st));
-                CK(cudaMemcpy(h.data(), tp.trace, trace_words * 8, cudaMemcpyDeviceToHost));
-                CK(cudaFree(tp.trace));
-                char name[512];
-                snprintf(name, sizeof(name), "%s.stage%d.bin", trace_file, i);
-                if (FILE *fp = fopen(name, "wb")) {
-                    const int hdr[8] = { ntiles, d.shape[i], tp.g[0], tp.g[1], tp.g[2], R, tp.tc, 0 };
-                    fwrite(hdr, sizeof(int), 8, fp);
-                    fwrite(h.data(), 8, trace_words, fp);
-                    fclose(fp);
-                }
+            if (tp.rows_R) CK(mmh_launch_march_rows(tp, ntiles, sm, st));
+            else CK(mmh_launch_march_tiled2(tp, R, ntiles, sm, st));
+            if (trace_file) {   // read back after the whole lattice has been enqueued (the stages overlap)
+                PendingTrace pt;
+                pt.dev = tp.trace; pt.words = trace_words; pt.stage = i;
+                pt.hdr[0] = ntiles; pt.hdr[1] = d.shape[i]; pt.hdr[2] = tp.g[0]; pt.hdr[3] = tp.g[1]; pt.hdr[4] = tp.g[2];
+                pt.hdr[5] = R; pt.hdr[6] = tp.tc; pt.hdr[7] = 0;
+                traces.push_back(pt);
             }
         } else {
             const long long P = d.strides[i];
@@ -542,6 +623,21 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
         g_launches++;
         CK(mmh_launch_chain(p, st));
     }
+    if (!traces.empty()) {
+        CK(cudaStreamSynchronize(st));
+        for (const PendingTrace &pt : traces) {
+            std::vector<unsigned long long> h(pt.words);
+            CK(cudaMemcpy(h.data(), pt.dev, pt.words * 8, cudaMemcpyDeviceToHost));
+            char name[512];
+            snprintf(name, sizeof(name), "%s.stage%d.bin", getenv("MMH_TRACE_FILE"), pt.stage);
+            if (FILE *fp = fopen(name, "wb")) {
+                fwrite(pt.hdr, sizeof(int), 8, fp);
+                fwrite(h.data(), 8, pt.words, fp);
+                fclose(fp);
+            }
+        }
+    }
+    if (trace_arena) { CK(cudaStreamSynchronize(st)); CK(cudaFree(trace_arena)); }
     return MMH_OK;
 }
 

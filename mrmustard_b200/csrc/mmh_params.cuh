@@ -79,6 +79,13 @@ struct TiledParams {
     int tc;                      // compute threads (multiple of 32); the CTA adds its halo warps on top
     int ls_max;                  // shared-memory stride of one panel buffer (>= local box size of any tile)
     int hc_max;                  // shared-memory stride of one halo ring slot (>= halo cells of any tile)
+    int rows_R;                  // 0: k_march_tiled2 (mmh_tiled.cu); > 0: k_march_rows (mmh_rows.cu) with that many cells per lane
+    int rows_C;                  // k_march_rows: lanes per row (chunks of rows_R cells along the last panel dim)
+    int rs;                      // k_march_rows: cells of one shared-memory row (>= rows_C * rows_R, chosen bank-conflict free)
+    int cells_max;               // k_march_rows: cells of the largest box
+    int xc_max;                  // k_march_rows: exported cells of the largest box
+    int strong_g;                // k_march_rows: 1 = lattice stores are strong (a later stage polls them), 0 = streaming stores
+    int dbg;                     // k_march_rows: tuning switches (MMH_ROWS_DBG), 0 in production
     int pdl;                     // 1: launched with programmatic stream serialization
     int poll0;                   // 1: the previous stage's kernel is still running: do not wait for its completion, validate
                                  //    every panel-0 amplitude by the sentinel the host pre-filled it with (stage overlap)
@@ -89,6 +96,10 @@ struct TiledParams {
 
 cudaError_t mmh_launch_march_tiled2(const TiledParams &p, int R, int ntiles, size_t smem, cudaStream_t st);
 size_t mmh_tiled2_smem(int ls_max, int hc_max, int S, int slots);
+cudaError_t mmh_launch_march_rows(const TiledParams &p, int ntiles, size_t smem, cudaStream_t st);
+size_t mmh_rows_smem(int ls_max, int hc_max, int S, int CR, int cells_max, int xc_max);
+int mmh_rows_max_threads(int R);
+bool mmh_rows_supported_R(int R);
 cudaError_t mmh_launch_march_stage(const StageParams &p, int R, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t mmh_launch_warp_tail(const StageParams &p, cudaStream_t st);
 bool mmh_plan_march_box(const LatticeDesc &d, int stage, BoxParams *bp, int *T_out, size_t *smem_out);

@@ -73,3 +73,46 @@ def test_batch_of_large_lattices_pipelined(S, O):
         assert np.array_equal(G[l], O.vanilla(shape, A[l], b[l], complex(c[l]))), l
     G2 = S.vanilla_batch_numba(shape, A, b, c)   # second call reuses the slots
     assert np.array_equal(G, G2)
+
+
+ROWS_CASES = [
+    ((9, 8, 7, 6), ["1,1,1", "2,2,2", "3,1,2", "1,1,3", "2,4,1", "4,3,3"]),   # stage 0: three panel dims, stage 1: two
+    ((7, 20, 19), ["1,1", "2,2", "5,1", "1,6", "7,7"]),                         # stage 0: two panel dims
+    ((5, 6, 5, 4, 3), ["2,2,2", "3,1,1", "1,2,3"]),                             # stages 1 and 2 (stage 0 has four panel dims: tiled2)
+    ((3, 13, 12, 11), ["3,3,2", "2,1,4"]),                                      # ragged boxes, rows longer than one chunk
+]
+
+
+@pytest.mark.parametrize("shape,grids", ROWS_CASES)
+def test_forced_row_lane_march_vs_oracle(S, O, monkeypatch, shape, grids):
+    """k_march_rows (mmh_rows.cu: row-owning compute lanes, service warps for halo import / drain) forced onto small lattices with
+    many box grids and every instantiated cells-per-lane count: bit-identical to the oracle."""
+    from mrmustard_b200 import _lib
+    A, b, c = random_triple(len(shape), (), seed=11 + len(shape))
+    want = O.vanilla(shape, A, b, complex(c))
+    monkeypatch.setenv("MMH_FORCE_TILED", "1")
+    for g in grids:
+        monkeypatch.setenv("MMH_ROWS_G", g)
+        for R in ("2", "3", "4", "5", "6"):
+            monkeypatch.setenv("MMH_ROWS_R", R)
+            n0 = _lib.launch_count()
+            got = S.vanilla_numba(shape, A, b, complex(c))
+            assert _lib.launch_count() > n0
+            assert np.array_equal(got, want), f"shape {shape} box grid {g} R {R}"
+
+
+def test_row_lane_march_default_and_reuse(S, O, golden, monkeypatch):
+    """The planner's own choice on lattices whose boxes are large enough for k_march_rows, repeated launches on the same exchange
+    buffer (self-cleaning sentinel), against the golden cfg2 lattice and against k_march_tiled2 (MMH_NO_ROWS)."""
+    A, b, c = golden["cfg2_A"], golden["cfg2_b"], complex(golden["cfg2_c"])
+    for _ in range(3):
+        assert sha(S.vanilla_numba((50,) * 4, A, b, c)) == str(golden["cfg2_G50_sha"])
+    for shape, seed in [((20, 47, 49, 51), 5), ((12, 60, 33, 40), 6)]:
+        A, b, c = random_triple(4, (), seed=seed)
+        got = S.vanilla_numba(shape, A, b, complex(c))
+        monkeypatch.setenv("MMH_NO_ROWS", "1")
+        ref = S.vanilla_numba(shape, A, b, complex(c))
+        monkeypatch.delenv("MMH_NO_ROWS")
+        assert np.array_equal(got.view(np.int64), ref.view(np.int64)), shape
+        # the recurrence only reads lower indices, so the corner of the large lattice is the small lattice of the same triple
+        assert np.array_equal(got[:3, :9, :9, :9], O.vanilla((3, 9, 9, 9), A, b, complex(c))), shape

@@ -31,6 +31,12 @@
 #define MMH_RW_NSV 4            // service warps (one per panel buffer): halo import, face export, drain to the lattice
 #define MMH_RW_SENTINEL 0xFFFFFFFFFFFFFFFFull
 #define MMH_RW_BAR_FREE 6       // + k: panel buffer k has been read by every compute warp
+#ifndef MMH_RW_HANDOFF_BAR
+#define MMH_RW_HANDOFF_BAR 0    // 1: debug build for compute-sanitizer racecheck -- the panel hand-offs (own cells stored + halo imported,
+                                //    panel drained) go through named barriers, which the tool models, instead of mbarrier arrive / wait
+#endif
+#define MMH_RW_BAR_FULL 1       // + k (debug hand-off only): panel buffer k is complete (compute threads + its service warp)
+#define MMH_RW_BAR_DRAINED 10   // + k (debug hand-off only): panel buffer k has been drained
 
 namespace {
 
@@ -306,10 +312,16 @@ __global__ void __launch_bounds__(MAXT, 1) k_march_rows(TiledParams p) {
                 }
                 if (p.trace && lane == 0) p.trace[((size_t)tile * S + s) * 8 + 4] = rw_timer();
                 __syncwarp();
+#if !MMH_RW_HANDOFF_BAR
                 if (lane == 0) rw_mbar_arrive(mb_halo + 8u * (unsigned)k);
+#endif
                 if (p.trace && lane == 0) p.trace[((size_t)tile * S + s) * 8 + 3] = rw_timer();
             }
+#if MMH_RW_HANDOFF_BAR
+            rw_bar_sync(MMH_RW_BAR_FULL + k, TC + 32);
+#else
             rw_mbar_wait(mb_own + 8u * (unsigned)k, (unsigned)((s - 1) >> 2) & 1u);   // the compute warps have stored panel s
+#endif
             c128 *gpan = p.G + (size_t)s * P;
 #pragma unroll 1
             for (int cb = 0; cb < ncell; cb += 32 * DB) {
@@ -328,7 +340,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_march_rows(TiledParams p) {
                 }
             }
             __syncwarp();
+#if MMH_RW_HANDOFF_BAR
+            if (s + NB < S) rw_bar_arrive(MMH_RW_BAR_DRAINED + k, TC + 32);
+#else
             if (lane == 0) rw_mbar_arrive(mb_drained + 8u * (unsigned)k);
+#endif
             if (imp) for (int c = lane; c < HC; c += 32) rw_stg_relaxed_u64(src + c, MMH_RW_SENTINEL, MMH_RW_SENTINEL);   // self-cleaning
         }
         return;
@@ -372,11 +388,19 @@ __global__ void __launch_bounds__(MAXT, 1) k_march_rows(TiledParams p) {
                 for (int r = 0; r < R; r++) if (r < nact) rw_stg_relaxed(xpan + xo1 + r, acc[r]);
             }
         }
+#if MMH_RW_HANDOFF_BAR
+        if (s > NB) rw_bar_sync(MMH_RW_BAR_DRAINED + k, TC + 32);
+#else
         if (s > NB) rw_mbar_wait(mb_drained + 8u * (unsigned)k, (unsigned)((s - NB - 1) >> 2) & 1u);   // panel s-NB has left this buffer
+#endif
 #pragma unroll
         for (int r = 0; r < R; r++) rw_sts(bcur + own_off + 16u * (unsigned)r, acc[r]);
         if ((xflags & 4u) && s <= S - 2) rw_stg_relaxed(p.X + (size_t)s * p.hc_max + xo2, rw_lds(bcur + xsrc2));
+#if MMH_RW_HANDOFF_BAR
+        rw_bar_sync(MMH_RW_BAR_FULL + k, TC + 32);
+#else
         rw_mbar_arrive(mb_own + 8u * (unsigned)k);   // my cells of panel s are in shared memory
+#endif
         // register-only part of step s+1: b_i P1 + A_ii sqrt(s) P2
         const c128 a00s = c_scale(a00, st.x);
 #pragma unroll
@@ -386,10 +410,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_march_rows(TiledParams p) {
             acc[r] = pn;
         }
         if (p.trace && tidc == 0) p.trace[((size_t)tile * S + s) * 8 + 2] = rw_timer() + 0 * (unsigned long long)__double_as_longlong(acc[0].x + acc[R - 1].y);
+#if !MMH_RW_HANDOFF_BAR
         if (s < S - 1) {
             rw_mbar_wait(mb_own + 8u * (unsigned)k, (unsigned)((s - 1) >> 2) & 1u);
             if (have_halo) rw_mbar_wait(mb_halo + 8u * (unsigned)k, (unsigned)((s - 1) >> 2) & 1u);
         }
+#endif
         if (p.trace && tidc == 0) p.trace[((size_t)tile * S + s) * 8 + 1] = rw_timer();
     }
     if (tl) timeline_stamp(p.timeline, i & 7, 3);

@@ -23,7 +23,13 @@ for shape, grid in [((9, 8, 7, 6), "2,2,2"), ((7, 20, 19), "2,2"), ((5, 6, 5, 4,
     os.environ["MMH_TILE_G"] = grid
     A, b, c = random_triple(len(shape), (), seed=7 + len(shape))
     check(f"tiled {shape} grid {grid}", np.array_equal(S.vanilla_numba(shape, A, b, complex(c)), oracle.vanilla(shape, A, b, complex(c))))
-del os.environ["MMH_FORCE_TILED"], os.environ["MMH_TILE_G"]
+del os.environ["MMH_TILE_G"]
+# row-lane march (k_march_rows): forced box grids, compute / service warp hand-offs, halo exchange through the sentinel buffer
+for shape, grid, R in [((9, 8, 7, 6), "2,2,2", "2"), ((7, 20, 19), "2,2", "3"), ((3, 13, 12, 11), "3,3,2", "5")]:
+    os.environ["MMH_ROWS_G"], os.environ["MMH_ROWS_R"] = grid, R
+    A, b, c = random_triple(len(shape), (), seed=11 + len(shape))
+    check(f"rows {shape} grid {grid} R {R}", np.array_equal(S.vanilla_numba(shape, A, b, complex(c)), oracle.vanilla(shape, A, b, complex(c))))
+del os.environ["MMH_FORCE_TILED"], os.environ["MMH_ROWS_G"], os.environ["MMH_ROWS_R"]
 # default single-lattice path with stage overlap (sentinel-validated panel 0) on a lattice large enough for it
 shape = (16, 17, 18, 19)
 A, b, c = random_triple(4, (), seed=2)

@@ -303,17 +303,10 @@ static bool plan_rows_for_grid(const LatticeDesc &d, int stage, const int *gin, 
         const long long lanes = (long long)em[0] * em[1] * C;
         if (lanes > mmh_rows_max_threads(R)) continue;
         const int TC = round_up32(lanes);
-        // shared-memory row stride (16-byte cells): the one with the fewest bank conflicts of a quarter-warp's LDS.128
-        int RS = C * R, bestc = 1 << 30;
-        for (int cand = C * R; cand <= C * R + 3; cand++) {
-            int conf = 0;
-            for (int q0 = 0; q0 < 32; q0 += 8) {
-                int cnt[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-                for (int q = q0; q < q0 + 8; q++) cnt[((q / C) * cand + (q % C) * R) & 7]++;
-                for (int b = 0; b < 8; b++) if (cnt[b] > 1) conf += cnt[b] - 1;
-            }
-            if (conf < bestc) { bestc = conf; RS = cand; }
-        }
+        // shared-memory row stride (16-byte cells): cell r of chunk ch sits at r * C + ch, so for a fixed r the C lanes of a row read
+        // consecutive cells; with RS congruent to C modulo 8 consecutive rows continue the sequence of bank groups (conflict free)
+        int RS = C * R;
+        while ((RS & 7) != (C & 7)) RS++;
         const long long next = (long long)(em[0] + 1) * (em[1] + 1);
         const long long LS = next * (RS + 1) + RS + 1;   // rows | dim-2 halo cells | zero row
         const int cells_max = em[0] * em[1] * em[2];

@@ -35,6 +35,12 @@
 #define MMH_RW_HANDOFF_BAR 0    // 1: debug build for compute-sanitizer racecheck -- the panel hand-offs (own cells stored + halo imported,
                                 //    panel drained) go through named barriers, which the tool models, instead of mbarrier arrive / wait
 #endif
+#ifndef MMH_RW_DATAFLOW
+#define MMH_RW_DATAFLOW 0       // 1: experiment -- a compute warp of step s+1 waits only for the warps whose rows it reads (per-warp progress
+                                //    words) instead of for the whole CTA.  Measured SLOWER (cfg2 132 vs 121 us: the warps drift apart only until
+                                //    the write-after-read limit of the four buffers, and the polls take issue slots), kept as a switch
+#endif
+#define MMH_RW_NWMAX 16         // compute warps per CTA at most (512 compute threads)
 #define MMH_RW_BAR_FULL 1       // + k (debug hand-off only): panel buffer k is complete (compute threads + its service warp)
 #define MMH_RW_BAR_DRAINED 10   // + k (debug hand-off only): panel buffer k has been drained
 
@@ -104,7 +110,7 @@ __device__ __forceinline__ void rw_div_all(c128 (&v)[R], double sqs, double rsqs
     }
 }
 
-// smem layout (bytes): buf[NB][ls_max] c128 | sqtab[S] double2 | (b_i, A_ii, A_i,last) c128[4] | mbar[3 NB] u64 |
+// smem layout (bytes): buf[NB][ls_max] c128 | sqtab[S] double2 | (b_i, A_ii, A_i,last) c128[4] | mbar[3 NB] u64 | prog[NWMAX] i32 |
 //                      celltab[cells_max] uint2 | hdst[hc_max] u32
 // NPD = panel dims of the stage = tiled dims (the kernel needs strides[stage + NPD] == 1); box dims are right-aligned in
 // (0, 1, 2): dim 2 is always the row direction, leading dims are trivial (extent 1, no halo) when NPD < 3.
@@ -160,7 +166,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_march_rows(TiledParams p) {
     const unsigned mb_own = (unsigned)__cvta_generic_to_shared(sba + 4);   // all compute threads have stored panel s
     const unsigned mb_halo = mb_own + 8u * NB;                               // the import warp has delivered the halo of panel s
     const unsigned mb_drained = mb_halo + 8u * NB;                           // the store warp has drained panel s
-    uint2 *celltab = (uint2 *)((double *)(sba + 4) + 3 * NB);   // per box cell, row-major: (byte offset in a buffer, offset in a lattice panel)
+    int *prog = (int *)((double *)(sba + 4) + 3 * NB);                       // [NWMAX]: last panel compute warp w has stored completely
+    uint2 *celltab = (uint2 *)(prog + MMH_RW_NWMAX);            // per box cell, row-major: (byte offset in a buffer, offset in a lattice panel)
     unsigned *hdst = (unsigned *)(celltab + p.cells_max);   // byte offset of imported halo cell c inside a panel buffer
     const size_t xtile = (size_t)S * p.hc_max;            // X cells per consumer box
 
@@ -170,12 +177,13 @@ __global__ void __launch_bounds__(MAXT, 1) k_march_rows(TiledParams p) {
         rw_mbar_init(mb_halo + 8u * (unsigned)tid, 1u);
         rw_mbar_init(mb_drained + 8u * (unsigned)tid, 1u);
     }
+    if (tid < MMH_RW_NWMAX) prog[tid] = 0;
     for (int s_ = tid; s_ < S; s_ += blockDim.x) sqtab[s_] = make_double2(p.sq[s_], p.rsq[s_]);
     for (int c = tid; c < NB * p.ls_max; c += blockDim.x) smem[c] = c_make(0.0, 0.0);
     if (tid == 0) { sba[0] = p.b[i]; sba[1] = p.A[i * D + i]; sba[2] = p.A[i * D + i + NPD]; }
     for (int c = tid; c < nrows * e[2]; c += blockDim.x) {
         const int r = c % e[2], jj = c / e[2], y0 = jj / e[1], y1 = jj % e[1];
-        celltab[c] = make_uint2((unsigned)(((y0 + 1) * W1 + (y1 + 1)) * RS + r) * 16u,
+        celltab[c] = make_uint2((unsigned)(((y0 + 1) * W1 + (y1 + 1)) * RS + (r % R) * C + r / R) * 16u,
                                 (unsigned)((lo[0] + y0) * gst[0] + (lo[1] + y1) * gst[1] + lo[2] + r));
     }
     // ---- per-lane constants (compute warps) -------------------------------------------------------------------
@@ -186,10 +194,15 @@ __global__ void __launch_bounds__(MAXT, 1) k_march_rows(TiledParams p) {
     const bool act = q >= 0 && j < nrows && r0 < e[2];
     const int nact = act ? (e[2] - r0 < R ? e[2] - r0 : R) : 0;
     const int erow = (x0 + 1) * W1 + (x1 + 1);            // row index in the extended grid
-    const unsigned own_off = act ? (unsigned)(erow * RS + r0) * 16u : zero_base + 16u;
+    // cell r of chunk ch sits at r * C + ch inside its row: for a fixed r the lanes of a warp read consecutive 16-byte cells (the row
+    // stride RS is congruent to C modulo 8, so the rows of a quarter-warp tile the eight bank groups): LDS.128 / STS.128 in four
+    // wavefronts.  (With the chunk's cells adjacent, R = 2 puts the lanes 32 bytes apart: eight wavefronts, measured 35 % of all
+    // shared-memory wavefronts of the kernel.)
+    const unsigned cstep = 16u * (unsigned)C;
+    const unsigned own_off = act ? (unsigned)(erow * RS + ch) * 16u : zero_base + 16u;
     const unsigned n0_off = act ? own_off - (unsigned)(W1 * RS) * 16u : own_off;   // same cells, row one lower in panel dim 0
     const unsigned n1_off = act ? own_off - (unsigned)RS * 16u : own_off;          // ... in panel dim 1
-    const unsigned nbl_off = act ? (r0 > 0 ? own_off - 16u : h2_base + (unsigned)erow * 16u) : zero_base;   // the cell before the lane's first
+    const unsigned nbl_off = act ? (ch > 0 ? own_off - 16u + (unsigned)(R - 1) * cstep : h2_base + (unsigned)erow * 16u) : zero_base;   // the cell before the lane's first: last cell of chunk ch - 1
     const c128 *Arow = p.A + i * D + i;
     c128 c0 = c_make(0.0, 0.0), c1 = c_make(0.0, 0.0);                             // A_ij sqrt(k_j)  (core.py:103)
     if (NPD >= 3 && act && lo[0] + x0 > 0) c0 = c_scale(Arow[1], p.sq[lo[0] + x0]);
@@ -211,7 +224,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_march_rows(TiledParams p) {
         const int e2c = (int)(((long long)(t[2] + 2) * shp[2]) / g[2]) - (int)(((long long)(t[2] + 1) * shp[2]) / g[2]);
         xflags |= 4u;
         xo2 = (unsigned)((size_t)(tile + 1) * xtile) + (unsigned)(h[0] * e[1] * e2c + h[1] * e[0] * e2c + x0 * e[1] + x1);
-        xsrc2 = own_off + (unsigned)(e[2] - 1 - r0) * 16u;
+        xsrc2 = own_off + (unsigned)(e[2] - 1 - r0) * cstep;
     }
     double sq2[R];                                        // sqrt(k_last) of the lane's cells (0 beyond the row / at k = 0)
 #pragma unroll
@@ -234,11 +247,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_march_rows(TiledParams p) {
         int go;
         if (c < F0) {
             const int r = c % e[2], y1 = c / e[2];
-            dst = (unsigned)((y1 + 1) * RS + r) * 16u;
+            dst = (unsigned)((y1 + 1) * RS + (r % R) * C + r / R) * 16u;
             go = (lo[0] - 1) * gst[0] + (lo[1] + y1) * gst[1] + lo[2] + r;
         } else if (c < F0 + F1) {
             const int cc = c - F0, r = cc % e[2], y0 = cc / e[2];
-            dst = (unsigned)((y0 + 1) * W1 * RS + r) * 16u;
+            dst = (unsigned)((y0 + 1) * W1 * RS + (r % R) * C + r / R) * 16u;
             go = (lo[0] + y0) * gst[0] + (lo[1] - 1) * gst[1] + lo[2] + r;
         } else {
             const int cc = c - F0 - F1, y1 = cc % e[1], y0 = cc / e[1];
@@ -258,7 +271,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_march_rows(TiledParams p) {
             for (int r = 0; r < R; r++) P1[r] = r < nact ? __ldcg(p.G + gofs + r) : c_make(0.0, 0.0);
         }
 #pragma unroll
-        for (int r = 0; r < R; r++) if (act) rw_sts(sbase + own_off + 16u * (unsigned)r, P1[r]);
+        for (int r = 0; r < R; r++) if (act) rw_sts(sbase + own_off + cstep * (unsigned)r, P1[r]);
     }
     __syncthreads();
 
@@ -356,6 +369,32 @@ __global__ void __launch_bounds__(MAXT, 1) k_march_rows(TiledParams p) {
 #pragma unroll
     for (int r = 0; r < R; r++) acc[r] = c_mul(b0, P1[r]);   // step 1: A_ii sqrt(0) P2 is skipped (core.py:100)
     if (tl) timeline_stamp(p.timeline, i & 7, 2);
+#if MMH_RW_DATAFLOW && !MMH_RW_HANDOFF_BAR
+    // Per-warp hand-off.  Lanes are row-major, so warp w reads (a) the previous chunk of a row (lane - 1), (b) row x1 - 1 (lane - C),
+    // (c) row x0 - 1 (lane - e1 C): its own warp, the previous one and at most four more.  Read-after-write: wait for those warps' panel s before
+    // step s+1.  Write-after-read: the warps that read MY rows (w + 1 and the one or two warps e1 * C lanes higher) must have
+    // finished step s-3 (they read panel s-4 there) before panel s goes into the same buffer.
+    const int cw = tidc >> 5, nwc = TC >> 5, dl = e[1] * C;
+    constexpr int ND = 5;
+    int raw[ND], war[ND];
+    raw[0] = cw - 1;                                                         // previous chunk of the row (lane - 1)
+    raw[1] = 32 * cw - C >= 0 ? (32 * cw - C) >> 5 : -1;                     // row x1 - 1 (lane - C)
+    raw[2] = 32 * cw + 31 - C >= 0 ? (32 * cw + 31 - C) >> 5 : -1;
+    raw[3] = 32 * cw - dl >= 0 ? (32 * cw - dl) >> 5 : -1;                   // row x0 - 1 (lane - e1 C)
+    raw[4] = 32 * cw + 31 - dl >= 0 ? (32 * cw + 31 - dl) >> 5 : -1;
+    war[0] = cw + 1;
+    war[1] = (32 * cw + C) >> 5;
+    war[2] = (32 * cw + 31 + C) >> 5;
+    war[3] = (32 * cw + dl) >> 5;
+    war[4] = (32 * cw + 31 + dl) >> 5;
+#pragma unroll
+    for (int a = 0; a < ND; a++) {
+        if (raw[a] >= cw) raw[a] = -1;                         // own warp: __syncwarp orders it
+        if (war[a] >= nwc || war[a] <= cw) war[a] = -1;
+#pragma unroll
+        for (int b = 0; b < a; b++) { if (raw[a] == raw[b]) raw[a] = -1; if (war[a] == war[b]) war[a] = -1; }
+    }
+#endif
 
 #pragma unroll 1
     for (int s = 1; s < S; s++) {
@@ -368,8 +407,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_march_rows(TiledParams p) {
 #pragma unroll
         for (int r = 0; r < R; r++) {
             c128 v = acc[r];
-            if (NPD >= 3) v = c_add(v, c_mul(c0, rw_lds(bprev + n0_off + 16u * (unsigned)r)));
-            if (NPD >= 2) v = c_add(v, c_mul(c1, rw_lds(bprev + n1_off + 16u * (unsigned)r)));
+            if (NPD >= 3) v = c_add(v, c_mul(c0, rw_lds(bprev + n0_off + cstep * (unsigned)r)));
+            if (NPD >= 2) v = c_add(v, c_mul(c1, rw_lds(bprev + n1_off + cstep * (unsigned)r)));
             v = c_add(v, c_mul(c_scale(a2, sq2[r]), r ? P1[r > 0 ? r - 1 : 0] : nbl));
             acc[r] = v;
         }
@@ -392,14 +431,30 @@ __global__ void __launch_bounds__(MAXT, 1) k_march_rows(TiledParams p) {
         if (s > NB) rw_bar_sync(MMH_RW_BAR_DRAINED + k, TC + 32);
 #else
         if (s > NB) rw_mbar_wait(mb_drained + 8u * (unsigned)k, (unsigned)((s - NB - 1) >> 2) & 1u);   // panel s-NB has left this buffer
+#if MMH_RW_DATAFLOW
+        if (s > NB) {   // the readers of my rows are past panel s-NB: they have stored panel s-NB+1
+            const int sr = s - NB + 1;
+            int lowest;
+            do {
+                lowest = sr;
+#pragma unroll
+                for (int a = 0; a < ND; a++) if (war[a] >= 0) lowest = min(lowest, ld_acquire_cta_shared(prog + war[a]));
+                if (lowest < sr) __nanosleep(64);
+            } while (lowest < sr);
+        }
+#endif
 #endif
 #pragma unroll
-        for (int r = 0; r < R; r++) rw_sts(bcur + own_off + 16u * (unsigned)r, acc[r]);
+        for (int r = 0; r < R; r++) rw_sts(bcur + own_off + cstep * (unsigned)r, acc[r]);
         if ((xflags & 4u) && s <= S - 2) rw_stg_relaxed(p.X + (size_t)s * p.hc_max + xo2, rw_lds(bcur + xsrc2));
 #if MMH_RW_HANDOFF_BAR
         rw_bar_sync(MMH_RW_BAR_FULL + k, TC + 32);
 #else
-        rw_mbar_arrive(mb_own + 8u * (unsigned)k);   // my cells of panel s are in shared memory
+        rw_mbar_arrive(mb_own + 8u * (unsigned)k);   // my cells of panel s are in shared memory (the service warp waits for all of them)
+#if MMH_RW_DATAFLOW
+        __syncwarp();   // every lane's stores of step s before the warp's progress word (and before its other lanes' loads of step s+1)
+        if ((tid & 31) == 0) st_release_cta_shared(prog + cw, s);
+#endif
 #endif
         // register-only part of step s+1: b_i P1 + A_ii sqrt(s) P2
         const c128 a00s = c_scale(a00, st.x);
@@ -412,7 +467,17 @@ __global__ void __launch_bounds__(MAXT, 1) k_march_rows(TiledParams p) {
         if (p.trace && tidc == 0) p.trace[((size_t)tile * S + s) * 8 + 2] = rw_timer() + 0 * (unsigned long long)__double_as_longlong(acc[0].x + acc[R - 1].y);
 #if !MMH_RW_HANDOFF_BAR
         if (s < S - 1) {
+#if MMH_RW_DATAFLOW
+            int lowest;
+            do {
+                lowest = s;
+#pragma unroll
+                for (int a = 0; a < ND; a++) if (raw[a] >= 0) lowest = min(lowest, ld_acquire_cta_shared(prog + raw[a]));
+                if (lowest < s) __nanosleep(64);
+            } while (lowest < s);
+#else
             rw_mbar_wait(mb_own + 8u * (unsigned)k, (unsigned)((s - 1) >> 2) & 1u);
+#endif
             if (have_halo) rw_mbar_wait(mb_halo + 8u * (unsigned)k, (unsigned)((s - 1) >> 2) & 1u);
         }
 #endif
@@ -451,7 +516,7 @@ bool mmh_rows_supported_R(int R) { return R >= 2 && R <= 6; }
 
 size_t mmh_rows_smem(int ls_max, int hc_max, int S, int CR, int cells_max, int xc_max) {
     (void)CR; (void)xc_max;
-    return sizeof(c128) * ((size_t)MMH_RW_NB * ls_max + (size_t)S + 4) + 8 * 3 * MMH_RW_NB + 8 * (size_t)cells_max +
+    return sizeof(c128) * ((size_t)MMH_RW_NB * ls_max + (size_t)S + 4) + 8 * 3 * MMH_RW_NB + 4 * MMH_RW_NWMAX + 8 * (size_t)cells_max +
            sizeof(unsigned) * (size_t)(hc_max + 4);
 }
 

@@ -593,7 +593,22 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
             }
             g_launches++;
             if (tp.rows_R) CK(mmh_launch_march_rows(tp, ntiles, sm, st));
-            else CK(mmh_launch_march_tiled2(tp, R, ntiles, sm, st));
+            else {
+                // small tile grids (stage 1 of a 4-index lattice: 12-16 tiles) can run as ONE thread-block cluster: halos are pushed
+                // into the consumer's shared memory (mmh_tiled.cu, CL variant) instead of through L2
+                const size_t smc = sm + mmh_tiled2_cluster_extra_smem(tp.hc_max, d.shape[i]);
+                // (opt-in, MMH_CLUSTER=1: bit-identical and measured NEUTRAL on cfg2 -- 119.0 vs 119.4 us, back-to-back 100.8 vs 100.8 us
+                //  per lattice: the lag of stage 1's far tiles comes from the rows of plane k1 = 0 that the one-warp tail kernel
+                //  delivers last, not from the hop through L2)
+                tp.cluster = (ntiles > 1 && ntiles <= 16 && d.D - 1 - i <= 3 && smc <= 200 * 1024 && getenv("MMH_CLUSTER")) ? 1 : 0;
+                cudaError_t ce = cudaSuccess;
+                if (tp.cluster) {
+                    ce = mmh_launch_march_tiled2(tp, R, ntiles, smc, st);
+                    if (getenv("MMH_DEBUG_CLUSTER")) fprintf(stderr, "[mmh] stage %d: cluster launch of %d tiles, %zu B smem: %s\n", i, ntiles, smc, cudaGetErrorString(ce));
+                    if (ce != cudaSuccess) { (void)cudaGetLastError(); tp.cluster = 0; }   // no GPC can host the cluster: through L2
+                }
+                if (!tp.cluster) CK(mmh_launch_march_tiled2(tp, R, ntiles, sm, st));
+            }
             if (trace_file) {   // read back after the whole lattice has been enqueued (the stages overlap)
                 PendingTrace pt;
                 pt.dev = tp.trace; pt.words = trace_words; pt.stage = i;

@@ -289,6 +289,10 @@ __device__ __forceinline__ void stg_strong(c128 *p, c128 v) {
     asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 
+// (Round 2 also measured an anti-diagonal wavefront of the same two stages -- lane l owns rows 2l, 2l+1 and step t computes the cells
+//  with k_{D-2} + k_{D-1} = t, so that the chain and the march overlap: bit-identical, but 32.7 us instead of 15.8 us on cfg2.  One
+//  warp issues ~200 instructions per step either way (~0.3 us); the wavefront needs Sc + S2 such steps, this kernel Sc cheap
+//  one-cell steps of 0.11 us followed by S2 of 0.2 us.)
 __global__ void __launch_bounds__(32) k_warp_tail(StageParams p) {
     __shared__ double2 sqt[64];
     __shared__ c128 chain[64];
@@ -396,6 +400,7 @@ __global__ void __launch_bounds__(32) k_warp_tail(StageParams p) {
 #undef MMH_TAIL_SQ
     if (lane == 0) timeline_stamp(p.timeline, 8, 3);
 }
+
 
 // all-ones sentinel over n amplitudes (stage overlap: panel 0 of the last tiled stage)
 struct FillArgs { ulonglong2 *p; long long n; };

@@ -84,6 +84,7 @@ struct TiledParams {
     int rs;                      // k_march_rows: cells of one shared-memory row (>= rows_C * rows_R, chosen bank-conflict free)
     int cells_max;               // k_march_rows: cells of the largest box
     int xc_max;                  // k_march_rows: exported cells of the largest box
+    int cluster;                 // k_march_tiled2: 1 = the tile grid is one thread-block cluster, halos pushed through distributed shared memory
     int strong_g;                // k_march_rows: 1 = lattice stores are strong (a later stage polls them), 0 = streaming stores
     int dbg;                     // k_march_rows: tuning switches (MMH_ROWS_DBG), 0 in production
     int pdl;                     // 1: launched with programmatic stream serialization
@@ -96,6 +97,7 @@ struct TiledParams {
 
 cudaError_t mmh_launch_march_tiled2(const TiledParams &p, int R, int ntiles, size_t smem, cudaStream_t st);
 size_t mmh_tiled2_smem(int ls_max, int hc_max, int S, int slots);
+size_t mmh_tiled2_cluster_extra_smem(int hc_max, int S);
 cudaError_t mmh_launch_march_rows(const TiledParams &p, int ntiles, size_t smem, cudaStream_t st);
 size_t mmh_rows_smem(int ls_max, int hc_max, int S, int CR, int cells_max, int xc_max);
 int mmh_rows_max_threads(int R);

@@ -81,6 +81,22 @@ __device__ __forceinline__ c128 lds_c128(unsigned addr) {
 __device__ __forceinline__ void sts_c128(unsigned addr, c128 v) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
 }
+// thread-block cluster / distributed shared memory (cluster variant: the whole tile grid is ONE cluster, halo cells are pushed straight
+// into the consumer tile's shared memory instead of through L2)
+__device__ __forceinline__ unsigned mapa_shared(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_c128(unsigned addr, c128 v) {
+    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void lds_volatile_v2(unsigned addr, unsigned long long &a, unsigned long long &b) {
+    asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // mbarrier (shared memory, CTA scope): split arrive / wait, so that the work after a thread's last shared-memory store of a
 // step (lattice store, exports, the register part of the next step) overlaps the wait for the slowest warp and for the halo
 __device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
@@ -122,7 +138,11 @@ __device__ __forceinline__ void div_all2(c128 (&v)[R], double sqs, double rsqs) 
 
 // smem layout (bytes):  buf[NB][ls_max] c128 | sqtab[S] double2 | (b_i, A_ii) c128[2] | sync[8] i32 |
 //                       xo[3][R * TC] u32 (export offsets of the high-face slots)
-template <int R, int NPD>
+// CL: cluster variant.  The tile grid (<= 16 tiles) is launched as one thread-block cluster; the exchange buffer lives in the
+// CONSUMER's shared memory ([S][hc_max] cells, sentinel filled at kernel start), producers push their high-face amplitudes there with
+// st.shared::cluster, the halo warps poll local shared memory.  Same sentinel protocol, no L2 round trip (a hop through L2 costs
+// ~1-2 us for small tiles, and stage 1 of a 4-index lattice pays it on every pipeline hop), nothing to clean up afterwards.
+template <int R, int NPD, bool CL>
 __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(TiledParams p) {
     extern __shared__ c128 smem[];
     const LatticeDesc &d = p.d;
@@ -183,6 +203,16 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
     const unsigned sync_base = (unsigned)__cvta_generic_to_shared(sba + 2);
     const size_t xtile = (size_t)S * p.hc_max;    // X elements per consumer tile
     const unsigned xo_base = sync_base + 32u;     // export offsets (c128 units inside X's panel row), [m][R * TC]
+    // cluster variant: this tile's exchange rows [S][hc_max] in its own shared memory, 16-byte aligned behind the offset table
+    const unsigned xs_base = (xo_base + 4u * (unsigned)(3 * R * TC) + 15u) & ~15u;
+    unsigned xs_up[3] = { 0u, 0u, 0u };           // the same buffer in the upper neighbour tiles (cluster shared window)
+    if (CL) {
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+            if (m < nt && t[m] + 1 < g[m]) xs_up[m] = mapa_shared(xs_base, (unsigned)(tile + (m == 0 ? g[1] * g[2] : (m == 1 ? g[2] : 1))));
+        for (unsigned c = tid; c < (unsigned)(S * p.hc_max); c += blockDim.x)
+            asm volatile("st.shared.v2.u64 [%0], {%1, %2};" ::"r"(xs_base + 16u * c), "l"(MMH_SENTINEL), "l"(MMH_SENTINEL) : "memory");
+    }
 
     // ---- tables that do not touch the lattice (overlap the previous stage's kernel under PDL) ---------------
     if (tid < NB) mbar_init(sync_base + 8u * (unsigned)tid, (unsigned)TC + (HC > 0 ? 1u : 0u));
@@ -247,12 +277,13 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
                 const int a = m == 0 ? 1 : 0, b = m == 2 ? 1 : 2;
                 const int up = tile + (m == 0 ? g[1] * g[2] : (m == 1 ? g[2] : 1));   // the consumer tile
                 flags[r] |= 2u << m;
-                const unsigned xo = (unsigned)(up * xtile) + (unsigned)(fo + (x[a] * ec[b] + x[b]) * inner + rr);
+                const unsigned xo = (CL ? 0u : (unsigned)(up * xtile)) + (unsigned)(fo + (x[a] * ec[b] + x[b]) * inner + rr);
                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(xo_base + 4u * (unsigned)(m * R * TC + q)), "r"(xo) : "memory");
             }
         }
     }
     __syncthreads();
+    if (CL) cluster_sync_all();   // every tile's exchange rows hold the sentinel before any producer pushes into them
     // panel 0 (written by the previous stages' kernels) and X are touched from here on.  Normally that waits for the previous
     // kernel to complete.  With poll0 the previous stage is still marching: every tile starts as soon as ITS part of panel 0
     // exists (the host pre-filled panel 0 with the sentinel), so the tile pipeline of this stage fills while the previous
@@ -300,7 +331,7 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
         // ahead.  The first attempt loads all cells of the panel at once (HCL per lane): ONE L2 round trip when the data
         // is there.  If cells are missing, three lanes watch one canary cell per face (its last cell, exported by the
         // producer's last warps) so that a waiting tile does not hammer L2, then the missing cells are re-polled at once.
-        if (HC == 0) return;
+        if (HC == 0) { if (CL) cluster_sync_all(); return; }
         static_assert(MMH_T2_NHW == MMH_T2_NB, "one halo warp per panel buffer");
         constexpr int HCL = 12;   // cells per lane and round
         const int lane = tid & 31, hw = tid >> 5;
@@ -316,6 +347,7 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
             if (u - (NB - 1) >= 1) bar_sync(MMH_T2_BAR_FREE + hw, TC + 32);   // buffer hw last held panel u-NB, read during step u-NB+1
             if (p.trace && lane == 0) p.trace[((size_t)tile * S + u) * 8 + 5] = gtimer_ns();
             c128 *src = const_cast<c128 *>(xin) + (size_t)u * p.hc_max;
+            const unsigned lsrc = xs_base + 16u * (unsigned)(u * p.hc_max);   // (cluster variant: the same row in local shared memory)
 #pragma unroll 1
             for (int cbase = 0; cbase < HC; cbase += 32 * HCL) {   // (warp-uniform trip count: __any_sync below)
                 const int c0 = cbase + lane;
@@ -327,7 +359,11 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
 #pragma unroll 1
                 while (true) {
 #pragma unroll
-                    for (int w = 0; w < HCL; w++) if ((pend >> w) & 1u) ldg_relaxed_v2(src + c0 + 32 * w, a[w], b[w]);
+                    for (int w = 0; w < HCL; w++)
+                        if ((pend >> w) & 1u) {
+                            if (CL) lds_volatile_v2(lsrc + 16u * (unsigned)(c0 + 32 * w), a[w], b[w]);
+                            else ldg_relaxed_v2(src + c0 + 32 * w, a[w], b[w]);
+                        }
 #pragma unroll
                     for (int w = 0; w < HCL; w++)
                         if (((pend >> w) & 1u) && a[w] != MMH_SENTINEL && b[w] != MMH_SENTINEL) {
@@ -342,8 +378,10 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
                     if (lane < 3 && can_h) {   // wait for the faces' canaries before polling whole faces again
                         unsigned long long a_, b_;
                         unsigned spins = 0;
-                        do { ldg_relaxed_v2(src + can_c, a_, b_); }
-                        while ((a_ == MMH_SENTINEL || b_ == MMH_SENTINEL) && ((++spins & 1023u) != 0u || gtimer_ns() < t_giveup));
+                        do {
+                            if (CL) lds_volatile_v2(lsrc + 16u * (unsigned)can_c, a_, b_);
+                            else ldg_relaxed_v2(src + can_c, a_, b_);
+                        } while ((a_ == MMH_SENTINEL || b_ == MMH_SENTINEL) && ((++spins & 1023u) != 0u || gtimer_ns() < t_giveup));
                     }
                     __syncwarp();
                 }
@@ -357,8 +395,9 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
 #endif
             if (p.trace && lane == 0) p.trace[((size_t)tile * S + u) * 8 + 3] = gtimer_ns();
             // self-cleaning, off the critical path: put the sentinel back for the next launch
-            for (int c = lane; c < HC; c += 32) stg_relaxed_v2(src + c, MMH_SENTINEL, MMH_SENTINEL);
+            if (!CL) for (int c = lane; c < HC; c += 32) stg_relaxed_v2(src + c, MMH_SENTINEL, MMH_SENTINEL);
         }
+        if (CL) cluster_sync_all();   // (all threads of every tile meet here: no tile's shared memory goes away under a late push)
         return;
     }
 
@@ -402,7 +441,8 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
                     if (m < NPD && (flags[r] & (2u << m))) {                                          \
                         unsigned xo_;                                                                 \
                         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(xo_) : "r"(xo_base + 4u * (unsigned)(m * R * TC + r * TC + tidc)) : "memory"); \
-                        stg_relaxed_c128(xpan + xo_, v[r]);   /* polled by the consumer: a strong (relaxed.gpu) store */ \
+                        if (CL) st_cluster_c128(xs_up[m] + 16u * ((unsigned)(s_ * p.hc_max) + xo_), v[r]);             \
+                        else stg_relaxed_c128(xpan + xo_, v[r]);   /* polled by the consumer: a strong (relaxed.gpu) store */ \
                     }                                                                                 \
         }                                                                                             \
         _Pragma("unroll") for (int r = 0; r < R; r++) sts_c128(bcur + loco[r], v[r]);                 \
@@ -434,56 +474,75 @@ __global__ void __launch_bounds__(512 + 32 * MMH_T2_NHW, 1) k_march_tiled2(Tiled
     if (s < S) MMH_T2_STEP(h1, h0, s)
 #undef MMH_T2_STEP
     if (tl) timeline_stamp(p.timeline, i & 7, 3);
+    if (CL) cluster_sync_all();
 }
 
-static cudaError_t launch_pdl2(void (*kern)(TiledParams), int grid, int block, size_t smem, cudaStream_t st, bool pdl,
+static cudaError_t launch_pdl2(void (*kern)(TiledParams), int grid, int block, size_t smem, cudaStream_t st, bool pdl, int cluster,
                                const TiledParams &p) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
+    if (cluster > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = (unsigned)cluster; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        na++;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
-template <int R>
+template <int R, bool CL>
 static cudaError_t launch_tiled2_R(const TiledParams &p, int ntiles, size_t smem, cudaStream_t st) {
     const int block = p.tc + 32 * MMH_T2_NHW;
     static size_t smem_set[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };   // opt-in dynamic shared memory already granted (per instantiation)
 #define MMH_CASE(N)                                                                                   \
     case N:                                                                                           \
         if (smem > 48 * 1024 && smem > smem_set[N]) {                                                 \
-            cudaFuncSetAttribute(k_march_tiled2<R, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            cudaFuncSetAttribute(k_march_tiled2<R, N, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             smem_set[N] = smem;                                                                       \
         }                                                                                             \
-        return launch_pdl2(k_march_tiled2<R, N>, ntiles, block, smem, st, p.pdl != 0, p);
+        if (CL) cudaFuncSetAttribute(k_march_tiled2<R, N, CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); \
+        return launch_pdl2(k_march_tiled2<R, N, CL>, ntiles, block, smem, st, p.pdl != 0, CL ? ntiles : 0, p);
     const int npd = p.d.D - 1 - p.stage;
     switch (npd) {
         MMH_CASE(1) MMH_CASE(2) MMH_CASE(3)
         default: break;
     }
-    if constexpr (R <= 2) {
+    if constexpr (R <= 2 && !CL) {
         switch (npd) { MMH_CASE(4) MMH_CASE(5) default: break; }
     }
-    if constexpr (R == 1) {
+    if constexpr (R == 1 && !CL) {
         switch (npd) { MMH_CASE(6) MMH_CASE(7) default: break; }
     }
 #undef MMH_CASE
     return cudaErrorInvalidValue;
 }
 
-// smem bytes of one CTA of k_march_tiled2 (host planner)
+// smem bytes of one CTA of k_march_tiled2 (host planner); cluster variant: + the tile's exchange rows [S][hc_max]
 size_t mmh_tiled2_smem(int ls_max, int hc_max, int S, int slots) {
     (void)hc_max;
     return sizeof(c128) * ((size_t)MMH_T2_NB * ls_max + (size_t)S + 2) + sizeof(unsigned) * (8 + 3 * (size_t)slots);
 }
+size_t mmh_tiled2_cluster_extra_smem(int hc_max, int S) { return 16 + sizeof(c128) * (size_t)S * (size_t)hc_max; }
 
 cudaError_t mmh_launch_march_tiled2(const TiledParams &p, int R, int ntiles, size_t smem, cudaStream_t st) {
+    if (p.cluster) {
+        switch (R) {
+            case 1: return launch_tiled2_R<1, true>(p, ntiles, smem, st);
+            case 2: return launch_tiled2_R<2, true>(p, ntiles, smem, st);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     switch (R) {
-        case 1: return launch_tiled2_R<1>(p, ntiles, smem, st);
-        case 2: return launch_tiled2_R<2>(p, ntiles, smem, st);
+        case 1: return launch_tiled2_R<1, false>(p, ntiles, smem, st);
+        case 2: return launch_tiled2_R<2, false>(p, ntiles, smem, st);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -116,3 +116,19 @@ def test_row_lane_march_default_and_reuse(S, O, golden, monkeypatch):
         assert np.array_equal(got.view(np.int64), ref.view(np.int64)), shape
         # the recurrence only reads lower indices, so the corner of the large lattice is the small lattice of the same triple
         assert np.array_equal(got[:3, :9, :9, :9], O.vanilla((3, 9, 9, 9), A, b, complex(c))), shape
+
+
+def test_cluster_variant_of_the_tiled_march(S, O, golden, monkeypatch):
+    """MMH_CLUSTER=1: tile grids of <= 16 tiles run as one thread-block cluster and push their halo cells into the consumer tile's
+    shared memory (st.shared::cluster) instead of through the L2 exchange buffer; same sentinel protocol, bit-identical results."""
+    monkeypatch.setenv("MMH_CLUSTER", "1")
+    A, b, c = golden["cfg2_A"], golden["cfg2_b"], complex(golden["cfg2_c"])
+    for _ in range(2):
+        assert sha(S.vanilla_numba((50,) * 4, A, b, c)) == str(golden["cfg2_G50_sha"])   # stage 1: 12 tiles in one cluster
+    monkeypatch.setenv("MMH_FORCE_TILED", "1")
+    for shape, grids in [((9, 8, 7, 6), ["2,2,2", "2,4,1", "4,2,2"]), ((7, 20, 19), ["2,2", "4,4", "1,6"]), ((12, 33), ["2", "11"])]:
+        A, b, c = random_triple(len(shape), (), seed=7 + len(shape))
+        want = O.vanilla(shape, A, b, complex(c))
+        for g in grids:
+            monkeypatch.setenv("MMH_TILE_G", g)
+            assert np.array_equal(S.vanilla_numba(shape, A, b, complex(c)), want), f"shape {shape} tile grid {g}"

@@ -770,6 +770,17 @@ static int vjp_impl(long long batch, int ndim, const int64_t *shape, const void 
             return MMH_OK;
         }
     }
+    // one (or a few) large 4-index lattices: plane tiles staged by the TMA engine (k_vjp_planes)
+    const long long planes_min_n = getenv("MMH_VJP_PLANES_MIN_N") ? atoll(getenv("MMH_VJP_PLANES_MIN_N")) : (1LL << 20);   // test hook
+    if (ndim == 4 && batch <= 8 && d.N >= planes_min_n && mmh_vjp_planes_smem(d) && !getenv("MMH_NO_VJP_PLANES")) {
+        if ((rc = ensure_scratch(ctx->partial, sizeof(c128) * (size_t)batch * ctx->sm_count * p.nacc))) return rc;
+        p.partial = (c128 *)ctx->partial.ptr;
+        p.nblk = ctx->sm_count;
+        int nblk = 0;
+        g_launches += 2;
+        CK(mmh_launch_vjp_planes(p, ctx->sm_count, &nblk, st));
+        return MMH_OK;
+    }
     // batched small lattices: few warps per lattice (long per-thread walks amortise the reduction); one large lattice:
     // 256-thread CTAs, ~8 per SM
     int block = 256;

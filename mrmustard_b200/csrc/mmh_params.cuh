@@ -121,6 +121,8 @@ cudaError_t mmh_launch_panel_step(const FwdParams &p, int stage, int s, long lon
                                   size_t smem, cudaStream_t st);
 cudaError_t mmh_launch_binomial(const BinomParams &p, int block, size_t smem, cudaStream_t st);
 cudaError_t mmh_launch_vjp(const VjpParams &p, int grid_y, int block, cudaStream_t st);
+size_t mmh_vjp_planes_smem(const LatticeDesc &d);
+cudaError_t mmh_launch_vjp_planes(const VjpParams &p, int sm_count, int *nblk_out, cudaStream_t st);
 
 // compactFock diagonal / one-leftover-mode sweep (mmh_diagonal.cu)
 struct DiagParams {

@@ -209,6 +209,218 @@ __global__ void __launch_bounds__(128) k_vjp_finish(VjpParams p) {
     if (lane == 0) vjp_write_entry(p, lat, e, s);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// ONE large 4-index lattice (vanilla_vjp_numba on a 4-mode ket at cutoff 40: cfg5): plane tiles staged by the TMA engine.
+// k_vjp_partial fetches the 15 neighbour amplitudes of every point with scattered 16-byte loads (160 registers, 12 warps per
+// SM: latency x occupancy bound, 0.19 of HBM).  The neighbours of the points of plane (k0, k1) -- its S2 x S3 amplitudes are
+// contiguous -- all lie in six planes:
+//     A0 = (k0, k1): G_k, k-e2, k-e3, k-2e2, k-2e3, k-e2-e3      A1 = (k0, k1-1): k-e1, k-e1-e2, k-e1-e3      A2 = (k0, k1-2): k-2e1
+//     B0 = (k0-1, k1): k-e0, k-e0-e2, k-e0-e3                     B1 = (k0-1, k1-1): k-e0-e1                   C0 = (k0-2, k1): k-2e0
+// A CTA takes a task (k0, segment of k1) and walks k1: the planes A and B rotate through shared memory (4 + 3 slots), each new
+// plane arrives with ONE bulk asynchronous copy (cp.async.bulk global -> shared, mbarrier complete_tx: SASS UBLKCP) issued one
+// step ahead, and every thread then reads its 14 shared-memory neighbours at unit stride (LDS.128, conflict free); k-2e0 and the
+// cotangent g_k are coalesced global loads.  Per point the arithmetic is the one of k_vjp_partial.  Deterministic: static task
+// assignment, fixed-order CTA reduction, partials summed by k_vjp_finish.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void vp_mbar_init(unsigned addr, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void vp_mbar_expect_tx(unsigned addr, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void vp_mbar_wait(unsigned addr, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void vp_bulk_prefetch_l2(const void *gsrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void vp_bulk_g2s(unsigned sdst, const void *gsrc, unsigned bytes, unsigned mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
+}
+
+#define MMH_VP_T 512     // threads per CTA at most
+#define MMH_VP_NP 4      // points of a plane per thread at most
+__global__ void __launch_bounds__(MMH_VP_T, 1) k_vjp_planes(VjpParams p, int nseg) {
+    extern __shared__ c128 vp_smem[];
+    constexpr int NACC = VjpAcc<4>::NACC;   // db0..3 | U00 U01 U02 U03 U11 U12 U13 U22 U23 U33 | dc
+    const LatticeDesc &d = p.d;
+    const int S0 = d.shape[0], S1 = d.shape[1], S2 = d.shape[2], S3 = d.shape[3];
+    const int PL = S2 * S3;                               // amplitudes of one plane
+    const unsigned PLB = (unsigned)PL * 16u;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const long long lat = blockIdx.y;
+    const c128 *G = p.G + lat * d.N;
+    const c128 *g = p.g + lat * d.N;
+    const double *__restrict__ sq = p.sq;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(vp_smem);
+    int kq[MMH_VP_NP];                                    // this thread's points of a plane: k2 << 16 | k3, -1 = none (the same in every plane)
+#pragma unroll
+    for (int n = 0; n < MMH_VP_NP; n++) {
+        const int q = tid + n * T;
+        kq[n] = q < PL ? ((q / S3) << 16) | (q % S3) : -1;
+    }
+    const unsigned mbar = sbase + 7u * PLB;               // two mbarriers behind the seven plane slots
+    if (tid == 0) { vp_mbar_init(mbar, 1u); vp_mbar_init(mbar + 8u, 1u); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    c128 acc[NACC];
+#pragma unroll
+    for (int e = 0; e < NACC; e++) acc[e] = c_make(0.0, 0.0);
+    unsigned cnt = 0;                                     // steps done by this CTA: barrier cnt & 1, parity (cnt >> 1) & 1
+
+    const int ntask = S0 * nseg;
+    for (int task = blockIdx.x; task < ntask; task += gridDim.x) {
+        const int k0 = task / nseg, seg = task - k0 * nseg;
+        const int k1a = (int)(((long long)seg * S1) / nseg), k1b = (int)(((long long)(seg + 1) * S1) / nseg);
+        if (k1a >= k1b) continue;
+        const c128 *Gk0 = G + (long long)k0 * S1 * PL, *Gk0m = G + (long long)(k0 >= 1 ? k0 - 1 : 0) * S1 * PL;
+        const double w0 = sq[k0], h00 = 0.5 * w0 * sq[k0 >= 1 ? k0 - 1 : 0];
+        __syncthreads();                                  // every thread has left the previous task's planes
+        if (tid == 0) {                                   // the planes of the first step
+            unsigned bytes = 0;
+            for (int k1 = k1a - 2; k1 <= k1a; k1++)
+                if (k1 >= 0) { vp_bulk_g2s(sbase + (unsigned)(k1 & 3) * PLB, Gk0 + (long long)k1 * PL, PLB, mbar + 8u * (cnt & 1u)); bytes += PLB; }
+            if (k0 >= 1)
+                for (int k1 = k1a - 1; k1 <= k1a; k1++)
+                    if (k1 >= 0) { vp_bulk_g2s(sbase + (unsigned)(4 + k1 % 3) * PLB, Gk0m + (long long)k1 * PL, PLB, mbar + 8u * (cnt & 1u)); bytes += PLB; }
+            vp_mbar_expect_tx(mbar + 8u * (cnt & 1u), bytes);
+        }
+        for (int k1 = k1a; k1 < k1b; k1++, cnt++) {
+            if (tid == 0 && k1 + 1 < k1b) {               // one step ahead: A(k1+1) replaces A(k1-3), B(k1+1) replaces B(k1-2)
+                const unsigned mb = mbar + 8u * ((cnt + 1u) & 1u);
+                vp_bulk_g2s(sbase + (unsigned)((k1 + 1) & 3) * PLB, Gk0 + (long long)(k1 + 1) * PL, PLB, mb);
+                if (k0 >= 1) vp_bulk_g2s(sbase + (unsigned)(4 + (k1 + 1) % 3) * PLB, Gk0m + (long long)(k1 + 1) * PL, PLB, mb);
+                vp_mbar_expect_tx(mb, k0 >= 1 ? 2u * PLB : PLB);
+                // the cotangent plane of the next step is cold (read once, from HBM): pull it into L2 a step ahead
+                vp_bulk_prefetch_l2(g + ((long long)k0 * S1 + k1 + 1) * PL, PLB);
+            }
+            const c128 *gp = g + ((long long)k0 * S1 + k1) * PL;
+            const c128 *Cp = G + ((long long)(k0 >= 2 ? k0 - 2 : k0) * S1 + k1) * PL;   // plane (k0-2, k1): weight 0 when absent
+            const c128 *sA0 = vp_smem + (size_t)(k1 & 3) * PL;
+            const c128 *sA1 = k1 >= 1 ? vp_smem + (size_t)((k1 - 1) & 3) * PL : sA0;
+            const c128 *sA2 = k1 >= 2 ? vp_smem + (size_t)((k1 - 2) & 3) * PL : sA0;
+            const c128 *sB0 = k0 >= 1 ? vp_smem + (size_t)(4 + k1 % 3) * PL : sA0;
+            const c128 *sB1 = (k0 >= 1 && k1 >= 1) ? vp_smem + (size_t)(4 + (k1 - 1) % 3) * PL : sA0;
+            const double w1 = sq[k1], h11 = 0.5 * w1 * sq[k1 >= 1 ? k1 - 1 : 0], w01 = w0 * w1;
+            // the global operands of all of this thread's points are issued before the wait (their latency overlaps it)
+            c128 gq[MMH_VP_NP], Cq[MMH_VP_NP];
+#pragma unroll
+            for (int n = 0; n < MMH_VP_NP; n++) {
+                const int q = tid + n * T;
+                gq[n] = kq[n] >= 0 ? gp[q] : c_make(0.0, 0.0);
+                Cq[n] = kq[n] >= 0 ? Cp[q] : c_make(0.0, 0.0);
+            }
+            vp_mbar_wait(mbar + 8u * (cnt & 1u), (cnt >> 1) & 1u);
+#pragma unroll
+            for (int n = 0; n < MMH_VP_NP; n++) {
+                if (kq[n] < 0) continue;
+                const int q = tid + n * T;
+                const c128 gk = gq[n], Ck = Cq[n];
+                const int k2 = kq[n] >> 16, k3 = kq[n] & 0xffff;
+                const double w2 = sq[k2], w3 = sq[k3];
+                const int o2 = k2 >= 1 ? S3 : 0, o22 = k2 >= 2 ? 2 * S3 : 0, o3 = k3 >= 1 ? 1 : 0, o33 = k3 >= 2 ? 2 : 0;
+                const int o23 = (k2 >= 1 && k3 >= 1) ? S3 + 1 : 0;
+                // all shared-memory operands first (independent loads), then the arithmetic
+                const c128 a_0 = sA0[q], a_2 = sA0[q - o2], a_3 = sA0[q - o3], a_22 = sA0[q - o22], a_33 = sA0[q - o33], a_23 = sA0[q - o23];
+                const c128 a1_0 = sA1[q], a1_2 = sA1[q - o2], a1_3 = sA1[q - o3], a2_0 = sA2[q];
+                const c128 b_0 = sB0[q], b_2 = sB0[q - o2], b_3 = sB0[q - o3], b1_0 = sB1[q];
+                c_fma(acc[NACC - 1], a_0, gk);                                              // dLdc numerator (gradients.py:80)
+                c_fma(acc[0], c_scale(b_0, w0), gk);                                        // db0   :68
+                c_fma(acc[4], c_scale(Ck, h00), gk);                                        // U00   :69-73
+                c_fma(acc[5], c_scale(b1_0, w01), gk);                                      // U01   :74-75
+                c_fma(acc[6], c_scale(b_2, w0 * w2), gk);                                   // U02
+                c_fma(acc[7], c_scale(b_3, w0 * w3), gk);                                   // U03
+                c_fma(acc[1], c_scale(a1_0, w1), gk);                                       // db1
+                c_fma(acc[8], c_scale(a2_0, h11), gk);                                      // U11
+                c_fma(acc[9], c_scale(a1_2, w1 * w2), gk);                                  // U12
+                c_fma(acc[10], c_scale(a1_3, w1 * w3), gk);                                 // U13
+                c_fma(acc[2], c_scale(a_2, w2), gk);                                        // db2
+                c_fma(acc[11], c_scale(a_22, 0.5 * w2 * sq[k2 >= 1 ? k2 - 1 : 0]), gk);     // U22
+                c_fma(acc[12], c_scale(a_23, w2 * w3), gk);                                 // U23
+                c_fma(acc[3], c_scale(a_3, w3), gk);                                        // db3
+                c_fma(acc[13], c_scale(a_33, 0.5 * w3 * sq[k3 >= 1 ? k3 - 1 : 0]), gk);     // U33
+            }
+            __syncthreads();                              // plane (k0, k1) consumed: the next step's prefetch may overwrite a slot
+        }
+    }
+
+    // CTA reduction: warp shuffles, then one smem pass (fixed order)
+    __shared__ double red[MMH_VP_T / 32][2 * NACC];
+    const int warp = tid >> 5, lane = tid & 31, nwarps = T >> 5;
+#pragma unroll
+    for (int e = 0; e < NACC; e++) {
+        const double re = warp_sum(acc[e].x), im = warp_sum(acc[e].y);
+        if (lane == 0) { red[warp][2 * e] = re; red[warp][2 * e + 1] = im; }
+    }
+    __syncthreads();
+    for (int t = tid; t < 2 * NACC; t += T) {
+        double sum = 0.0;
+        for (int w = 0; w < nwarps; w++) sum += red[w][t];
+        double *out = (double *)(p.partial + (lat * p.nblk + blockIdx.x) * (long long)NACC);
+        out[t] = sum;
+    }
+}
+
+// shared memory of k_vjp_planes: seven plane slots + two mbarriers; 0 when the lattice does not qualify
+size_t mmh_vjp_planes_smem(const LatticeDesc &d) {
+    if (d.D != 4) return 0;
+    const size_t pl = (size_t)d.shape[2] * d.shape[3];
+    const size_t smem = 7 * pl * sizeof(c128) + 16;
+    if (smem > 200 * 1024 || pl < 256 || pl > (size_t)MMH_VP_NP * MMH_VP_T || d.shape[0] < 4 || d.shape[1] < 4) return 0;
+    return smem;
+}
+
+// tasks = shape[0] x nseg segments of k1; nseg is the count that leaves the fewest idle CTA-steps with one CTA per SM
+cudaError_t mmh_launch_vjp_planes(const VjpParams &p_in, int sm_count, int *nblk_out, cudaStream_t st) {
+    VjpParams p = p_in;
+    const size_t smem = mmh_vjp_planes_smem(p.d);
+    if (!smem) return cudaErrorInvalidValue;
+    const int S0 = p.d.shape[0], S1 = p.d.shape[1];
+    int best_nseg = 1;
+    double best_cost = 1e300;
+    for (int nseg = 1; nseg <= S1 && nseg <= 16; nseg++) {
+        const int ntask = S0 * nseg, grid = ntask < sm_count ? ntask : sm_count;
+        const int per_cta = (ntask + grid - 1) / grid;
+        const double L = (double)S1 / nseg;
+        const double cost = per_cta * (L + 1.0);   // steps of the busiest CTA + ~1 step of prologue (three extra plane loads) per task
+        if (cost < best_cost) { best_cost = cost; best_nseg = nseg; }
+    }
+    if (const char *e = getenv("MMH_VJP_NSEG")) best_nseg = atoi(e) > 0 ? atoi(e) : best_nseg;
+    const int ntask = S0 * best_nseg, grid = ntask < sm_count ? ntask : sm_count;
+    p.nblk = grid;
+    *nblk_out = grid;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_vjp_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        smem_set = smem;
+    }
+    // threads: the multiple of 32 (<= 512) that leaves the fewest idle point slots at ceil(PL / T) points per thread
+    const int PL = p.d.shape[2] * p.d.shape[3];
+    int T = MMH_VP_T;
+    double best_waste = 1e300;
+    for (int t = 256; t <= MMH_VP_T; t += 32) {
+        const int np = (PL + t - 1) / t;
+        if (np > MMH_VP_NP) continue;
+        const double waste = (double)np * t / PL;
+        if (waste < best_waste - 1e-9 || (waste < best_waste + 1e-9 && t > T)) { best_waste = waste; T = t; }
+    }
+    if (const char *e = getenv("MMH_VJP_T")) T = atoi(e);
+    k_vjp_planes<<<dim3(grid, (unsigned)p.batch), T, smem, st>>>(p, best_nseg);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const long long warps = p.batch * p.nacc;
+    k_vjp_finish<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Batches of 2-index lattices (vanilla_batch_vjp_numba over 2-mode kets, gradients.py:85-116; cfg3): warp-synchronous row walk.
 // k_vjp_partial fetches the five neighbours of every point through L1 (seven 16-byte loads per amplitude: L1 wavefronts bound

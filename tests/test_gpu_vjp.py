@@ -144,3 +144,25 @@ def test_more_shapes_vs_oracle(shape, batch):
         got, want = S.vanilla_batch_vjp_numba(G, c, g), oracle.vanilla_batch_vjp(G, c, g)
     for x, y, nm in zip(got, want, ("dLdA", "dLdb", "dLdc")):
         assert_parity(np.asarray(x, dtype=np.complex128), np.asarray(y, dtype=np.complex128), f"{shape} {nm} vs oracle")
+
+
+@pytest.mark.parametrize("shape,nseg", [((6, 7, 16, 17), None), ((5, 9, 20, 13), "3"), ((4, 4, 33, 31), "4"), ((9, 5, 16, 16), "1"),
+                                         ((12, 11, 19, 23), "5")])
+def test_plane_tile_vjp_vs_oracle(S, O, monkeypatch, shape, nseg):
+    """k_vjp_planes (TMA-staged plane tiles of one 4-index lattice, the cfg5 kernel) forced onto small lattices: every plane role
+    (k0 - 1, k0 - 2, k1 - 1, k1 - 2 absent at the low edges), ragged k1 segments, several tasks per CTA; gate 1e-10 / 1e-14."""
+    from mrmustard_b200 import _lib
+    monkeypatch.setenv("MMH_VJP_PLANES_MIN_N", "1")
+    if nseg:
+        monkeypatch.setenv("MMH_VJP_NSEG", nseg)
+    A, b, c = random_triple(4, (), seed=41)
+    G = O.vanilla(shape, A, b, complex(c))
+    g = np.random.RandomState(21).standard_normal(shape) + 1j * np.random.RandomState(22).standard_normal(shape)
+    n0 = _lib.launch_count()
+    got = S.vanilla_vjp_numba(G, complex(c), g)
+    assert _lib.launch_count() == n0 + 2
+    _check(got, O.vanilla_vjp(G, complex(c), g), f"planes {shape}")
+    monkeypatch.setenv("MMH_NO_VJP_PLANES", "1")
+    ref = S.vanilla_vjp_numba(G, complex(c), g)
+    for x, y in zip(got, ref):
+        assert np.allclose(np.asarray(x), np.asarray(y), rtol=1e-11, atol=1e-14)

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(CSRC, "libmmhermite.so")
-SOURCES = ["mmh_api.cu", "mmh_forward.cu", "mmh_march.cu", "mmh_lanes.cu", "mmh_box.cu", "mmh_tiled.cu", "mmh_rows.cu", "mmh_vjp.cu", "mmh_diagonal.cu", "mmh_diagonal_rolling.cu", "mmh_gates.cu", "mmh_autoshape.cu", "mmh_einsum.cu"]
+SOURCES = ["mmh_api.cu", "mmh_forward.cu", "mmh_march.cu", "mmh_lanes.cu", "mmh_box.cu", "mmh_tiled.cu", "mmh_rows.cu", "mmh_stable_boxes.cu", "mmh_vjp.cu", "mmh_diagonal.cu", "mmh_diagonal_rolling.cu", "mmh_gates.cu", "mmh_autoshape.cu", "mmh_einsum.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

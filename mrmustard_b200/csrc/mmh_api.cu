@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <string>
@@ -52,6 +53,7 @@ struct DeviceCtx {
     Scratch ones;                 // vacuum amplitudes c = 1 of mmh_forward_contract
     Scratch ein_ws;               // offset tables of the Fock-space contraction
     Scratch dot_ws;               // per-CTA partials of mmh_overlap
+    Scratch sbox_ws;              // stable box wavefront: ready flags + ticket of the current call
     Scratch gate_ws;              // gate strategies: log-factorial table, transposition buffer, masked cotangent
     Scratch host_slots[8];        // staging for the *_host entry points
     int *err_host = nullptr;      // mapped page-locked word the watchdogs of the polling kernels set when they give up
@@ -649,6 +651,100 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
     return MMH_OK;
 }
 
+
+// ---- stable rule on a wavefront of boxes (mmh_stable_boxes.cu): per-shape tables, cached on the device ---------------------------
+struct StableBoxPlan { int *box_order; unsigned *cell_order; int *lvl_start; int nb[4]; int E; int nbox; int ncell; int nlev; };
+static int stable_box_plan(const LatticeDesc &d, int device, StableBoxPlan **out) {
+    static std::map<std::string, StableBoxPlan> cache;
+    std::string key((const char *)d.shape, sizeof(int) * (size_t)d.D);
+    key.push_back((char)d.D); key.append(std::to_string(device));
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        StableBoxPlan pl;
+        memset(&pl, 0, sizeof(pl));
+        const int D = d.D, pad = 4 - D, E = mmh_stable_boxes_edge(D);
+        pl.E = E;
+        int nbox = 1;
+        for (int j = 0; j < 4; j++) { pl.nb[j] = j < pad ? 1 : (d.shape[j - pad] + E - 1) / E; nbox *= pl.nb[j]; }
+        pl.nbox = nbox;
+        // boxes by level (sum of box coordinates), lexicographic inside a level: every box comes after all boxes below it
+        std::vector<std::pair<int, int>> lv((size_t)nbox);
+        for (int b = 0; b < nbox; b++) {
+            int r = b, s = 0;
+            for (int j = 3; j >= 0; j--) { s += r % pl.nb[j]; r /= pl.nb[j]; }
+            lv[(size_t)b] = std::make_pair(s, b);
+        }
+        std::sort(lv.begin(), lv.end());
+        std::vector<int> order((size_t)nbox);
+        for (int n = 0; n < nbox; n++) order[(size_t)n] = lv[(size_t)n].second;
+        // cells of a full box by local level
+        int ncell = 1;
+        for (int j = 0; j < D; j++) ncell *= E;
+        const int nlev = D * (E - 1) + 1;
+        std::vector<std::vector<unsigned>> by((size_t)nlev);
+        for (int c = 0; c < ncell; c++) {
+            int r = c, s = 0;
+            unsigned packed = 0;
+            for (int j = 3; j >= pad; j--) { const int x = r % E; r /= E; s += x; packed |= (unsigned)x << (8 * j); }
+            by[(size_t)s].push_back(packed);
+        }
+        std::vector<unsigned> cells;
+        std::vector<int> starts((size_t)nlev + 1);
+        for (int m = 0; m < nlev; m++) { starts[(size_t)m] = (int)cells.size(); cells.insert(cells.end(), by[(size_t)m].begin(), by[(size_t)m].end()); }
+        starts[(size_t)nlev] = (int)cells.size();
+        pl.ncell = ncell; pl.nlev = nlev;
+        CK(cudaMalloc(&pl.box_order, sizeof(int) * (size_t)nbox));
+        CK(cudaMalloc(&pl.cell_order, sizeof(unsigned) * cells.size()));
+        CK(cudaMalloc(&pl.lvl_start, sizeof(int) * starts.size()));
+        CK(cudaMemcpy(pl.box_order, order.data(), sizeof(int) * (size_t)nbox, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(pl.cell_order, cells.data(), sizeof(unsigned) * cells.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(pl.lvl_start, starts.data(), sizeof(int) * starts.size(), cudaMemcpyHostToDevice));
+        it = cache.emplace(key, pl).first;
+    }
+    *out = &it->second;
+    return MMH_OK;
+}
+
+static int forward_stable_boxes(const FwdParams &p, DeviceCtx *ctx, int device, cudaStream_t st) {
+    StableBoxPlan *pl;
+    int rc;
+    if ((rc = stable_box_plan(p.d, device, &pl))) return rc;
+    if ((rc = ensure_scratch(ctx->sbox_ws, sizeof(int) * ((size_t)pl->nbox + 16)))) return rc;
+    CK(cudaMemsetAsync(ctx->sbox_ws.ptr, 0, sizeof(int) * ((size_t)pl->nbox + 16), st));
+    StableBoxParams q;
+    memset(&q, 0, sizeof(q));
+    q.d = p.d; q.A = p.A; q.b = p.b; q.c = p.c; q.G = p.G; q.sq = p.sq; q.rsq = p.rsq;
+    for (int j = 0; j < 4; j++) q.nb[j] = pl->nb[j];
+    q.E = pl->E; q.nbox = pl->nbox; q.ncell = pl->ncell; q.nlev = pl->nlev;
+    int mxs = 0;
+    for (int j = 0; j < p.d.D; j++) mxs = p.d.shape[j] > mxs ? p.d.shape[j] : mxs;
+    q.ntab = mxs + 1;
+    q.xshift = 0;
+    while ((1 << q.xshift) < pl->E + 2) q.xshift++;
+    q.box_order = pl->box_order; q.cell_order = pl->cell_order; q.lvl_start = pl->lvl_start;
+    q.ticket = (int *)ctx->sbox_ws.ptr;
+    q.flags = (int *)ctx->sbox_ws.ptr + 16;
+    q.err = ctx->err_dev;
+    const char *trace_file = getenv("MMH_SB_TRACE");
+    if (trace_file) { CK(cudaMalloc(&q.trace, 64 * 8 * 8)); CK(cudaMemset(q.trace, 0, 64 * 8 * 8)); }
+    g_launches++;
+    CK(mmh_launch_stable_boxes(q, ctx->sm_count, st));
+    if (trace_file) {
+        unsigned long long h[64 * 8];
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpy(h, q.trace, sizeof(h), cudaMemcpyDeviceToHost));
+        CK(cudaFree(q.trace));
+        if (FILE *fp = fopen(trace_file, "w")) {
+            for (int n = 0; n < 64 && h[n * 8]; n++)
+                fprintf(fp, "box %5llu  ticket %.2f  deps %.2f  halo %.2f  levels %.2f  publish %.2f   (us; start %.2f)\n", h[n * 8 + 6],
+                        (h[n * 8 + 1] - h[n * 8]) / 1e3, (h[n * 8 + 2] - h[n * 8 + 1]) / 1e3, (h[n * 8 + 3] - h[n * 8 + 2]) / 1e3,
+                        (h[n * 8 + 4] - h[n * 8 + 3]) / 1e3, (h[n * 8 + 5] - h[n * 8 + 4]) / 1e3, (h[n * 8] - h[0]) / 1e3);
+            fclose(fp);
+        }
+    }
+    return MMH_OK;
+}
+
 static int forward_impl(long long batch, int ndim, const int64_t *shape, const void *dA, const void *db,
                         const void *dc, void *dG, int stable, cudaStream_t st) {
     if (batch < 0) return MMH_ERR_BAD_BATCH;
@@ -713,6 +809,19 @@ static int forward_impl(long long batch, int ndim, const int64_t *shape, const v
             q.A = p.A + l * ndim * ndim; q.b = p.b + l * ndim; q.c = p.c + l; q.G = p.G + l * d.N;
             q.batch = 1;
             if ((rc = forward_single_staged(q, ctx, st, l))) return rc;
+        }
+        return MMH_OK;
+    }
+    // stable rule, 2..4 indices, a lattice of many boxes: wavefront of boxes (no grid barrier, neighbours from shared memory)
+    if (stable && ndim >= 2 && ndim <= 4 && mx <= 4096 &&
+        d.N >= (getenv("MMH_STABLE_BOXES_MIN_N") ? atoll(getenv("MMH_STABLE_BOXES_MIN_N")) : 200000LL) && !getenv("MMH_NO_STABLE_BOXES")) {
+        int device = 0;
+        CK(cudaGetDevice(&device));
+        for (long long l = 0; l < batch; l++) {
+            FwdParams q = p;
+            q.A = p.A + l * ndim * ndim; q.b = p.b + l * ndim; q.c = p.c + l; q.G = p.G + l * d.N;
+            q.batch = 1;
+            if ((rc = forward_stable_boxes(q, ctx, device, st))) return rc;
         }
         return MMH_OK;
     }

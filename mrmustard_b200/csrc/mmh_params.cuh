@@ -95,6 +95,30 @@ struct TiledParams {
     unsigned long long *timeline;   // per-launch debug stamps (mmh_common.cuh timeline_stamp), may be NULL
 };
 
+// stable rule on a wavefront of boxes (mmh_stable_boxes.cu)
+struct StableBoxParams {
+    LatticeDesc d;               // 2 <= D <= 4
+    const c128 *A, *b, *c;       // one triple
+    c128 *G;
+    const double *sq, *rsq;
+    int nb[4];                   // boxes per dim, right-aligned in four padded dims (leading dims: 1)
+    int E;                       // box edge
+    int nbox;
+    const int *box_order;        // [nbox] box ids sorted by box level (a topological order)
+    int *flags;                  // [nbox] 0 -> 1 when the box is complete (zeroed per call)
+    int *ticket;                 // next position in box_order (zeroed per call)
+    const unsigned *cell_order;  // [E^D] packed local coordinates of a full box's cells sorted by local level
+    const int *lvl_start;        // [nlev + 1] offsets of the local levels in cell_order
+    int ncell, nlev;             // E^D, D (E - 1) + 1
+    int ntab;                    // entries of the sqrt table the kernel copies to shared memory (max shape + 1)
+    int xshift;                  // log2 of the extended box edge E + 2
+    int *err;                    // watchdog word
+    unsigned long long *trace;   // debug: %globaltimer stamps of CTA 0's first 64 boxes (MMH_SB_TRACE), else NULL
+};
+int mmh_stable_boxes_edge(int D);
+size_t mmh_stable_boxes_smem(int D, int ntab, int ncell, int nlev);
+cudaError_t mmh_launch_stable_boxes(const StableBoxParams &p, int sm_count, cudaStream_t st);
+
 cudaError_t mmh_launch_march_tiled2(const TiledParams &p, int R, int ntiles, size_t smem, cudaStream_t st);
 size_t mmh_tiled2_smem(int ls_max, int hc_max, int S, int slots);
 size_t mmh_tiled2_cluster_extra_smem(int hc_max, int S);

@@ -5,6 +5,6 @@
 set -e
 cd "$(dirname "$0")/../mrmustard_b200/csrc"
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --fmad=false -Xcompiler -fPIC -shared -DMMH_T2_HANDOFF_BAR=1 -DMMH_RW_HANDOFF_BAR=1 \
-     -o libmmhermite_barsync.so mmh_api.cu mmh_forward.cu mmh_march.cu mmh_lanes.cu mmh_box.cu mmh_tiled.cu mmh_rows.cu mmh_vjp.cu mmh_diagonal.cu \
+     -o libmmhermite_barsync.so mmh_api.cu mmh_forward.cu mmh_march.cu mmh_lanes.cu mmh_box.cu mmh_tiled.cu mmh_rows.cu mmh_stable_boxes.cu mmh_vjp.cu mmh_diagonal.cu \
      mmh_diagonal_rolling.cu mmh_gates.cu mmh_autoshape.cu mmh_einsum.cu -lcudart
 echo built libmmhermite_barsync.so

@@ -284,3 +284,28 @@ def test_underflowing_and_overflowing_lattices_bit_exact(S, O):
     want = O.vanilla_batch((300, 200), A, b, c)
     assert ((np.abs(want) < 2.0 ** -899) & (np.abs(want) > 0)).any()
     assert np.array_equal(S.vanilla_batch_numba((300, 200), A, b, c), want)
+
+
+@pytest.mark.parametrize("shape", [(7, 6, 9, 8), (13, 5, 14, 7), (6, 6, 6, 6), (20, 33, 17), (15, 14, 29), (70, 130), (62, 63), (5, 1, 9, 13)])
+def test_stable_box_wavefront_vs_oracle(S, O, monkeypatch, shape):
+    """k_stable_boxes (mmh_stable_boxes.cu: persistent CTAs take boxes of the lattice in a topological order, two-deep halos from the
+    lattice, local level wavefront in shared memory) forced onto small lattices with ragged boxes in 2, 3 and 4 indices: bit-identical
+    to the oracle's stable rule, also when called twice in a row (flags and ticket are reset per call)."""
+    from mrmustard_b200 import _lib
+    monkeypatch.setenv("MMH_STABLE_BOXES_MIN_N", "1")
+    A, b, c = random_triple(len(shape), (), seed=17 + len(shape))
+    want = O.vanilla(shape, A, b, complex(c), stable=True)
+    for _ in range(2):
+        n0 = _lib.launch_count()
+        got = S.stable_numba(shape, A, b, complex(c))
+        assert _lib.launch_count() == n0 + 1
+        assert np.array_equal(got, want), shape
+
+
+def test_stable_box_wavefront_batched_and_default(S, O, golden):
+    # a batch of lattices large enough for the box wavefront by default (one launch per lattice)
+    shape = (24, 25, 26, 27)
+    A, b, c = random_triple(4, (2,), seed=23)
+    G = S.vanilla_batch_numba(shape, A, b, c, True)
+    for l in range(2):
+        assert np.array_equal(G[l], O.vanilla(shape, A[l], b[l], complex(c[l]), stable=True)), l

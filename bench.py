@@ -580,7 +580,7 @@ def cfg2_record(ctx, steps, warmup, with_cpu=True, with_e2e=True):
     step = ms / steps
     rec = {"value": world * n / (step * 1e-3), "unit": UNIT, "ms_per_step": step, "steps": steps, "gpu_launches": int(launches),
            "clocks": clocks, "e2e": e2e,
-           "roofline": _roofline("mmh_forward: k_warp_tail + k_march_tiled2 (stage 1) + k_march_tiled2 (stage 0, dominant); the kernels overlap",
+           "roofline": _roofline("mmh_forward: k_warp_tail + k_march_tiled2 (stage 1) + k_march_rows (stage 0, dominant: 65 % of the serialised time); the kernels overlap",
                                  ALGO_BYTES_PER_AMP_FWD * n, step, "cfg2", peak, peak_src),
            "notes": {"l2": "flushed between timed steps (untimed 256 MiB write; one lattice = 100 MB < 126 MB L2)",
                      "parity": "every rank's device result sha256-checked against the reference golden before timing"}}

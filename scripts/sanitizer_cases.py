@@ -45,6 +45,21 @@ check(f"box march {shape} x 40", np.array_equal(S.vanilla_batch_numba(shape, A, 
 shape = (9, 8, 7, 6)
 A, b, c = random_triple(4, (), seed=5)
 check("stable", np.array_equal(S.stable_numba(shape, A, b, complex(c)), oracle.vanilla(shape, A, b, complex(c), stable=True)))
+# stable rule on a wavefront of boxes (k_stable_boxes): ticket order, ready flags, ragged boxes in 2 / 3 / 4 indices
+os.environ["MMH_STABLE_BOXES_MIN_N"] = "1"
+for shp in [(7, 6, 9, 8), (15, 14, 29), (70, 130)]:
+    A_, b_, c_ = random_triple(len(shp), (), seed=17 + len(shp))
+    check(f"stable boxes {shp}", np.array_equal(S.stable_numba(shp, A_, b_, complex(c_)), oracle.vanilla(shp, A_, b_, complex(c_), stable=True)))
+del os.environ["MMH_STABLE_BOXES_MIN_N"]
+# VJP on TMA-staged plane tiles (k_vjp_planes): bulk copies + mbarrier transaction counts, several tasks per CTA
+os.environ["MMH_VJP_PLANES_MIN_N"], os.environ["MMH_VJP_NSEG"] = "1", "3"
+shp = (5, 9, 20, 13)
+A_, b_, c_ = random_triple(4, (), seed=41)
+G_ = oracle.vanilla(shp, A_, b_, complex(c_))
+g_ = np.random.RandomState(21).standard_normal(shp) + 1j * np.random.RandomState(22).standard_normal(shp)
+got, want = S.vanilla_vjp_numba(G_, complex(c_), g_), oracle.vanilla_vjp(G_, complex(c_), g_)
+check("vjp planes", all(np.allclose(x, y, rtol=1e-10, atol=1e-14) for x, y in zip(got, want)))
+del os.environ["MMH_VJP_PLANES_MIN_N"], os.environ["MMH_VJP_NSEG"]
 # VJP: partial + finish, and the lane row walk
 G = oracle.vanilla(shape, A, b, complex(c))
 g = np.random.RandomState(1).standard_normal(shape) + 0j

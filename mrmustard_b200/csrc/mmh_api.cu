@@ -94,7 +94,22 @@ static int ensure_tables(DeviceCtx &c, int need) {
     return 0;
 }
 
+extern char **environ;
+static std::vector<const char *> g_env_mmh;   // the "MMH_..." entries of the environment at the start of the current API call
+void mmh_env_refresh() {
+    g_env_mmh.clear();
+    for (char **e = environ; e && *e; ++e)
+        if ((*e)[0] == 'M' && (*e)[1] == 'M' && (*e)[2] == 'H' && (*e)[3] == '_') g_env_mmh.push_back(*e);
+}
+const char *mmh_getenv(const char *name) {
+    const size_t n = strlen(name);
+    for (const char *e : g_env_mmh)
+        if (!strncmp(e, name, n) && e[n] == '=') return e + n + 1;
+    return nullptr;
+}
+
 static int get_ctx(DeviceCtx **out) {
+    mmh_env_refresh();   // every compute entry point comes through here first (under g_mutex)
     int dev = 0, ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev < 1) { cudaGetLastError(); return MMH_ERR_NO_DEVICE; }
@@ -199,7 +214,7 @@ static bool plan_march_stage(const LatticeDesc &d, int stage, long long batch, i
     if (npd < 1 || npd > 7) return false;
     const long long P = d.strides[stage];
     if (P > 1024) return false;
-    const char *eL = getenv("MMH_K2_L"), *eR = getenv("MMH_K2_R");
+    const char *eL = mmh_getenv("MMH_K2_L"), *eR = mmh_getenv("MMH_K2_R");
     double best = -1.0;
     int bL = 0, bR = 0, bT = 0;
     size_t bsmem = 0;
@@ -240,16 +255,16 @@ static int forward_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_t st, b
         box[i] = false;
         if (plan_march_stage(d, i, p.batch, &L[i], &R[i], &T[i], &sm[i])) continue;
         // panels beyond one CTA's shared memory: the same CTA marches the lattice box by box (mmh_box.cu)
-        if (d.shape[i] == 1 || getenv("MMH_NO_BOX") || !mmh_plan_march_box(d, i, &bp[i], &T[i], &sm[i])) return MMH_OK;
+        if (d.shape[i] == 1 || mmh_getenv("MMH_NO_BOX") || !mmh_plan_march_box(d, i, &bp[i], &T[i], &sm[i])) return MMH_OK;
         box[i] = true;
     }
     // stage D-2 of a real batch runs on the warp-synchronous lane march (mmh_lanes.cu), which then also computes the chain
     // (stage D-1) of its lattices itself: one launch instead of two, panel 0 never re-read from HBM
     int Rl = 0, ln = 0, Lw = 0;
     const bool lanes = d.D >= 2 && !box[d.D - 2] && p.batch >= 256 && d.shape[d.D - 2] > 1 && d.shape[d.D - 2] <= 4096 &&
-                       !getenv("MMH_NO_LANES") && mmh_plan_march_lanes(d.shape[d.D - 1], &Rl, &ln, &Lw) &&
+                       !mmh_getenv("MMH_NO_LANES") && mmh_plan_march_lanes(d.shape[d.D - 1], &Rl, &ln, &Lw) &&
                        (long long)Lw * d.N < (1LL << 32);   // 32-bit store offsets
-    const bool fuse_chain = lanes && !getenv("MMH_NO_FUSE_CHAIN");
+    const bool fuse_chain = lanes && !mmh_getenv("MMH_NO_FUSE_CHAIN");
     if (!fuse_chain) {
         g_launches++;
         CK(mmh_launch_chain(p, st));
@@ -331,9 +346,9 @@ static bool plan_rows_for_grid(const LatticeDesc &d, int stage, const int *gin, 
 static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, TiledParams *tp, int *R_out,
                              int *ntiles_out, size_t *smem_out, double *cost_out = nullptr) {
     // test / tuning hook: MMH_ROWS_G="g0,g1,g2" forces k_march_rows with that box grid (MMH_ROWS_R: cells per lane)
-    const int rows_forcedR = getenv("MMH_ROWS_R") ? atoi(getenv("MMH_ROWS_R")) : 0;
-    if (const char *eg = getenv("MMH_ROWS_G"))
-        if (!getenv("MMH_NO_ROWS") && (!getenv("MMH_TILE_STAGE") || atoi(getenv("MMH_TILE_STAGE")) == stage)) {
+    const int rows_forcedR = mmh_getenv("MMH_ROWS_R") ? atoi(mmh_getenv("MMH_ROWS_R")) : 0;
+    if (const char *eg = mmh_getenv("MMH_ROWS_G"))
+        if (!mmh_getenv("MMH_NO_ROWS") && (!mmh_getenv("MMH_TILE_STAGE") || atoi(mmh_getenv("MMH_TILE_STAGE")) == stage)) {
             int fg[3] = { 1, 1, 1 };
             sscanf(eg, "%d,%d,%d", &fg[0], &fg[1], &fg[2]);
             if (plan_rows_for_grid(d, stage, fg, rows_forcedR, tp, ntiles_out, smem_out)) { *R_out = tp->rows_R; return true; }
@@ -348,8 +363,8 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
     int shp[3] = { 1, 1, 1 };
     for (int m = 0; m < nt; m++) shp[m] = d.shape[stage + 1 + m];
     int forced[3] = { 0, 0, 0 };
-    if (const char *eg = getenv("MMH_TILE_G"))   // test / tuning hook; MMH_TILE_STAGE restricts it to one stage
-        if (!getenv("MMH_TILE_STAGE") || atoi(getenv("MMH_TILE_STAGE")) == stage)
+    if (const char *eg = mmh_getenv("MMH_TILE_G"))   // test / tuning hook; MMH_TILE_STAGE restricts it to one stage
+        if (!mmh_getenv("MMH_TILE_STAGE") || atoi(mmh_getenv("MMH_TILE_STAGE")) == stage)
             sscanf(eg, "%d,%d,%d", &forced[0], &forced[1], &forced[2]);
     double best = 1e300;
     int bg[3] = { 0, 0, 0 }, bR = 0, bTC = 0, bLS = 0, bHC = 0;
@@ -373,7 +388,7 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
                 const long long HCs = HC > 0 ? HC : 1;   // X rows are laid out with stride hc_max >= 1
                 int R = 0;
                 const int Rs[2] = { 1, 2 };
-                const char *eR = getenv("MMH_TILE_R");
+                const char *eR = mmh_getenv("MMH_TILE_R");
                 for (int r = 0; r < 2; r++) {
                     const int tcmax = 512;
                     if (eR && atoi(eR) != Rs[r]) continue;
@@ -400,8 +415,8 @@ static bool plan_march_tiled(const LatticeDesc &d, int stage, int sm_count, Tile
     // Boxes with enough arithmetic per step run on the row-lane kernel (mmh_rows.cu) with the same grid: its compute warps do
     // nothing but the recurrence (service warps import, export and drain).  Small boxes stay on k_march_tiled2, whose step is
     // bound by the hand-off latency either way (measured: (40,)^4 in 8x8x8 boxes 84 vs 80 us, (50,)^4 in 10x10x10 boxes 121 vs 131 us).
-    if (npd == 3 && inner == 1 && !getenv("MMH_NO_ROWS") && !forced[0]) {
-        const long long min_cells = getenv("MMH_ROWS_MIN_CELLS") ? atoll(getenv("MMH_ROWS_MIN_CELLS")) : 700;
+    if (npd == 3 && inner == 1 && !mmh_getenv("MMH_NO_ROWS") && !forced[0]) {
+        const long long min_cells = mmh_getenv("MMH_ROWS_MIN_CELLS") ? atoll(mmh_getenv("MMH_ROWS_MIN_CELLS")) : 700;
         long long cells = 1;
         for (int m = 0; m < 3; m++) cells *= (shp[m] + bg[m] - 1) / bg[m];
         if (cells >= min_cells && plan_rows_for_grid(d, stage, bg, rows_forcedR, tp, ntiles_out, smem_out)) {
@@ -428,7 +443,7 @@ static bool plan_march_tiled_cached(const LatticeDesc &d, int stage, int sm_coun
     std::string key((const char *)d.shape, sizeof(int) * (size_t)d.D);
     key.push_back((char)stage); key.push_back((char)d.D); key.append(std::to_string(sm_count));
     for (const char *name : { "MMH_TILE_G", "MMH_TILE_STAGE", "MMH_TILE_R", "MMH_NO_ROWS", "MMH_ROWS_G", "MMH_ROWS_R", "MMH_ROWS_MIN_CELLS" }) {
-        const char *v = getenv(name);
+        const char *v = mmh_getenv(name);
         key.push_back('|');
         if (v) key.append(v);
     }
@@ -462,7 +477,7 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
     // successor at once and the successor's prologue (index decode, tables) overlaps it, blocking only where it first
     // touches the lattice.  The chain (stage D-1) is fused into the first march launch when that is a single CTA.
     const size_t absmem = sizeof(c128) * (size_t)(D * D + D);
-    const bool use_pdl = !getenv("MMH_NO_PDL");
+    const bool use_pdl = !mmh_getenv("MMH_NO_PDL");
     if (!ctx->timeline.ptr) {
         int rc0;
         if ((rc0 = ensure_scratch(ctx->timeline, 256 * sizeof(unsigned long long)))) return rc0;
@@ -474,7 +489,7 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
     const size_t kTraceArenaWords = 4u << 20;   // one arena, allocated and cleared before the first launch (no sync between stages)
     unsigned long long *trace_arena = nullptr;
     size_t trace_used = 0;
-    if (getenv("MMH_TRACE_FILE")) {
+    if (mmh_getenv("MMH_TRACE_FILE")) {
         CK(cudaMalloc(&trace_arena, kTraceArenaWords * 8));
         CK(cudaMemsetAsync(trace_arena, 0, kTraceArenaWords * 8, st));
     }
@@ -490,19 +505,19 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
     bool pipelined = false;          // this lattice's first kernels are chained behind the previous lattice's (see kMaxInFlight)
     size_t xbase = 0;                // exchange-buffer slot of this lattice
     size_t xoff1 = 0;                // exchange-buffer offset (bytes) of stage i0 when it overlaps stage i1
-    if (use_pdl && i1 >= 0 && (!getenv("MMH_TRACE_FILE") || getenv("MMH_TRACE_OVERLAP")) && !getenv("MMH_NO_OVERLAP")) {
+    if (use_pdl && i1 >= 0 && (!mmh_getenv("MMH_TRACE_FILE") || mmh_getenv("MMH_TRACE_OVERLAP")) && !mmh_getenv("MMH_NO_OVERLAP")) {
         int L_, R_, T_, n0 = 0, n1 = 0;
         size_t sm_;
         TiledParams t0, t1;
-        const bool k2_0 = !getenv("MMH_FORCE_TILED") && plan_march_stage(d, i0, 1, &L_, &R_, &T_, &sm_);
-        const bool k2_1 = !getenv("MMH_FORCE_TILED") && plan_march_stage(d, i1, 1, &L_, &R_, &T_, &sm_);
-        const bool tail1 = i1 == D - 2 && d.shape[D - 1] <= 64 && !getenv("MMH_NO_WARP_TAIL") && !getenv("MMH_FORCE_TILED");
+        const bool k2_0 = !mmh_getenv("MMH_FORCE_TILED") && plan_march_stage(d, i0, 1, &L_, &R_, &T_, &sm_);
+        const bool k2_1 = !mmh_getenv("MMH_FORCE_TILED") && plan_march_stage(d, i1, 1, &L_, &R_, &T_, &sm_);
+        const bool tail1 = i1 == D - 2 && d.shape[D - 1] <= 64 && !mmh_getenv("MMH_NO_WARP_TAIL") && !mmh_getenv("MMH_FORCE_TILED");
         if (!k2_0 && !k2_1 && !tail1 && plan_march_tiled_cached(d, i0, ctx->sm_count, &t0, &R_, &n0, &sm_) &&
             plan_march_tiled_cached(d, i1, ctx->sm_count, &t1, &R_, &n1, &sm_) && n0 + n1 <= ctx->sm_count &&
             d.strides[i0] * (long long)sizeof(c128) <= (64LL << 20)) {
             overlap = true;
-            overlap1 = i1 == D - 3 && d.shape[D - 2] > 1 && d.shape[D - 1] <= 64 && !getenv("MMH_NO_WARP_TAIL") &&
-                       !getenv("MMH_FORCE_TILED") && !getenv("MMH_NO_OVERLAP1");
+            overlap1 = i1 == D - 3 && d.shape[D - 2] > 1 && d.shape[D - 1] <= 64 && !mmh_getenv("MMH_NO_WARP_TAIL") &&
+                       !mmh_getenv("MMH_FORCE_TILED") && !mmh_getenv("MMH_NO_OVERLAP1");
             xoff1 = (sizeof(c128) * (size_t)n1 * d.shape[i1] * t1.hc_max + 255) / 256 * 256;
             const size_t xslot = (xoff1 + sizeof(c128) * (size_t)n0 * d.shape[i0] * t0.hc_max + 255) / 256 * 256;
             const size_t xtotal = xslot * (size_t)kMaxInFlight;
@@ -523,7 +538,7 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
         int L, R, T, ntiles;
         size_t sm;
         TiledParams tp;
-        if (i == D - 2 && !chain_done && d.shape[D - 1] <= 64 && !getenv("MMH_NO_WARP_TAIL") && !getenv("MMH_FORCE_TILED")) {
+        if (i == D - 2 && !chain_done && d.shape[D - 1] <= 64 && !mmh_getenv("MMH_NO_WARP_TAIL") && !mmh_getenv("MMH_FORCE_TILED")) {
             // the two trailing stages by one warp (shuffles instead of shared memory + barriers)
             StageParams sp;
             sp.d = d; sp.A = p.A; sp.b = p.b; sp.G = p.G; sp.sq = p.sq; sp.rsq = p.rsq;
@@ -539,7 +554,7 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
         // (1.0 us at 1000 points, measured); tiles of 100-200 points step in ~0.15 us and pay ~1 us per pipeline hop once.
         // Long marches of mid-size panels ((1000,1000): 999 steps of 1000 points) are 3x faster tiled.
         bool prefer_tiled = false;
-        if (!getenv("MMH_FORCE_TILED") && !getenv("MMH_NO_PREFER_TILED") && d.strides[i] >= 192 && d.strides[i] <= 1024) {
+        if (!mmh_getenv("MMH_FORCE_TILED") && !mmh_getenv("MMH_NO_PREFER_TILED") && d.strides[i] >= 192 && d.strides[i] <= 1024) {
             double tcost = 0.0;
             int R_, n_;
             size_t sm_;
@@ -552,7 +567,7 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
                 if ((d.shape[i] - 1) * tstep < 0.75 * k2cost) prefer_tiled = true;
             }
         }
-        if (!prefer_tiled && !getenv("MMH_FORCE_TILED") && plan_march_stage(d, i, 1, &L, &R, &T, &sm)) {
+        if (!prefer_tiled && !mmh_getenv("MMH_FORCE_TILED") && plan_march_stage(d, i, 1, &L, &R, &T, &sm)) {
             StageParams sp;
             sp.d = d; sp.A = p.A; sp.b = p.b; sp.G = p.G; sp.sq = p.sq; sp.rsq = p.rsq;
             sp.batch = 1; sp.lat_stride = d.N; sp.stage = i; sp.L = L;
@@ -575,7 +590,7 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
             first = false;
             tp.poll0 = ((overlap && i == i0) || (overlap1 && i == i1)) ? 1 : 0;
             tp.strong_g = (overlap && i == i1) ? 1 : 0;   // only a stage that a later stage polls needs strong lattice stores
-            tp.dbg = getenv("MMH_ROWS_DBG") ? atoi(getenv("MMH_ROWS_DBG")) : 0;
+            tp.dbg = mmh_getenv("MMH_ROWS_DBG") ? atoi(mmh_getenv("MMH_ROWS_DBG")) : 0;
             if (tp.dbg & 2) tp.strong_g = 1;
             {   // exchange buffer: grow-only scratch, (re)filled with the sentinel whenever it is (re)allocated
                 const size_t xoff = xbase + ((overlap && i == i0) ? xoff1 : 0);
@@ -586,7 +601,7 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
                 }
                 tp.X = (c128 *)((char *)ctx->xbuf.ptr + xoff);
             }
-            const char *trace_file = getenv("MMH_TRACE_FILE");   // debug timeline of the tile pipeline
+            const char *trace_file = mmh_getenv("MMH_TRACE_FILE");   // debug timeline of the tile pipeline
             const size_t trace_words = (size_t)ntiles * d.shape[i] * 8;
             if (trace_file) {
                 if (trace_used + trace_words > kTraceArenaWords) return MMH_ERR_TOO_LARGE;
@@ -602,11 +617,11 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
                 // (opt-in, MMH_CLUSTER=1: bit-identical and measured NEUTRAL on cfg2 -- 119.0 vs 119.4 us, back-to-back 100.8 vs 100.8 us
                 //  per lattice: the lag of stage 1's far tiles comes from the rows of plane k1 = 0 that the one-warp tail kernel
                 //  delivers last, not from the hop through L2)
-                tp.cluster = (ntiles > 1 && ntiles <= 16 && d.D - 1 - i <= 3 && smc <= 200 * 1024 && getenv("MMH_CLUSTER")) ? 1 : 0;
+                tp.cluster = (ntiles > 1 && ntiles <= 16 && d.D - 1 - i <= 3 && smc <= 200 * 1024 && mmh_getenv("MMH_CLUSTER")) ? 1 : 0;
                 cudaError_t ce = cudaSuccess;
                 if (tp.cluster) {
                     ce = mmh_launch_march_tiled2(tp, R, ntiles, smc, st);
-                    if (getenv("MMH_DEBUG_CLUSTER")) fprintf(stderr, "[mmh] stage %d: cluster launch of %d tiles, %zu B smem: %s\n", i, ntiles, smc, cudaGetErrorString(ce));
+                    if (mmh_getenv("MMH_DEBUG_CLUSTER")) fprintf(stderr, "[mmh] stage %d: cluster launch of %d tiles, %zu B smem: %s\n", i, ntiles, smc, cudaGetErrorString(ce));
                     if (ce != cudaSuccess) { (void)cudaGetLastError(); tp.cluster = 0; }   // no GPC can host the cluster: through L2
                 }
                 if (!tp.cluster) CK(mmh_launch_march_tiled2(tp, R, ntiles, sm, st));
@@ -639,7 +654,7 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
             std::vector<unsigned long long> h(pt.words);
             CK(cudaMemcpy(h.data(), pt.dev, pt.words * 8, cudaMemcpyDeviceToHost));
             char name[512];
-            snprintf(name, sizeof(name), "%s.stage%d.bin", getenv("MMH_TRACE_FILE"), pt.stage);
+            snprintf(name, sizeof(name), "%s.stage%d.bin", mmh_getenv("MMH_TRACE_FILE"), pt.stage);
             if (FILE *fp = fopen(name, "wb")) {
                 fwrite(pt.hdr, sizeof(int), 8, fp);
                 fwrite(h.data(), 8, pt.words, fp);
@@ -725,7 +740,7 @@ static int forward_stable_boxes(const FwdParams &p, DeviceCtx *ctx, int device, 
     q.ticket = (int *)ctx->sbox_ws.ptr;
     q.flags = (int *)ctx->sbox_ws.ptr + 16;
     q.err = ctx->err_dev;
-    const char *trace_file = getenv("MMH_SB_TRACE");
+    const char *trace_file = mmh_getenv("MMH_SB_TRACE");
     if (trace_file) { CK(cudaMalloc(&q.trace, 64 * 8 * 8)); CK(cudaMemset(q.trace, 0, 64 * 8 * 8)); }
     g_launches++;
     CK(mmh_launch_stable_boxes(q, ctx->sm_count, st));
@@ -773,7 +788,7 @@ static int forward_impl(long long batch, int ndim, const int64_t *shape, const v
     // on (32 x (30,)^4: 0.77 vs 1.78 ms; 8 x (30,)^4: 0.73 vs 0.45 ms).
     long long per_cta_batch = 2LL * ctx->sm_count;
     if (!stable && d.N > kSingleCtaN && batch > 1) {
-        const bool boxed = ndim <= 5 && !getenv("MMH_NO_BOX");
+        const bool boxed = ndim <= 5 && !mmh_getenv("MMH_NO_BOX");
         const double rate = boxed ? 1.1e-3 : 3.0e-3;   // us per amplitude and CTA
         const long long slots = (boxed ? 1LL : 2LL) * ctx->sm_count;
         long long steps = 0;
@@ -784,8 +799,8 @@ static int forward_impl(long long batch, int ndim, const int64_t *shape, const v
         const double t_cta = waves * rate * (double)d.N;
         if (t_cta < t_pipe) per_cta_batch = batch;
     }
-    if (const char *e = getenv("MMH_PER_CTA_BATCH")) per_cta_batch = atoll(e);   // tuning hook
-    const bool per_cta = (d.N <= kSingleCtaN && !getenv("MMH_FORCE_TILED")) || batch >= per_cta_batch;
+    if (const char *e = mmh_getenv("MMH_PER_CTA_BATCH")) per_cta_batch = atoll(e);   // tuning hook
+    const bool per_cta = (d.N <= kSingleCtaN && !mmh_getenv("MMH_FORCE_TILED")) || batch >= per_cta_batch;
     if (!stable && (ndim == 1 || per_cta)) {
         bool done = false;
         if ((rc = forward_staged(p, ctx, st, &done))) return rc;
@@ -802,7 +817,7 @@ static int forward_impl(long long batch, int ndim, const int64_t *shape, const v
         CK(mmh_launch_fwd_cta(p, stable != 0, (int)grid, block, smem, st));
         return MMH_OK;
     }
-    if (!stable && ndim >= 2 && ndim <= 8 && !getenv("MMH_FORCE_COOP")) {
+    if (!stable && ndim >= 2 && ndim <= 8 && !mmh_getenv("MMH_FORCE_COOP")) {
         // large lattices, vanilla rule: chain + per-stage march kernels, every SM on the same lattice
         for (long long l = 0; l < batch; l++) {
             FwdParams q = p;
@@ -814,7 +829,7 @@ static int forward_impl(long long batch, int ndim, const int64_t *shape, const v
     }
     // stable rule, 2..4 indices, a lattice of many boxes: wavefront of boxes (no grid barrier, neighbours from shared memory)
     if (stable && ndim >= 2 && ndim <= 4 && mx <= 4096 &&
-        d.N >= (getenv("MMH_STABLE_BOXES_MIN_N") ? atoll(getenv("MMH_STABLE_BOXES_MIN_N")) : 200000LL) && !getenv("MMH_NO_STABLE_BOXES")) {
+        d.N >= (mmh_getenv("MMH_STABLE_BOXES_MIN_N") ? atoll(mmh_getenv("MMH_STABLE_BOXES_MIN_N")) : 200000LL) && !mmh_getenv("MMH_NO_STABLE_BOXES")) {
         int device = 0;
         CK(cudaGetDevice(&device));
         for (long long l = 0; l < batch; l++) {
@@ -873,15 +888,15 @@ static int vjp_impl(long long batch, int ndim, const int64_t *shape, const void 
     // batches of 2-index lattices: warp-synchronous row walk, every amplitude loaded once (k_vjp_lanes)
     {
         int Rl, ln, Lw;
-        if (ndim == 2 && batch >= 256 && d.shape[0] > 1 && !getenv("MMH_NO_LANES") && mmh_plan_march_lanes(d.shape[1], &Rl, &ln, &Lw)) {
+        if (ndim == 2 && batch >= 256 && d.shape[0] > 1 && !mmh_getenv("MMH_NO_LANES") && mmh_plan_march_lanes(d.shape[1], &Rl, &ln, &Lw)) {
             g_launches++;
             CK(mmh_launch_vjp_lanes(p, Rl, ln, Lw, ctx->sm_count, st));
             return MMH_OK;
         }
     }
     // one (or a few) large 4-index lattices: plane tiles staged by the TMA engine (k_vjp_planes)
-    const long long planes_min_n = getenv("MMH_VJP_PLANES_MIN_N") ? atoll(getenv("MMH_VJP_PLANES_MIN_N")) : (1LL << 20);   // test hook
-    if (ndim == 4 && batch <= 8 && d.N >= planes_min_n && mmh_vjp_planes_smem(d) && !getenv("MMH_NO_VJP_PLANES")) {
+    const long long planes_min_n = mmh_getenv("MMH_VJP_PLANES_MIN_N") ? atoll(mmh_getenv("MMH_VJP_PLANES_MIN_N")) : (1LL << 20);   // test hook
+    if (ndim == 4 && batch <= 8 && d.N >= planes_min_n && mmh_vjp_planes_smem(d) && !mmh_getenv("MMH_NO_VJP_PLANES")) {
         if ((rc = ensure_scratch(ctx->partial, sizeof(c128) * (size_t)batch * ctx->sm_count * p.nacc))) return rc;
         p.partial = (c128 *)ctx->partial.ptr;
         p.nblk = ctx->sm_count;
@@ -895,13 +910,13 @@ static int vjp_impl(long long batch, int ndim, const int64_t *shape, const void 
     int block = 256;
     if (batch >= 4LL * ctx->sm_count && d.N <= 8192) block = d.N >= 4096 ? 128 : 64;
     else block = 128;
-    if (const char *e = getenv("MMH_VJP_BLOCK")) block = atoi(e);
+    if (const char *e = mmh_getenv("MMH_VJP_BLOCK")) block = atoi(e);
     long long want = (d.N + block * 4 - 1) / (block * 4);   // ~4 points per thread
     // one wave of resident CTAs over the whole batch (at most 4 per SM)
     int per_sm = mmh_vjp_blocks_per_sm(p, block);
     if (per_sm > 4) per_sm = 4;
     long long cap = ((long long)per_sm * ctx->sm_count + batch - 1) / batch;
-    if (const char *e = getenv("MMH_VJP_CTAS_PER_SM")) cap = ((long long)atoi(e) * ctx->sm_count + batch - 1) / batch;
+    if (const char *e = mmh_getenv("MMH_VJP_CTAS_PER_SM")) cap = ((long long)atoi(e) * ctx->sm_count + batch - 1) / batch;
     if (cap < 1) cap = 1;
     if (want > cap) want = cap;
     if (want < 1) want = 1;
@@ -989,7 +1004,7 @@ static int diagonal_impl(int M, const int64_t *cutoffs, int L0, const void *dA, 
     // Large sweeps of the pure diagonal case: rolling weight-level buffers (mmh_diagonal_rolling.cu) -- the reference layout of the
     // auxiliary arrays is 0.94 TB for the 8-mode, cutoff-12 config; two level buffers are 18 GB.  MMH_DIAG_ROLLING=0/1 forces a path.
     {
-        const char *er = getenv("MMH_DIAG_ROLLING");
+        const char *er = mmh_getenv("MMH_DIAG_ROLLING");
         const bool rolling = !L0 && (er ? atoi(er) != 0 : bytes > ((size_t)1 << 30));
         if (rolling) {
             const size_t ws = mmh_diagonal_rolling_workspace(Md, q.cut, q.nb);
@@ -1400,6 +1415,8 @@ extern "C" int mmh_debug_timeline(unsigned long long *out64) {
 
 // debug aid, host only: the launch plans of the batched lane / box kernels (tests/test_host_logic.py)
 extern "C" int mmh_debug_plan(int what, int ndim, const int64_t *shape, int stage, int *out6) {
+    std::lock_guard<std::mutex> lk_env(g_mutex);   // host-only planner export: takes the lock for the environment snapshot
+    mmh_env_refresh();
     if (!shape || !out6) return MMH_ERR_NULL_POINTER;
     LatticeDesc d;
     int mx;

@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(HIST ? 256 : 512, HIST ? 2 : 1) k_march_box(Bo
 // 592 lattices: (20,)^4 0.693 / 0.751 ms, (30,)^4 3.85 / 3.91 ms, (64,)^3 0.862 / 0.808 ms (R = 2 / R = 4): twice the chains in
 // flight buy nothing, an SM marches ~1000 points per microsecond either way.
 int mmh_box_slots() {
-    const char *e = getenv("MMH_BOX_R");
+    const char *e = mmh_getenv("MMH_BOX_R");
     return (e && atoi(e) == 4) ? 4 : 2;
 }
 
@@ -290,7 +290,7 @@ bool mmh_plan_march_box(const LatticeDesc &d, int stage, BoxParams *bp, int *T_o
     // read-modify-writes (148 x (20,)^4 in 10 x 10 x 10 boxes: 0.69 ms; in 5 x 10 x 20 boxes: 0.20 ms; 32 lattices, L2
     // resident: 0.19 ms either way)
     long long max_ts = 1024;
-    if (const char *e_ = getenv("MMH_BOX_MAXTS")) max_ts = atoll(e_);   // tuning hook
+    if (const char *e_ = mmh_getenv("MMH_BOX_MAXTS")) max_ts = atoll(e_);   // tuning hook
     if (inner > max_ts) return false;
     double best_cost = 1e300;
     long long best_tiles = -1;

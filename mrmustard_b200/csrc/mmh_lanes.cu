@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(128) k_march_lanes(StageParams p, int ln, int 
 // plan: R positions per lane, ln lanes per lattice row, Lw lattices per warp; false when a row does not fit one warp
 bool mmh_plan_march_lanes(int n1, int *R_out, int *ln_out, int *Lw_out) {
     double best = -1.0;
-    const char *eR = getenv("MMH_LANES_R");
+    const char *eR = mmh_getenv("MMH_LANES_R");
     for (int R = 2; R <= 8; R++) {
         if (eR && atoi(eR) != R) continue;
         const int ln = (n1 + R - 1) / R;
@@ -192,13 +192,13 @@ cudaError_t mmh_launch_march_lanes(const StageParams &p, int R, int ln, int Lw, 
     // 512 four-warp CTAs = 3.46 per SM, i.e. the SMs holding 4 set the time: +16%; 1,024 two-warp CTAs balance to 1%)
     int block = 128;
     if ((p.batch + 4LL * Lw - 1) / (4LL * Lw) < 8LL * sm_count) block = 64;
-    if (const char *e = getenv("MMH_LANES_BLOCK")) block = atoi(e) == 64 ? 64 : (atoi(e) == 32 ? 32 : 128);
+    if (const char *e = mmh_getenv("MMH_LANES_BLOCK")) block = atoi(e) == 64 ? 64 : (atoi(e) == 32 ? 32 : 128);
     const int nw = block / 32;
     const long long grid = (p.batch + (long long)nw * Lw - 1) / ((long long)nw * Lw);
     if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
     const int S = p.d.shape[p.d.D - 2], n1 = p.d.shape[p.d.D - 1];
     const bool fuse = p.fuse_chain != 0;
-    const bool pdl = !getenv("MMH_NO_PDL");
+    const bool pdl = !mmh_getenv("MMH_NO_PDL");
     const size_t ntab = (fuse && n1 > S) ? n1 : S;
 #define MMH_LAUNCH(N, F)                                                                                               \
     {                                                                                                                  \

@@ -465,7 +465,7 @@ cudaError_t mmh_launch_march_stage(const StageParams &p, int R, int grid, int bl
 
 cudaError_t mmh_launch_chain(const FwdParams &p, cudaStream_t st) {
     const int S_ = p.d.shape[p.d.D - 1];
-    if (p.batch >= 256 && S_ >= 4 && S_ <= 8192 && !getenv("MMH_NO_CHAIN_ROWS")) {   // batches: staged chunks, coalesced stores
+    if (p.batch >= 256 && S_ >= 4 && S_ <= 8192 && !mmh_getenv("MMH_NO_CHAIN_ROWS")) {   // batches: staged chunks, coalesced stores
         const int T = 128;
         const size_t smem_ = sizeof(double2) * (size_t)S_ + sizeof(c128) * (size_t)2 * T * (MMH_CHAIN_CH + 1);
         if (smem_ > 48 * 1024) cudaFuncSetAttribute(k_fwd_chain_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);

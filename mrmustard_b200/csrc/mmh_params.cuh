@@ -2,6 +2,12 @@
 #pragma once
 #include "mmh_common.cuh"
 
+// Tuning / test hooks are environment variables named MMH_*.  The entry points take ONE snapshot of them per API call
+// (mmh_env_refresh, a single pass over `environ`) and every later lookup reads the snapshot: ~40 getenv() scans per single-lattice
+// call were 6-12 us of host time in front of the first kernel launch.
+void mmh_env_refresh();
+const char *mmh_getenv(const char *name);
+
 struct FwdParams {
     LatticeDesc d;
     const c128 *A;      // [batch, D, D]

@@ -392,7 +392,7 @@ cudaError_t mmh_launch_vjp_planes(const VjpParams &p_in, int sm_count, int *nblk
         const double cost = per_cta * (L + 1.0);   // steps of the busiest CTA + ~1 step of prologue (three extra plane loads) per task
         if (cost < best_cost) { best_cost = cost; best_nseg = nseg; }
     }
-    if (const char *e = getenv("MMH_VJP_NSEG")) best_nseg = atoi(e) > 0 ? atoi(e) : best_nseg;
+    if (const char *e = mmh_getenv("MMH_VJP_NSEG")) best_nseg = atoi(e) > 0 ? atoi(e) : best_nseg;
     const int ntask = S0 * best_nseg, grid = ntask < sm_count ? ntask : sm_count;
     p.nblk = grid;
     *nblk_out = grid;
@@ -412,7 +412,7 @@ cudaError_t mmh_launch_vjp_planes(const VjpParams &p_in, int sm_count, int *nblk
         const double waste = (double)np * t / PL;
         if (waste < best_waste - 1e-9 || (waste < best_waste + 1e-9 && t > T)) { best_waste = waste; T = t; }
     }
-    if (const char *e = getenv("MMH_VJP_T")) T = atoi(e);
+    if (const char *e = mmh_getenv("MMH_VJP_T")) T = atoi(e);
     k_vjp_planes<<<dim3(grid, (unsigned)p.batch), T, smem, st>>>(p, best_nseg);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -523,11 +523,11 @@ __global__ void __launch_bounds__(128) k_vjp_lanes(VjpParams p, int ln, int Lw) 
 cudaError_t mmh_launch_vjp_lanes(const VjpParams &p, int R, int ln, int Lw, int sm_count, cudaStream_t st) {
     int block = 128;   // 2 warps per CTA when the batch leaves less than ~8 CTAs per SM (see mmh_launch_march_lanes)
     if ((p.batch + 4LL * Lw - 1) / (4LL * Lw) < 8LL * sm_count) block = 64;
-    if (const char *e = getenv("MMH_LANES_BLOCK")) block = atoi(e) == 64 ? 64 : (atoi(e) == 32 ? 32 : 128);
+    if (const char *e = mmh_getenv("MMH_LANES_BLOCK")) block = atoi(e) == 64 ? 64 : (atoi(e) == 32 ? 32 : 128);
     const int nw = block / 32;
     const long long grid = (p.batch + (long long)nw * Lw - 1) / ((long long)nw * Lw);
     if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-    const bool pdl = !getenv("MMH_NO_PDL");
+    const bool pdl = !mmh_getenv("MMH_NO_PDL");
     const dim3 g((unsigned)grid), b(block);
     switch (R) {
         case 2: return mmh_launch_ex(k_vjp_lanes<2>, g, b, 0, st, pdl, p, ln, Lw);

@@ -4,16 +4,20 @@
 // s = 1 .. shape[i]-1, halo faces travel through the sentinel-validated exchange buffer X), but a different division of labour
 // inside the CTA.  k_march_tiled2 gives every thread R = 2 scattered cells and lets the 16 compute warps also store the lattice and
 // export the faces: 255 warp-instructions per warp-step for 100 FP64 ones, every warp in the same phase of the step.  Here:
-//   * COMPUTE warps: a lane owns R (3..6) CONSECUTIVE cells of a row along the last panel dim.  The neighbour k - e_i - e_last of
-//     a cell is the lane's own previous cell (a register; the first cell reads the cell before it from shared memory), the
-//     neighbours in the other panel dims are the same cells of the row one lower in that dim (unit-stride, conflict-free
-//     shared-memory loads).  Per step a compute lane only loads neighbours, runs its 2 R independent FP64 chains, stores its R
-//     cells to shared memory and arrives on an mbarrier -- no global store, no export, no address bookkeeping per cell.
-//   * STORE warps (two, alternating panels) wait for "panel s complete in shared memory", first copy the cells on the high faces
-//     to the exchange buffers of the upper neighbour boxes (the neighbours' critical path), then drain the whole box to the lattice
-//     in cell order: every STG.128 covers whole row segments (coalesced), and all of it overlaps the compute warps' step s+1.
-//   * IMPORT warps (two, alternating panels) poll the exchange buffer for the low halo faces of the next panels, put them into the
-//     halo rows of the panel buffer and arrive on that buffer's halo mbarrier; the sentinel is written back (self-cleaning).
+//   * COMPUTE warps: a lane owns R (2..6, R = 2 by default) CONSECUTIVE cells of a row along the last panel dim.  The neighbour
+//     k - e_i - e_last of a cell is the lane's own previous cell (a register; the first cell reads the cell before it from shared
+//     memory), the neighbours in the other panel dims are the same cells of the row one lower in that dim (unit-stride,
+//     conflict-free LDS.128: cell r of chunk ch sits at r * C + ch of its row).  Per step a compute lane loads its neighbours, runs
+//     its 2 R independent FP64 chains, pushes the cells it owns on a high face of the box to the upper neighbour's exchange rows
+//     (strong stores straight after the quotient: the neighbours' critical path), stores its R cells to shared memory and arrives
+//     on an mbarrier -- no lattice store, no address bookkeeping per cell.
+//   * SERVICE warps (four, one per panel buffer, panels s = w mod 4): poll the exchange buffer for the low halo faces of panel s,
+//     put them into the halo rows of the buffer and arrive on its halo mbarrier; wait for "panel s complete in shared memory";
+//     drain the box to the lattice in cell order through a per-cell table (every STG.128 covers whole row segments, streaming
+//     stores unless a later stage polls the lattice); hand the buffer back (drained mbarrier); write the sentinel back into the
+//     consumed exchange rows (self-cleaning).  All of it overlaps the compute warps' next steps.
+//   Hand-offs: three mbarrier families per buffer (own cells stored: count = compute threads; halo imported; drained) and a named
+//   barrier "panel read" (compute arrive, service sync) before a buffer's halo cells are overwritten four panels later.
 // Why no cp.async.bulk (TMA) for the drain: UBLKCP is a warp-uniform instruction; a box row is 80-160 contiguous bytes, so a box
 // needs ~100 copies per step, each costing more issue slots (uniform address arithmetic or a per-lane R2UR loop, measured in the
 // first version of this file: step 1.25 us) than the 2.5 instructions per row of the coalesced LDS.128 + STG.128 drain.

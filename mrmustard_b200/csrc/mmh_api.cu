@@ -639,7 +639,7 @@ static int forward_single_staged(const FwdParams &p, DeviceCtx *ctx, cudaStream_
             if (grid > 8LL * ctx->sm_count) grid = 8LL * ctx->sm_count;
             for (int s = 1; s < d.shape[i]; s++) {
                 g_launches++;
-                CK(mmh_launch_panel_step(p, i, s, 0, P, (int)grid, absmem, st));
+                CK(mmh_launch_panel_step(p, i, s, 0, P, (int)grid, absmem, st, true));   // consecutive steps of one lattice: chained with PDL
             }
             first = false;
         }
@@ -1215,8 +1215,9 @@ int mmh_forward_panel_range(int ndim, const int64_t *shape, const void *dA, cons
     long long grid = (f_hi - f_lo + 255) / 256;
     if (grid > 8LL * ctx->sm_count) grid = 8LL * ctx->sm_count;
     g_launches++;
+    // plain launch: the caller orders panel ranges with events across streams / ranks (sharding.SingleLatticePlan, also under graph capture)
     CK(mmh_launch_panel_step(p, stage, (int)step, f_lo, f_hi, (int)grid, sizeof(c128) * (size_t)(ndim * ndim + ndim),
-                             (cudaStream_t)stream));
+                             (cudaStream_t)stream, false));
     return MMH_OK;
 }
 

@@ -349,6 +349,11 @@ __global__ void __launch_bounds__(256) k_panel_step_walk(FwdParams p, int stage,
 #pragma unroll
         for (int jj = 0; jj < NPD; jj++) { k[jj] = (int)(rem / st[jj]); rem -= (unsigned)k[jj] * st[jj]; }
     }
+    // Launched with programmatic stream serialization (mid-size panels are one launch per step, launch-latency bound): everything
+    // above -- A, b (caller inputs, never written), the tables, the index decode -- overlaps the previous step's kernel; the lattice
+    // is only touched behind this wait, which returns once that kernel has completed and flushed.  Without the attribute: no-ops.
+    pdl_trigger();
+    pdl_wait();
     for (; f < f_hi; f += stride) {
         // all loads of the point first, unconditionally (an absent neighbour re-reads the pivot and is not used): with a branch
         // around each of them they issue one L2/DRAM latency after the other, and this kernel is latency bound
@@ -379,7 +384,7 @@ __global__ void __launch_bounds__(256) k_panel_step_walk(FwdParams p, int stage,
 }
 
 cudaError_t mmh_launch_panel_step(const FwdParams &p, int stage, int s, long long f_lo, long long f_hi, int grid,
-                                  size_t smem, cudaStream_t st) {
+                                  size_t smem, cudaStream_t st, bool pdl) {
     const int npd = p.d.D - 1 - stage;
     if (p.d.N < 0x7fffffffLL && npd >= 1 && npd <= 8) {
         // a grid-stride sweep wants exactly one resident wave: 8 CTAs per SM were asked for, 6 fit (40 registers), and the
@@ -408,7 +413,7 @@ cudaError_t mmh_launch_panel_step(const FwdParams &p, int stage, int s, long lon
             else w.dig[0] = (int)(sd < (1 << 30) ? sd : (1 << 30));
         }
         switch (npd) {
-#define MMH_CASE(N) case N: k_panel_step_walk<N><<<grid, 256, smem, st>>>(p, stage, s, (unsigned)f_lo, (unsigned)f_hi, w); break;
+#define MMH_CASE(N) case N: return mmh_launch_ex(k_panel_step_walk<N>, dim3(grid), dim3(256), smem, st, pdl && !mmh_getenv("MMH_NO_PDL"), p, stage, s, (unsigned)f_lo, (unsigned)f_hi, w);
             MMH_CASE(1) MMH_CASE(2) MMH_CASE(3) MMH_CASE(4) MMH_CASE(5) MMH_CASE(6) MMH_CASE(7) MMH_CASE(8)
 #undef MMH_CASE
         }

@@ -148,7 +148,7 @@ cudaError_t mmh_launch_fwd_cta(const FwdParams &p, bool stable, int grid, int bl
 cudaError_t mmh_coop_max_blocks(bool stable, int block, size_t smem, int *per_sm);
 cudaError_t mmh_launch_fwd_coop(const FwdParams &p, bool stable, int grid, int block, size_t smem, cudaStream_t st);
 cudaError_t mmh_launch_panel_step(const FwdParams &p, int stage, int s, long long f_lo, long long f_hi, int grid,
-                                  size_t smem, cudaStream_t st);
+                                  size_t smem, cudaStream_t st, bool pdl);
 cudaError_t mmh_launch_binomial(const BinomParams &p, int block, size_t smem, cudaStream_t st);
 cudaError_t mmh_launch_vjp(const VjpParams &p, int grid_y, int block, cudaStream_t st);
 size_t mmh_vjp_planes_smem(const LatticeDesc &d);

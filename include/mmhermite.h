@@ -248,6 +248,9 @@ int mmh_debug_timeline(unsigned long long *out64);
 /* debug aid, host only (no device needed): the launch plans of the batched kernels, for the CPU tests of the planners.
  * what = 0: lane layout of a lattice row of n1 = shape[ndim-1] positions (mmh_lanes.cu)  -> out = {R, ln, Lw}
  * what = 1: box grid of stage `stage` (mmh_box.cu)                                       -> out = {g0, g1, g2, threads, nt, ls}
+ * what = 2: single-lattice march of stage `stage` planned for 148 SMs (mmh_rows.cu / mmh_tiled.cu)
+ *           -> out = {1 = row-lane march | 0 = tiled march, g0, g1, g2, R * 1000 + C | R, row stride | compute threads}
+ * what = 3: stable-rule box wavefront (mmh_stable_boxes.cu) -> out = {box edge, boxes per dim (four, right-aligned), -}
  * returns MMH_ERR_UNSUPPORTED when the kernel does not take the shape (the caller then uses another kernel).          */
 int mmh_debug_plan(int what, int ndim, const int64_t *shape, int stage, int *out6);
 

@@ -1437,6 +1437,26 @@ extern "C" int mmh_debug_plan(int what, int ndim, const int64_t *shape, int stag
         out6[0] = bp.g[0]; out6[1] = bp.g[1]; out6[2] = bp.g[2]; out6[3] = T; out6[4] = bp.nt; out6[5] = bp.ls;
         return MMH_OK;
     }
+    if (what == 2) {   // single-lattice march of stage `stage` on 148 SMs: which kernel, which grid
+        if (stage < 0 || stage > ndim - 2) return MMH_ERR_BAD_SHAPE;
+        TiledParams tp;
+        int R = 0, ntiles = 0;
+        size_t smem = 0;
+        if (!plan_march_tiled(d, stage, 148, &tp, &R, &ntiles, &smem)) return MMH_ERR_UNSUPPORTED;
+        out6[0] = tp.rows_R ? 1 : 0;                         // 1: k_march_rows, 0: k_march_tiled2
+        out6[1] = tp.g[0]; out6[2] = tp.g[1]; out6[3] = tp.g[2];
+        out6[4] = tp.rows_R ? tp.rows_R * 1000 + tp.rows_C : R;
+        out6[5] = tp.rows_R ? tp.rs : tp.tc;
+        return MMH_OK;
+    }
+    if (what == 3) {   // stable box wavefront: box edge and boxes per dim (right-aligned in four dims)
+        const int E = mmh_stable_boxes_edge(ndim);
+        if (!E) return MMH_ERR_UNSUPPORTED;
+        out6[0] = E;
+        for (int j = 0; j < 4; j++) out6[1 + j] = j < 4 - ndim ? 1 : (d.shape[j - (4 - ndim)] + E - 1) / E;
+        out6[5] = (int)mmh_stable_boxes_smem(ndim, mx + 1, 1, 1);
+        return MMH_OK;
+    }
     return MMH_ERR_UNSUPPORTED;
 }
 

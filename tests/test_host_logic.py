@@ -117,3 +117,43 @@ def test_box_plan_limits():
     assert _plan(1, (4, 2000, 2000), 1)[0] == 0             # stage 1: a 1-D panel of 2000 points, two boxes
     assert _plan(1, (4, 2000, 2000), 1)[1][:3] == [2, 1, 1]
     assert _plan(1, (4, 3, 2000), 5)[0] != 0                # bad stage
+
+
+# ---- single-lattice planners of round 2 (mmh_rows.cu, mmh_stable_boxes.cu), host only ---------------------------------------
+def test_row_lane_plan_for_cfg2_and_thresholds():
+    # cfg2 stage 0: 125 boxes of 10x10x10 on the row-lane march, two cells per lane, five lanes per row, conflict-free row stride
+    rc, (rows, g0, g1, g2, rc_, rs) = _plan(2, (50, 50, 50, 50), 0)
+    assert rc == 0 and rows == 1 and (g0, g1, g2) == (5, 5, 5)
+    R, C = divmod(rc_, 1000)
+    assert (R, C) == (2, 5) and rs >= R * C and rs % 8 == C % 8
+    # stage 1 (a 50 x 50 panel) and lattices with boxes below 700 cells stay on the tiled march
+    assert _plan(2, (50, 50, 50, 50), 1)[1][0] == 0
+    assert _plan(2, (40, 40, 40, 40), 0)[1][0] == 0
+    # a panel beyond 148 x 1024 cells has no box plan at all (per-step launches)
+    assert _plan(2, (56, 56, 56, 56), 0)[0] != 0
+
+
+@pytest.mark.parametrize("shape", [(8, 45, 45, 45), (3, 50, 49, 48), (20, 47, 49, 51), (6, 44, 52, 50), (5, 53, 46, 47)])
+def test_row_lane_plan_invariants(shape):
+    rc, (rows, g0, g1, g2, rc_, rs) = _plan(2, shape, 0)
+    assert rc == 0
+    if not rows:
+        return
+    R, C = divmod(rc_, 1000)
+    e = [-(-shape[1 + m] // g) for m, g in enumerate((g0, g1, g2))]
+    assert g0 * g1 * g2 <= 148 and e[0] * e[1] * e[2] >= 700
+    assert C * R >= e[2] > (C - 1) * R                      # the chunks of a row cover it without an idle chunk
+    assert e[0] * e[1] * C <= 512                           # compute lanes of one CTA
+    assert rs >= R * C and rs % 8 == C % 8                  # row stride continues the bank groups from row to row
+
+
+@pytest.mark.parametrize("shape", [(50, 50, 50, 50), (100, 100, 100), (1000, 1000), (7, 6, 9, 8), (62, 63)])
+def test_stable_box_plan(shape):
+    D = len(shape)
+    rc, (E, n0, n1, n2, n3, smem) = _plan(3, shape)
+    assert rc == 0 and E == {4: 6, 3: 14, 2: 62}[D]
+    nb = [n0, n1, n2, n3]
+    assert nb[:4 - D] == [1] * (4 - D)
+    assert all(nb[4 - D + j] == -(-shape[j] // E) for j in range(D))
+    assert (E + 2) ** D == 4096 and smem < 200 * 1024       # the extended box (two-deep lower halo) is 4096 cells = 64 KB
+    assert _plan(3, (5,) * 5)[0] != 0                        # five indices: level wavefront
